@@ -1,0 +1,453 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a).
+//
+// One kernel serves every forward convolution and every data-gradient convolution on the
+// MaskCycleGAN-VC path (reference: mask_cyclegan_vc/model.py:116-211 Generator layers,
+// :290-334 Discriminator layers; their autograd dgrads).  The conv is never lowered to an explicit
+// im2col matrix: for every filter tap the A operand is a shifted 128-position x 64-channel box of
+// the NHWC activation, fetched by TMA (out-of-bounds = zero padding), the B operand is the tap's
+// [N][64] weight slice, and tcgen05.mma accumulates all taps x channel blocks into TMEM.
+//
+// Warp roles (256 threads, persistent over output tiles):
+//   warp 0  lane 0 : TMA producer  (full/empty mbarrier ring)
+//   warp 1  lane 0 : MMA issuer    (tcgen05.mma, tcgen05.commit)
+//   warp 2         : TMEM allocator
+//   warps 4..7     : epilogue (tcgen05.ld -> bias/residual -> global), double-buffered in TMEM
+//
+// Precision: nPass = 3 runs the split-bf16 scheme  A*W ~= Ah*Wh + Ah*Wl + Al*Wh  (fp32 accumulate),
+// nPass = 1 runs plain bf16.
+#include "gemm_types.cuh"
+#include "ptx.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cuda_bf16.h>
+
+namespace mcgvc {
+
+// ------------------------------------------------------------------------------------------------
+// error string (C ABI surfaces it through mcgvc_last_error)
+static thread_local char g_err[512] = "";
+const char* last_error() { return g_err; }
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 tensor [B][P][Y][X][C] -> rank-5 map, box (64, BX, BY, 1, BB), 128B swizzle, zero OOB fill.
+bool make_act_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int BX, int BY, int BB) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.X, (cuuint64_t)a.Y, (cuuint64_t)a.P,
+                        (cuuint64_t)a.B};
+  cuuint64_t strides[4];
+  strides[0] = (cuuint64_t)a.C * 2;
+  strides[1] = strides[0] * a.X;
+  strides[2] = strides[1] * a.Y;
+  strides[3] = strides[2] * a.P;
+  cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)BX, (cuuint32_t)BY, 1u, (cuuint32_t)BB};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(act C=%d X=%d Y=%d P=%d B=%d box %d,%d,%d) failed: %d", a.C,
+              a.X, a.Y, a.P, a.B, BX, BY, BB, (int)r);
+    return false;
+  }
+  return true;
+}
+// bf16 weights [T][N][K] -> rank-3 map, box (64, boxN, 1).
+bool make_wgt_tmap(CUtensorMap* m, const void* base, const WgtOperand& w, int boxN) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)w.K, (cuuint64_t)w.N, (cuuint64_t)w.T};
+  cuuint64_t strides[2] = {(cuuint64_t)w.K * 2, (cuuint64_t)w.K * 2 * w.N};
+  cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)boxN, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(wgt K=%d N=%d T=%d boxN=%d) failed: %d", w.K, w.N, w.T, boxN,
+              (int)r);
+    return false;
+  }
+  return true;
+}
+
+bool choose_box(int B, int Y, int X, int boxPositions, int* oBX, int* oBY, int* oBB) {
+  long long best = -1;
+  int bx = 0, by = 0, bb = 0;
+  for (int BX = 1; BX <= boxPositions && BX <= 256; BX *= 2) {
+    for (int BY = 1; BX * BY <= boxPositions; BY *= 2) {
+      int BB = boxPositions / (BX * BY);
+      if (BX * BY * BB != boxPositions || BB > 256) continue;
+      long long tiles = (long long)((X + BX - 1) / BX) * ((Y + BY - 1) / BY) * ((B + BB - 1) / BB);
+      // fewer tiles first; tie -> widest X box (longest contiguous runs), then tallest Y box
+      long long score = tiles * 1000000LL - BX * 1000LL - BY;
+      if (best < 0 || score < best) {
+        best = score;
+        bx = BX; by = BY; bb = BB;
+      }
+    }
+  }
+  if (best < 0) return false;
+  *oBX = bx; *oBY = by; *oBB = bb;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int NPASS>
+struct ConvCfg {
+  static constexpr int kABytes = kTileM * kBlockK * 2;    // 16 KB
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = (kABytes + kBBytes) * (NPASS == 3 ? 2 : 1);
+  static constexpr int kBudget = 222 * 1024;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BLOCK_N;           // two accumulator buffers
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kStages >= 2, "need at least two pipeline stages");
+  static_assert(kTmemCols >= 32 && kTmemCols <= 512, "TMEM columns");
+};
+
+template <int BLOCK_N, int NPASS>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+               const __grid_constant__ ConvGeom g) {
+  using Cfg = ConvCfg<BLOCK_N, NPASS>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmAh);
+    ptx::prefetch_tmap(&tmWh);
+    if (NPASS == 3) {
+      ptx::prefetch_tmap(&tmAl);
+      ptx::prefetch_tmap(&tmWl);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nTiles = g.w.N / BLOCK_N;
+  const int mTiles = g.tilesX * g.tilesY * g.tilesB;
+  const int totalTiles = nTiles * mTiles;
+  const int numK = g.nTaps * g.cBlocks;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+      const int nt = tile % nTiles;
+      int mt = tile / nTiles;
+      const int tx = mt % g.tilesX;
+      mt /= g.tilesX;
+      const int ty = mt % g.tilesY;
+      const int tb = mt / g.tilesY;
+      const int x0 = tx * g.BX, y0 = ty * g.BY, b0 = tb * g.BB, n0 = nt * BLOCK_N;
+      for (int t = 0; t < g.nTaps; ++t) {
+        const Tap tap = g.taps[t];
+        for (int cb = 0; cb < g.cBlocks; ++cb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          ptx::mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          ptx::tma_load_5d(st, &tmAh, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
+                           tap.plane, b0);
+          ptx::tma_load_3d(st + Cfg::kABytes, &tmWh, &full[stage], cb * kBlockK, n0, tap.w);
+          if (NPASS == 3) {
+            uint8_t* lo = st + Cfg::kABytes + Cfg::kBBytes;
+            ptx::tma_load_5d(lo, &tmAl, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
+                             tap.plane, b0);
+            ptx::tma_load_3d(lo + Cfg::kABytes, &tmWl, &full[stage], cb * kBlockK, n0, tap.w);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ptx::mbar_wait(&tempty[acc], aphase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < numK; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sA = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sB = sA + Cfg::kABytes;
+        const uint32_t sAl = sB + Cfg::kBBytes;
+        const uint32_t sBl = sAl + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t dAh = ptx::umma_smem_desc_sw128(sA + k * 32, 0, 1024);
+          const uint64_t dBh = ptx::umma_smem_desc_sw128(sB + k * 32, 0, 1024);
+          ptx::umma_bf16(d_tmem, dAh, dBh, idesc, (kb | k) != 0);
+          if (NPASS == 3) {
+            const uint64_t dAl = ptx::umma_smem_desc_sw128(sAl + k * 32, 0, 1024);
+            const uint64_t dBl = ptx::umma_smem_desc_sw128(sBl + k * 32, 0, 1024);
+            ptx::umma_bf16(d_tmem, dAh, dBl, idesc, 1);
+            ptx::umma_bf16(d_tmem, dAl, dBh, idesc, 1);
+          }
+        }
+        ptx::umma_commit(&empty[stage]);
+        if (kb == numK - 1) ptx::umma_commit(&tfull[acc]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int nt = tile % nTiles;
+      int mt = tile / nTiles;
+      const int tx = mt % g.tilesX;
+      mt /= g.tilesX;
+      const int ty = mt % g.tilesY;
+      const int tb = mt / g.tilesY;
+      const int n0 = nt * BLOCK_N;
+      const int bx = row % g.BX;
+      const int by = (row / g.BX) % g.BY;
+      const int bb = row / (g.BX * g.BY);
+      const int x = tx * g.BX + bx, y = ty * g.BY + by, b = tb * g.BB + bb;
+      const bool valid = (x < g.oX) && (y < g.oY) && (b < g.oB);
+      const long long off = (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
+                            (long long)(n0 / g.nSplit) * g.sNhi + (n0 % g.nSplit);
+      float* orow = g.out + off;
+      const float* arow = g.addsrc ? g.addsrc + off : nullptr;
+
+      ptx::mbar_wait(&tfull[acc], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int j = 0; j < BLOCK_N / 32; ++j) {
+        uint32_t v[32];
+        ptx::tmem_ld32(taddr + j * 32, v);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[i + 0]);
+            o.y = __uint_as_float(v[i + 1]);
+            o.z = __uint_as_float(v[i + 2]);
+            o.w = __uint_as_float(v[i + 3]);
+            if (g.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j * 32 + i));
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            }
+            if (arow) {
+              const float4 av = *reinterpret_cast<const float4*>(arow + j * 32 + i);
+              o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w;
+            }
+            *reinterpret_cast<float4*>(orow + j * 32 + i) = o;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static bool check_conv_geom(const ConvGeom& g, int blockN) {
+  if (g.BX * g.BY * g.BB != kTileM) { set_error("conv: box %dx%dx%d != 128", g.BX, g.BY, g.BB); return false; }
+  if (g.w.N % blockN) { set_error("conv: N=%d not a multiple of %d", g.w.N, blockN); return false; }
+  if (g.a.C % kBlockK || g.a.C != g.w.K) { set_error("conv: C=%d K=%d must match and be multiples of 64", g.a.C, g.w.K); return false; }
+  if (g.nSplit % blockN) { set_error("conv: nSplit=%d not a multiple of %d", g.nSplit, blockN); return false; }
+  if (g.nTaps < 1 || g.nTaps > kMaxTaps) { set_error("conv: nTaps=%d", g.nTaps); return false; }
+  if (g.cBlocks != g.a.C / kBlockK) { set_error("conv: cBlocks"); return false; }
+  if (g.nPass != 1 && g.nPass != 3) { set_error("conv: nPass=%d", g.nPass); return false; }
+  return true;
+}
+
+template <int BLOCK_N, int NPASS>
+static cudaError_t launch_conv_tc_t(const ConvGeom& g, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N, NPASS>;
+  if (!check_conv_geom(g, BLOCK_N)) return cudaErrorInvalidValue;
+  CUtensorMap tmAh, tmAl, tmWh, tmWl;
+  if (!make_act_tmap(&tmAh, g.a.hi, g.a, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_wgt_tmap(&tmWh, g.w.hi, g.w, BLOCK_N)) return cudaErrorInvalidValue;
+  if (NPASS == 3) {
+    if (!make_act_tmap(&tmAl, g.a.lo, g.a, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+    if (!make_wgt_tmap(&tmWl, g.w.lo, g.w, BLOCK_N)) return cudaErrorInvalidValue;
+  } else {
+    tmAl = tmAh;
+    tmWl = tmWh;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, NPASS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("conv: smem attr: %s", cudaGetErrorString(e)); return e; }
+    attr_set = true;
+  }
+  const int total = (g.w.N / BLOCK_N) * g.tilesX * g.tilesY * g.tilesB;
+  const int grid = total < num_sms() ? total : num_sms();
+  conv_tc_kernel<BLOCK_N, NPASS><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
+  return cudaGetLastError();
+}
+
+// BLOCK_N selection: widest tile that divides N and nSplit (256 halves B-operand smem traffic per
+// MMA; 64 exists for the narrow data-gradient outputs of the two stem layers).
+static int g_force_block_n = 0;
+void set_force_block_n(int n) { g_force_block_n = n; }
+
+cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream) {
+  int bn = 64;
+  if (g.w.N % 128 == 0 && g.nSplit % 128 == 0) bn = 128;
+  if (g_force_block_n == 256 && g.w.N % 256 == 0 && g.nSplit % 256 == 0) bn = 256;
+  if (g_force_block_n == 64) bn = 64;
+  if (g.nPass == 3) {
+    if (bn == 256) return launch_conv_tc_t<256, 3>(g, stream);
+    if (bn == 128) return launch_conv_tc_t<128, 3>(g, stream);
+    return launch_conv_tc_t<64, 3>(g, stream);
+  }
+  if (bn == 256) return launch_conv_tc_t<256, 1>(g, stream);
+  if (bn == 128) return launch_conv_tc_t<128, 1>(g, stream);
+  return launch_conv_tc_t<64, 1>(g, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT checking kernel: same operands, same tap table, one thread per output element.  It exists so
+// the tcgen05 kernel can be validated against something that shares no descriptor/swizzle logic
+// with it; it is not used by the network path unless MCGVC_BACKEND=simt is set for debugging.
+__device__ __forceinline__ float bf16_bits_to_f(uint16_t v) {
+  return __uint_as_float(static_cast<uint32_t>(v) << 16);
+}
+
+__global__ void conv_simt_kernel(const __grid_constant__ ConvGeom g) {
+  const long long total = (long long)g.tilesX * g.tilesY * g.tilesB * kTileM * g.w.N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx % g.w.N);
+  long long r = idx / g.w.N;
+  const int row = (int)(r % kTileM);
+  int mt = (int)(r / kTileM);
+  const int tx = mt % g.tilesX;
+  mt /= g.tilesX;
+  const int ty = mt % g.tilesY;
+  const int tb = mt / g.tilesY;
+  const int bx = row % g.BX, by = (row / g.BX) % g.BY, bb = row / (g.BX * g.BY);
+  const int x = tx * g.BX + bx, y = ty * g.BY + by, b = tb * g.BB + bb;
+  if (x >= g.oX || y >= g.oY || b >= g.oB) return;
+  const uint16_t* Ah = reinterpret_cast<const uint16_t*>(g.a.hi);
+  const uint16_t* Al = reinterpret_cast<const uint16_t*>(g.a.lo);
+  const uint16_t* Wh = reinterpret_cast<const uint16_t*>(g.w.hi);
+  const uint16_t* Wl = reinterpret_cast<const uint16_t*>(g.w.lo);
+  float acc = 0.f;
+  for (int t = 0; t < g.nTaps; ++t) {
+    const Tap tap = g.taps[t];
+    const int xx = x + tap.dx, yy = y + tap.dy;
+    if (xx < 0 || xx >= g.a.X || yy < 0 || yy >= g.a.Y) continue;
+    const long long aoff = ((((long long)b * g.a.P + tap.plane) * g.a.Y + yy) * g.a.X + xx) * g.a.C;
+    const long long woff = ((long long)tap.w * g.w.N + n) * g.w.K;
+    for (int c = 0; c < g.a.C; ++c) {
+      const float ah = bf16_bits_to_f(Ah[aoff + c]);
+      const float wh = bf16_bits_to_f(Wh[woff + c]);
+      acc = fmaf(ah, wh, acc);
+      if (g.nPass == 3) {
+        const float al = bf16_bits_to_f(Al[aoff + c]);
+        const float wl = bf16_bits_to_f(Wl[woff + c]);
+        acc = fmaf(ah, wl, acc);
+        acc = fmaf(al, wh, acc);
+      }
+    }
+  }
+  const long long off = (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
+                        (long long)(n / g.nSplit) * g.sNhi + (n % g.nSplit);
+  if (g.bias) acc += g.bias[n];
+  if (g.addsrc) acc += g.addsrc[off];
+  g.out[off] = acc;
+}
+
+cudaError_t launch_conv_simt(const ConvGeom& g, cudaStream_t stream) {
+  if (!check_conv_geom(g, 64)) return cudaErrorInvalidValue;
+  const long long total = (long long)g.tilesX * g.tilesY * g.tilesB * kTileM * g.w.N;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  conv_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace mcgvc

@@ -1,0 +1,84 @@
+// Kernel-level C entry points used by tests/ to check the tensor-core kernels in isolation
+// (tcgen05 path against the SIMT checking kernels and against torch on the same operands).
+#include "../../include/mcgvc.h"
+#include "gemm_types.cuh"
+
+using namespace mcgvc;
+
+namespace mcgvc { void set_force_block_n(int n); }
+
+extern "C" {
+
+int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY, int aP, int aB,
+                     const void* w_hi, const void* w_lo, int wK, int wN, int wT, int oX, int oY,
+                     int oB, int nTaps, const int8_t* taps4, float* out, long long sB,
+                     long long sY, long long sX, int nSplit, long long sNhi, const float* bias,
+                     const float* addsrc, int nPass, int backend, int blockN, void* stream) {
+  ConvGeom g{};
+  g.a = ActOperand{a_hi, a_lo, aC, aX, aY, aP, aB};
+  g.w = WgtOperand{w_hi, w_lo, wK, wN, wT};
+  g.oX = oX; g.oY = oY; g.oB = oB;
+  if (!choose_box(oB, oY, oX, kTileM, &g.BX, &g.BY, &g.BB)) { set_error("choose_box failed"); return 1; }
+  g.tilesX = (oX + g.BX - 1) / g.BX;
+  g.tilesY = (oY + g.BY - 1) / g.BY;
+  g.tilesB = (oB + g.BB - 1) / g.BB;
+  if (nTaps > kMaxTaps) { set_error("too many taps"); return 1; }
+  g.nTaps = nTaps;
+  g.cBlocks = aC / kBlockK;
+  for (int t = 0; t < nTaps; ++t) {
+    g.taps[t].dx = taps4[4 * t + 0];
+    g.taps[t].dy = taps4[4 * t + 1];
+    g.taps[t].plane = (uint8_t)taps4[4 * t + 2];
+    g.taps[t].w = (uint8_t)taps4[4 * t + 3];
+  }
+  g.sB = sB; g.sY = sY; g.sX = sX; g.nSplit = nSplit; g.sNhi = sNhi;
+  g.out = out; g.bias = bias; g.addsrc = addsrc; g.nPass = nPass;
+  set_force_block_n(blockN);
+  cudaError_t e = backend == 0 ? launch_conv_tc(g, (cudaStream_t)stream)
+                               : launch_conv_simt(g, (cudaStream_t)stream);
+  set_force_block_n(0);
+  if (e != cudaSuccess) {
+    if (!last_error()[0]) set_error("conv launch: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int mcgvc_debug_wgrad(const void* z_hi, const void* z_lo, int zC, int zX, int zY, int zB,
+                      const void* x_hi, const void* x_lo, int xC, int xX, int xY, int xP, int xB,
+                      int pX, int pY, int pB, int nTaps, const int8_t* taps4,
+                      const int8_t* ztaps4, float* dw, int cTile, int splitK, int nPass,
+                      int backend, void* stream) {
+  WgradGeom g{};
+  g.dz = ActOperand{z_hi, z_lo, zC, zX, zY, 1, zB};
+  g.x = ActOperand{x_hi, x_lo, xC, xX, xY, xP, xB};
+  g.pX = pX; g.pY = pY; g.pB = pB;
+  if (!choose_box(pB, pY, pX, 64, &g.BX, &g.BY, &g.BB)) { set_error("choose_box failed"); return 1; }
+  g.tilesX = (pX + g.BX - 1) / g.BX;
+  g.tilesY = (pY + g.BY - 1) / g.BY;
+  g.tilesB = (pB + g.BB - 1) / g.BB;
+  if (nTaps > kMaxTaps) { set_error("too many taps"); return 1; }
+  g.nTaps = nTaps;
+  for (int t = 0; t < nTaps; ++t) {
+    g.taps[t].dx = taps4[4 * t + 0];
+    g.taps[t].dy = taps4[4 * t + 1];
+    g.taps[t].plane = (uint8_t)taps4[4 * t + 2];
+    g.taps[t].w = (uint8_t)taps4[4 * t + 3];
+    g.ztaps[t].dx = ztaps4[4 * t + 0];
+    g.ztaps[t].dy = ztaps4[4 * t + 1];
+    g.ztaps[t].plane = 0;
+    g.ztaps[t].w = 0;
+  }
+  g.N = zC; g.C = xC; g.cTile = cTile; g.splitK = splitK; g.dw = dw; g.nPass = nPass;
+  cudaError_t e = backend == 0 ? launch_wgrad_tc(g, (cudaStream_t)stream)
+                               : launch_wgrad_simt(g, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    if (!last_error()[0]) set_error("wgrad launch: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+const char* mcgvc_last_error(void) { return last_error(); }
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Shared descriptions of the two tensor-core kernels (implicit-GEMM conv and weight-gradient GEMM).
+// The same structs drive the tcgen05/TMA kernels and the plain SIMT checking kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mcgvc {
+
+constexpr int kMaxTaps = 80;   // 5x15 head/stem = 75 taps is the largest filter on the path
+constexpr int kTileM = 128;    // output positions per tile (UMMA M)
+constexpr int kBlockK = 64;    // channels per k-block = one 128-byte swizzle row of bf16
+
+// One filter tap: where to read the activation (offset in the operand's X/Y grid and which
+// parity plane for stride-2 layers) and which weight slice it multiplies.
+struct Tap {
+  int8_t dx, dy;
+  uint8_t plane, w;
+};
+
+// Activation operand: bf16 hi/lo planes laid out [B][P][Y][X][C] (C contiguous).
+struct ActOperand {
+  const void* hi;
+  const void* lo;
+  int C, X, Y, P, B;
+};
+// Weight operand: bf16 hi/lo, [T][N][K] (K contiguous, K = channels per tap).
+struct WgtOperand {
+  const void* hi;
+  const void* lo;
+  int K, N, T;
+};
+
+// Implicit-GEMM convolution:  out[row(b,y,x), n] = bias[n] + addsrc[..] +
+//     sum_t sum_c A[b, plane_t, y+dy_t, x+dx_t, c] * W[w_t][n][c]
+// Rows are enumerated over output positions (oB, oY, oX) in boxes of BB x BY x BX = 128.
+struct ConvGeom {
+  ActOperand a;
+  WgtOperand w;
+  int oX, oY, oB;
+  int BX, BY, BB;
+  int tilesX, tilesY, tilesB;
+  int nTaps, cBlocks;
+  Tap taps[kMaxTaps];
+  // output addressing, in floats
+  long long sB, sY, sX;
+  int nSplit;          // column n lives at (n / nSplit) * sNhi + (n % nSplit)
+  long long sNhi;
+  float* out;
+  const float* bias;    // [N] or null
+  const float* addsrc;  // same addressing as out, or null
+  int nPass;            // 1 = bf16 (hi only), 3 = split-bf16 (hi*hi + hi*lo + lo*hi)
+};
+
+// Weight-gradient GEMM:  dW[w_t][n][c] += sum over positions (b,y,x) in this CTA's K-slice of
+//     dz[b, y+dyz_t, x+dxz_t, n] * x[b, plane_t, y+dy_t, x+dx_t, c]
+// Positions are enumerated over (pB, pY, pX) in boxes of BB x BY x BX = 64 (one k-block).
+struct WgradGeom {
+  ActOperand dz;   // channels = N
+  ActOperand x;    // channels = C
+  int pX, pY, pB;
+  int BX, BY, BB;
+  int tilesX, tilesY, tilesB;
+  int nTaps;
+  Tap taps[kMaxTaps];    // offsets applied to the x operand
+  Tap ztaps[kMaxTaps];   // offsets applied to the dz operand (dx, dy only)
+  int N, C;              // dW slice is [N][C] per tap
+  int cTile;             // columns of C per CTA (64, 128 or 256)
+  int splitK;
+  float* dw;             // [T][N][C] fp32, accumulated with atomics
+  int nPass;
+};
+
+cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);
+cudaError_t launch_conv_simt(const ConvGeom& g, cudaStream_t stream);
+cudaError_t launch_wgrad_tc(const WgradGeom& g, cudaStream_t stream);
+cudaError_t launch_wgrad_simt(const WgradGeom& g, cudaStream_t stream);
+
+// Fill tile counts / box shape for a position grid (B, Y, X): picks BX*BY*BB == boxPositions
+// minimising padded work. Returns false if impossible.
+bool choose_box(int B, int Y, int X, int boxPositions, int* BX, int* BY, int* BB);
+
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+}  // namespace mcgvc
