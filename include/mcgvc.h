@@ -1,5 +1,14 @@
-/* mcgvc.h -- C ABI of the B200-native MaskCycleGAN-VC conv engine (libmcgvc.so).
- * Work in progress header: kernel-level debug entry points first; network-level entry points follow. */
+/* mcgvc.h -- C ABI of libmcgvc.so, the B200-native (sm_100a) MaskCycleGAN-VC conv engine.
+ *
+ * The reference (GANtastic3/MaskCycleGAN-VC) has no FFI: its hot path is the pair of Python
+ * nn.Modules in mask_cyclegan_vc/model.py whose arithmetic PyTorch dispatches to cuDNN / oneDNN.
+ * This ABI is what a binding for that path attaches to; each entry point names the reference
+ * interface it replaces.  All pointers are raw device pointers (plain host integers for sizes); no
+ * torch types cross the boundary.  Every function returns 0 on success, non-zero on failure with
+ * a message available from mcgvc_last_error().  Nothing is allocated behind the caller's back:
+ * the caller provides the packed-weight blob, the saved-activation blob and the workspace, sized
+ * by the *_bytes queries below.  All work is enqueued on the given cudaStream_t (passed as void*).
+ */
 #ifndef MCGVC_H
 #define MCGVC_H
 #include <stddef.h>
@@ -8,14 +17,67 @@
 extern "C" {
 #endif
 
-const char* mcgvc_last_error(void);
+#define MCGVC_GENERATOR 0
+#define MCGVC_DISCRIMINATOR 1
+#define MCGVC_BACKEND_TCGEN05 0   /* tcgen05 + TMA kernels (the product path) */
+#define MCGVC_BACKEND_SIMT 1      /* plain CUDA checking kernels (tests / debugging only) */
+#define MCGVC_PRECISION_PARITY 3  /* split-bf16 x3: Ah*Wh + Ah*Wl + Al*Wh, fp32 accumulate */
+#define MCGVC_PRECISION_FAST 1    /* single bf16 pass */
 
+const char* mcgvc_last_error(void);
+int mcgvc_set_device(int device);
+int mcgvc_set_backend(int backend);
+int mcgvc_set_precision(int n_pass);
+int mcgvc_get_precision(void);
+
+/* Model geometry.  Replaces Generator.__init__ / Discriminator.__init__ bookkeeping
+ * (model.py:110-211, :287-327): number of floats in the reference-order flat parameter buffer
+ * (order of nn.Module.parameters()), and sizes of the engine-side blobs. */
+long long mcgvc_param_count(int model);
+long long mcgvc_packed_bytes(int model);
+long long mcgvc_grad_blob_floats(int model);
+long long mcgvc_saved_bytes(int model, int batch, int frames);
+long long mcgvc_fwd_workspace_bytes(int model, int batch, int frames);
+long long mcgvc_bwd_workspace_bytes(int model, int batch, int frames);
+int mcgvc_generator_out_frames(int frames); /* model.py:278-279: 4*ceil(ceil(T/2)/2) */
+int mcgvc_discriminator_out_frames(int frames); /* model.py:348: ceil(T/8) */
+
+/* Reference-layout fp32 parameters (OIHW conv weights, biases, InstanceNorm affine) -> engine
+ * layout (per-tap [N][C] bf16 hi/lo slices for the forward and data-gradient GEMMs, permuted
+ * small vectors).  Call after every optimizer step on the module's parameters. */
+int mcgvc_pack_weights(int model, const float* params_flat, void* packed, void* stream);
+/* grad_flat (reference order) += engine-layout gradient blob.  Replaces autograd's AccumulateGrad
+ * for the module's parameters (train.py:241,298). */
+int mcgvc_unpack_grads(int model, const float* grad_blob, float* grad_flat, void* stream);
+
+/* Generator.forward(x, mask), model.py:239-280.  x, mask: [B][80][T] fp32; out: [B][80][T'] fp32. */
+int mcgvc_generator_forward(const void* packed, const float* x, const float* mask, int batch,
+                            int frames, float* out, void* saved, void* workspace, void* stream);
+/* Backward of the above (autograd through model.py:239-280).  dout: [B][80][T']; dx: [B][80][T] or
+ * NULL when the input needs no gradient; grad_blob: engine-layout fp32 accumulator (+=), may be
+ * NULL when need_wgrad == 0. */
+int mcgvc_generator_backward(const void* packed, const void* saved, const float* mask,
+                             const float* dout, int batch, int frames, float* dx, float* grad_blob,
+                             int need_wgrad, void* workspace, void* stream);
+/* Discriminator.forward(x), model.py:340-349.  x: [B][80][T]; out: [B][1][10][ceil(T/8)]. */
+int mcgvc_discriminator_forward(const void* packed, const float* x, int batch, int frames,
+                                float* out, void* saved, void* workspace, void* stream);
+int mcgvc_discriminator_backward(const void* packed, const void* saved, const float* out,
+                                 const float* dout, int batch, int frames, float* dx,
+                                 float* grad_blob, int need_wgrad, void* workspace, void* stream);
+
+/* Introspection for layer-by-layer parity tests: the index-th named tensor inside the saved blob.
+ * Returns 0 and fills name/offset/bytes, or 1 when index is past the end. */
+int mcgvc_saved_layout(int model, int batch, int frames, int index, char* name, int name_cap,
+                       long long* offset, long long* bytes);
+
+/* Kernel-level entry points (tests): one implicit-GEMM convolution / one weight-gradient GEMM on
+ * caller-provided bf16 hi/lo operands, through either backend. */
 int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY, int aP, int aB,
                      const void* w_hi, const void* w_lo, int wK, int wN, int wT, int oX, int oY,
                      int oB, int nTaps, const int8_t* taps4, float* out, long long sB,
                      long long sY, long long sX, int nSplit, long long sNhi, const float* bias,
                      const float* addsrc, int nPass, int backend, int blockN, void* stream);
-
 int mcgvc_debug_wgrad(const void* z_hi, const void* z_lo, int zC, int zX, int zY, int zB,
                       const void* x_hi, const void* x_lo, int xC, int xX, int xY, int xP, int xB,
                       int pX, int pY, int pB, int nTaps, const int8_t* taps4,

@@ -1,0 +1,1081 @@
+// Host-side orchestration: model descriptions, weight packing, and the forward / backward layer
+// schedules of the Generator and Discriminator (reference mask_cyclegan_vc/model.py:239-280 and
+// :340-349; backward = what autograd derives for them, train.py:241,298).
+#include "network.cuh"
+
+#include <cstdio>
+#include <map>
+
+namespace mcgvc {
+
+// ================================================================================================
+// model descriptions
+namespace {
+
+struct ParamTable {
+  std::map<std::string, long long> off;
+  long long total = 0;
+  void add(const std::string& name, long long numel) {
+    off[name] = total;
+    total += numel;
+  }
+  void conv(const std::string& name, int n, int c, int t) {
+    add(name + ".weight", (long long)n * c * t);
+    add(name + ".bias", n);
+  }
+  void norm(const std::string& name, int n) {
+    add(name + ".weight", n);
+    add(name + ".bias", n);
+  }
+  long long at(const std::string& name) const { return off.at(name); }
+};
+
+long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+struct DescBuilder {
+  ModelDesc d;
+  const ParamTable& pt;
+  explicit DescBuilder(const ParamTable& p) : pt(p) {
+    d.packedBf16 = d.packedF32 = d.gradFloats = 0;
+    d.paramCount = p.total;
+  }
+  void conv(const std::string& name, std::vector<std::string> parts, int refN, int refC, int refT,
+            int kind, int biasKind, int Np, int Cp, int Tp, int Cd) {
+    ConvDesc c{};
+    c.name = name;
+    c.nParts = (int)parts.size();
+    for (int i = 0; i < c.nParts; ++i) {
+      c.wOff[i] = pt.at(parts[i] + ".weight");
+      c.bOff[i] = pt.at(parts[i] + ".bias");
+    }
+    c.refN = refN; c.refC = refC; c.refT = refT;
+    c.kind = kind; c.biasKind = biasKind;
+    c.Np = Np; c.Cp = Cp; c.Tp = Tp; c.Cd = Cd;
+    const long long fsz = align_up((long long)Tp * Np * Cp, 128);
+    const long long dsz = align_up((long long)Tp * Cd * Np, 128);
+    c.fHi = d.packedBf16; d.packedBf16 += fsz;
+    c.fLo = d.packedBf16; d.packedBf16 += fsz;
+    if (Cd) {
+      c.dHi = d.packedBf16; d.packedBf16 += dsz;
+      c.dLo = d.packedBf16; d.packedBf16 += dsz;
+    } else {
+      c.dHi = c.dLo = -1;
+    }
+    c.biasEng = d.packedF32; d.packedF32 += align_up(Np, 64);
+    c.gW = d.gradFloats; d.gradFloats += align_up((long long)Tp * Np * Cp, 64);
+    c.gB = d.gradFloats; d.gradFloats += align_up(Np, 64);
+    d.convs.push_back(c);
+  }
+  void norm(const std::string& name, std::vector<std::string> parts, int n, int vecKind) {
+    NormDesc m{};
+    m.name = name;
+    m.nParts = (int)parts.size();
+    for (int i = 0; i < m.nParts; ++i) {
+      m.gOff[i] = pt.at(parts[i] + ".weight");
+      m.bOff[i] = pt.at(parts[i] + ".bias");
+    }
+    m.n = n;
+    m.vecKind = vecKind;
+    m.affPeriod = vecKind == kVecHC20 ? 20 : 1;
+    m.Nstat = vecKind == kVecHC20 ? n / 20 : n * m.nParts;
+    const long long tot = align_up((long long)n * m.nParts, 64);
+    m.gammaEng = d.packedF32; d.packedF32 += tot;
+    m.betaEng = d.packedF32; d.packedF32 += tot;
+    m.gGamma = d.gradFloats; d.gradFloats += tot;
+    m.gBeta = d.gradFloats; d.gradFloats += tot;
+    d.norms.push_back(m);
+  }
+};
+
+// conv indices
+enum { G_STEM = 0, G_DS1, G_DS2, G_2DTO1D, G_RES0 /* 2 per block: a, b */, G_1DTO2D = G_RES0 + 12,
+       G_UP1, G_UP2, G_HEAD, G_NCONV };
+// norm indices
+enum { GN_DS1 = 0, GN_DS2, GN_2DTO1D, GN_RES0 /* 2 per block */, GN_1DTO2D = GN_RES0 + 12, GN_UP1,
+       GN_UP2, GN_NNORM };
+enum { D_STEM = 0, D_DS1, D_DS2, D_DS3, D_HEAD, D_NCONV };
+enum { DN_DS1 = 0, DN_DS2, DN_DS3, DN_NNORM };
+
+ModelDesc build_generator() {
+  // reference parameter order = Generator.parameters() (model.py:110-211; `convLayer` is the
+  // upSample2 Sequential registered under the attribute name written at :227, ahead of upSample1)
+  ParamTable pt;
+  pt.conv("conv1", 128, 2, 75);
+  pt.conv("conv1_gates", 128, 2, 75);
+  for (int i = 1; i <= 2; ++i) {
+    const std::string p = "downSample" + std::to_string(i);
+    const int cin = i == 1 ? 128 : 256;
+    pt.conv(p + ".convLayer.0", 256, cin, 25);
+    pt.norm(p + ".convLayer.1", 256);
+    pt.conv(p + ".convLayer_gates.0", 256, cin, 25);
+    pt.norm(p + ".convLayer_gates.1", 256);
+  }
+  pt.conv("conv2dto1dLayer", 256, 5120, 1);
+  pt.norm("conv2dto1dLayer_tfan", 256);
+  for (int i = 1; i <= 6; ++i) {
+    const std::string p = "residualLayer" + std::to_string(i);
+    pt.conv(p + ".conv1d_layer.0", 512, 256, 3);
+    pt.norm(p + ".conv1d_layer.1", 512);
+    pt.conv(p + ".conv_layer_gates.0", 512, 256, 3);
+    pt.norm(p + ".conv_layer_gates.1", 512);
+    pt.conv(p + ".conv1d_out_layer.0", 256, 512, 3);
+    pt.norm(p + ".conv1d_out_layer.1", 256);
+  }
+  pt.conv("conv1dto2dLayer", 5120, 256, 1);
+  pt.norm("conv1dto2dLayer_tfan", 5120);
+  pt.conv("convLayer.0", 512, 256, 25);   // == upSample2.0
+  pt.norm("convLayer.2", 128);            // == upSample2.2
+  pt.conv("upSample1.0", 1024, 256, 25);
+  pt.norm("upSample1.2", 256);
+  pt.conv("lastConvLayer", 1, 128, 75);
+
+  DescBuilder b(pt);
+  b.conv("stem", {"conv1", "conv1_gates"}, 128, 2, 75, kPackStemG, kVecIdent, 256, 64, 5, 64);
+  b.conv("ds1", {"downSample1.convLayer.0", "downSample1.convLayer_gates.0"}, 256, 128, 25,
+         kPackStd, kVecIdent, 512, 128, 25, 128);
+  b.conv("ds2", {"downSample2.convLayer.0", "downSample2.convLayer_gates.0"}, 256, 256, 25,
+         kPackStd, kVecIdent, 512, 256, 25, 256);
+  b.conv("2dto1d", {"conv2dto1dLayer"}, 256, 5120, 1, kPack2dTo1d, kVecIdent, 256, 256, 20, 256);
+  for (int i = 1; i <= 6; ++i) {
+    const std::string p = "residualLayer" + std::to_string(i);
+    b.conv("res" + std::to_string(i) + "a", {p + ".conv1d_layer.0", p + ".conv_layer_gates.0"}, 512,
+           256, 3, kPackStd, kVecIdent, 1024, 256, 3, 256);
+    b.conv("res" + std::to_string(i) + "b", {p + ".conv1d_out_layer.0"}, 256, 512, 3, kPackStd,
+           kVecIdent, 256, 512, 3, 512);
+  }
+  b.conv("1dto2d", {"conv1dto2dLayer"}, 5120, 256, 1, kPack1dTo2d, kVecHC20, 5120, 256, 1, 256);
+  b.conv("up1", {"upSample1.0"}, 1024, 256, 25, kPackShuffle, kVecShuffle, 1024, 256, 25, 256);
+  b.conv("up2", {"convLayer.0"}, 512, 256, 25, kPackShuffle, kVecShuffle, 512, 256, 25, 256);
+  b.conv("head", {"lastConvLayer"}, 1, 128, 75, kPackHead, kVecIdent, 128, 128, 1, 128);
+
+  b.norm("ds1", {"downSample1.convLayer.1", "downSample1.convLayer_gates.1"}, 256, kVecIdent);
+  b.norm("ds2", {"downSample2.convLayer.1", "downSample2.convLayer_gates.1"}, 256, kVecIdent);
+  b.norm("2dto1d", {"conv2dto1dLayer_tfan"}, 256, kVecIdent);
+  for (int i = 1; i <= 6; ++i) {
+    const std::string p = "residualLayer" + std::to_string(i);
+    b.norm("res" + std::to_string(i) + "a", {p + ".conv1d_layer.1", p + ".conv_layer_gates.1"}, 512,
+           kVecIdent);
+    b.norm("res" + std::to_string(i) + "b", {p + ".conv1d_out_layer.1"}, 256, kVecIdent);
+  }
+  b.norm("1dto2d", {"conv1dto2dLayer_tfan"}, 5120, kVecHC20);
+  b.norm("up1", {"upSample1.2"}, 256, kVecIdent);
+  b.norm("up2", {"convLayer.2"}, 128, kVecIdent);
+  return b.d;
+}
+
+ModelDesc build_discriminator() {
+  ParamTable pt;
+  pt.conv("convLayer1.0", 128, 1, 9);
+  pt.conv("downSample1.0", 256, 128, 9);
+  pt.norm("downSample1.1", 256);
+  pt.conv("downSample2.0", 512, 256, 9);
+  pt.norm("downSample2.1", 512);
+  pt.conv("downSample3.0", 1024, 512, 9);
+  pt.norm("downSample3.1", 1024);
+  pt.conv("downSample4.0", 1024, 1024, 10);  // never used in forward (model.py:316-320 vs :340-349)
+  pt.norm("downSample4.1", 1024);
+  pt.conv("outputConvLayer.0", 1, 1024, 3);
+
+  DescBuilder b(pt);
+  b.conv("stem", {"convLayer1.0"}, 128, 1, 9, kPackStemD, kVecIdent, 128, 64, 1, 64);
+  b.conv("ds1", {"downSample1.0"}, 256, 128, 9, kPackStd, kVecIdent, 256, 128, 9, 128);
+  b.conv("ds2", {"downSample2.0"}, 512, 256, 9, kPackStd, kVecIdent, 512, 256, 9, 256);
+  b.conv("ds3", {"downSample3.0"}, 1024, 512, 9, kPackStd, kVecIdent, 1024, 512, 9, 512);
+  b.conv("head", {"outputConvLayer.0"}, 1, 1024, 3, kPackHead, kVecIdent, 128, 1024, 1, 1024);
+  b.norm("ds1", {"downSample1.1"}, 256, kVecIdent);
+  b.norm("ds2", {"downSample2.1"}, 512, kVecIdent);
+  b.norm("ds3", {"downSample3.1"}, 1024, kVecIdent);
+  return b.d;
+}
+
+}  // namespace
+
+const ModelDesc& generator_desc() {
+  static const ModelDesc d = build_generator();
+  return d;
+}
+const ModelDesc& discriminator_desc() {
+  static const ModelDesc d = build_discriminator();
+  return d;
+}
+
+// ================================================================================================
+// helpers
+namespace {
+
+struct Run {
+  RunCfg rc;
+  bool ok = true;
+  void check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess && ok) {
+      ok = false;
+      if (!last_error()[0] || e != cudaErrorInvalidValue)
+        set_error("%s: %s", what, cudaGetErrorString(e));
+    }
+  }
+};
+
+struct Arena {
+  uint8_t* base;
+  long long off = 0;
+  std::vector<SavedEntry>* layout = nullptr;
+  explicit Arena(void* b) : base(reinterpret_cast<uint8_t*>(b)) {}
+  void* take(long long bytes, const char* name = nullptr) {
+    off = align_up(off, 256);
+    void* p = base ? base + off : nullptr;
+    if (layout && name) layout->push_back(SavedEntry{name, off, bytes});
+    off += bytes;
+    return p;
+  }
+  template <class T>
+  T* takeT(long long count, const char* name = nullptr) {
+    return reinterpret_cast<T*>(take(count * (long long)sizeof(T), name));
+  }
+};
+
+struct Weights {   // views into the packed blob
+  const __nv_bfloat16* bf;
+  const float* f32;
+  Weights(const void* packed, const ModelDesc& d)
+      : bf(reinterpret_cast<const __nv_bfloat16*>(packed)),
+        f32(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) +
+                                           d.packedBf16 * 2)) {}
+  WgtOperand fwd(const ConvDesc& c) const { return WgtOperand{bf + c.fHi, bf + c.fLo, c.Cp, c.Np, c.Tp}; }
+  // data-gradient operand viewed as [T][N=Cd][K=Np]
+  WgtOperand bwd(const ConvDesc& c) const { return WgtOperand{bf + c.dHi, bf + c.dLo, c.Np, c.Cd, c.Tp}; }
+  const float* bias(const ConvDesc& c) const { return f32 + c.biasEng; }
+  const float* gamma(const NormDesc& n) const { return f32 + n.gammaEng; }
+  const float* beta(const NormDesc& n) const { return f32 + n.betaEng; }
+};
+
+struct TapList {
+  int n = 0;
+  Tap t[kMaxTaps];
+  void add(int dx, int dy, int plane, int w) {
+    t[n].dx = (int8_t)dx; t[n].dy = (int8_t)dy; t[n].plane = (uint8_t)plane; t[n].w = (uint8_t)w;
+    ++n;
+  }
+};
+// stride-1 KHxKW taps (forward, or data-gradient when sign = -1)
+TapList taps_s1(int KH, int KW, int padH, int padW, int sign) {
+  TapList l;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) l.add(sign * (kw - padW), sign * (kh - padH), 0, kh * KW + kw);
+  return l;
+}
+// stride-2 KxK forward taps over a parity-split input
+TapList taps_s2_fwd(int K, int pad) {
+  TapList l;
+  for (int kh = 0; kh < K; ++kh)
+    for (int kw = 0; kw < K; ++kw) {
+      const int oy = kh - pad, ox = kw - pad;
+      const int ph = ((oy % 2) + 2) % 2, pw = ((ox % 2) + 2) % 2;
+      l.add((ox - pw) / 2, (oy - ph) / 2, ph * 2 + pw, kh * K + kw);
+    }
+  return l;
+}
+// stride-2 data-gradient taps producing input parity plane (ph, pw): reads dz at y' + (ph+pad-kh)/2
+TapList taps_s2_bwd(int K, int pad, int ph, int pw) {
+  TapList l;
+  for (int kh = 0; kh < K; ++kh) {
+    if (((ph + pad - kh) % 2 + 2) % 2) continue;
+    for (int kw = 0; kw < K; ++kw) {
+      if (((pw + pad - kw) % 2 + 2) % 2) continue;
+      l.add((pw + pad - kw) / 2, (ph + pad - kh) / 2, 0, kh * K + kw);
+    }
+  }
+  return l;
+}
+TapList taps_rows(int n, int sign) {  // n taps along Y (2D<->1D flatten), weight slice = row
+  TapList l;
+  for (int h = 0; h < n; ++h) l.add(0, sign * h, 0, h);
+  return l;
+}
+TapList taps_one() {
+  TapList l;
+  l.add(0, 0, 0, 0);
+  return l;
+}
+
+struct OutAddr {
+  float* out;
+  long long sB, sY, sX;
+  int nSplit;
+  long long sNhi;
+};
+OutAddr plain_out(float* out, int Y, int X, int N) {
+  return OutAddr{out, (long long)Y * X * N, (long long)X * N, (long long)N, N, 0};
+}
+
+void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& taps, int oB, int oY,
+              int oX, const OutAddr& o, const float* bias, const float* addsrc, const char* what) {
+  if (!r.ok) return;
+  ConvGeom g{};
+  g.a = a;
+  g.w = w;
+  g.oX = oX; g.oY = oY; g.oB = oB;
+  if (!choose_box(oB, oY, oX, kTileM, &g.BX, &g.BY, &g.BB)) { r.ok = false; set_error("%s: box", what); return; }
+  g.tilesX = (oX + g.BX - 1) / g.BX;
+  g.tilesY = (oY + g.BY - 1) / g.BY;
+  g.tilesB = (oB + g.BB - 1) / g.BB;
+  g.nTaps = taps.n;
+  g.cBlocks = a.C / kBlockK;
+  for (int i = 0; i < taps.n; ++i) g.taps[i] = taps.t[i];
+  g.sB = o.sB; g.sY = o.sY; g.sX = o.sX; g.nSplit = o.nSplit; g.sNhi = o.sNhi;
+  g.out = o.out; g.bias = bias; g.addsrc = addsrc;
+  g.nPass = r.rc.nPass;
+  r.check(r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream), what);
+}
+
+void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList& xtaps,
+               const TapList* ztaps, int pB, int pY, int pX, float* dw, const char* what) {
+  if (!r.ok) return;
+  WgradGeom g{};
+  g.dz = dz;
+  g.x = x;
+  g.pX = pX; g.pY = pY; g.pB = pB;
+  if (!choose_box(pB, pY, pX, 64, &g.BX, &g.BY, &g.BB)) { r.ok = false; set_error("%s: box", what); return; }
+  g.tilesX = (pX + g.BX - 1) / g.BX;
+  g.tilesY = (pY + g.BY - 1) / g.BY;
+  g.tilesB = (pB + g.BB - 1) / g.BB;
+  g.nTaps = xtaps.n;
+  for (int i = 0; i < xtaps.n; ++i) {
+    g.taps[i] = xtaps.t[i];
+    if (ztaps) g.ztaps[i] = ztaps->t[i];
+    else g.ztaps[i] = Tap{0, 0, 0, 0};
+  }
+  g.N = dz.C;
+  g.C = x.C;
+  g.cTile = x.C % 128 == 0 ? 128 : 64;
+  const long long outTiles = (long long)xtaps.n * (g.N / 128) * (g.C / g.cTile);
+  const long long posTiles = (long long)g.tilesX * g.tilesY * g.tilesB;
+  long long sk = (2 * 148 + outTiles - 1) / outTiles;
+  if (sk > posTiles / 4) sk = posTiles / 4;
+  if (sk < 1) sk = 1;
+  g.splitK = (int)sk;
+  g.dw = dw;
+  g.nPass = r.rc.nPass;
+  r.check(r.rc.backend == 0 ? launch_wgrad_tc(g, r.rc.stream) : launch_wgrad_simt(g, r.rc.stream), what);
+}
+
+ActOperand plain_op(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int B, int Y, int X, int C) {
+  return ActOperand{hi, lo, C, X, Y, 1, B};
+}
+ActOperand parity_op(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int B, int Y, int X, int C) {
+  return ActOperand{hi, lo, C, (X + 1) / 2, (Y + 1) / 2, 4, B};
+}
+long long parity_elems(int B, int Y, int X, int C) {
+  return (long long)B * 4 * ((Y + 1) / 2) * ((X + 1) / 2) * C;
+}
+
+struct BfPair {
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+};
+BfPair take_pair(Arena& a, long long elems, const char* name) {
+  BfPair p;
+  p.hi = a.takeT<__nv_bfloat16>(elems, name);
+  p.lo = a.takeT<__nv_bfloat16>(elems);
+  return p;
+}
+struct Stat {
+  float* mean;
+  float* rstd;
+};
+Stat take_stat(Arena& a, long long n) {
+  Stat s;
+  s.mean = a.takeT<float>(n);
+  s.rstd = a.takeT<float>(n);
+  return s;
+}
+
+ApplyArgs mk_apply(int mode, const float* z, int Nz, int zY, int zX, const Stat& st, int Nstat,
+                   const float* gamma, const float* beta, int affPeriod, const float* residual,
+                   ActBuf out) {
+  ApplyArgs a{};
+  a.mode = mode; a.z = z; a.Nz = Nz; a.zY = zY; a.zX = zX;
+  a.mean = st.mean; a.rstd = st.rstd; a.Nstat = Nstat;
+  a.gamma = gamma; a.beta = beta; a.affPeriod = affPeriod;
+  a.residual = residual; a.out = out;
+  return a;
+}
+ApplyBwdArgs mk_bwd(int mode, const float* z, int Nz, int zY, int zX, const Stat& st, int Nstat,
+                    const float* gamma, const float* beta, int affPeriod, ActBuf dA, float* t1,
+                    float* t2, float* dgamma, float* dbeta, BfPair dz, float* dbias) {
+  ApplyBwdArgs a{};
+  a.mode = mode; a.z = z; a.Nz = Nz; a.zY = zY; a.zX = zX;
+  a.mean = st.mean; a.rstd = st.rstd; a.Nstat = Nstat;
+  a.gamma = gamma; a.beta = beta; a.affPeriod = affPeriod;
+  a.dA = dA; a.t1 = t1; a.t2 = t2; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.dz_hi = dz.hi; a.dz_lo = dz.lo; a.dbias = dbias;
+  return a;
+}
+void run_bwd(Run& r, const ApplyBwdArgs& a, const char* what) {
+  if (!r.ok) return;
+  r.check(launch_apply_bwd_reduce(a, r.rc.stream), what);
+  r.check(launch_apply_bwd(a, r.rc.stream), what);
+}
+
+}  // namespace
+
+// ================================================================================================
+// packing
+int pack_model(const ModelDesc& d, const float* params, void* packed, const RunCfg& rc) {
+  Run r{rc};
+  __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(packed);
+  float* f32 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + d.packedBf16 * 2);
+  // padding elements (unused taps / channels) must be zero
+  r.check(launch_fill_zero(packed, (size_t)d.packed_bytes(), rc.stream), "pack: zero");
+  for (const ConvDesc& c : d.convs) {
+    for (int p = 0; p < c.nParts; ++p) {
+      PackArgs a{};
+      a.kind = c.kind;
+      a.ref = params + c.wOff[p];
+      a.N = c.refN; a.C = c.refC; a.T = c.refT;
+      a.nOffset = p * c.refN;
+      a.Np = c.Np; a.Cp = c.Cp; a.Tp = c.Tp;
+      a.f_hi = bf + c.fHi; a.f_lo = bf + c.fLo;
+      a.d_hi = c.Cd ? bf + c.dHi : nullptr;
+      a.d_lo = c.Cd ? bf + c.dLo : nullptr;
+      a.Cd = c.Cd;
+      r.check(launch_pack_weight(a, rc.stream), "pack: weight");
+      r.check(launch_pack_vec(c.biasKind, params + c.bOff[p], c.refN, f32 + c.biasEng + p * c.refN,
+                              rc.stream), "pack: bias");
+    }
+  }
+  for (const NormDesc& n : d.norms) {
+    for (int p = 0; p < n.nParts; ++p) {
+      r.check(launch_pack_vec(n.vecKind, params + n.gOff[p], n.n, f32 + n.gammaEng + p * n.n, rc.stream), "pack: gamma");
+      r.check(launch_pack_vec(n.vecKind, params + n.bOff[p], n.n, f32 + n.betaEng + p * n.n, rc.stream), "pack: beta");
+    }
+  }
+  return r.ok ? 0 : 1;
+}
+
+int unpack_grads(const ModelDesc& d, const float* gblob, float* gradFlat, const RunCfg& rc) {
+  Run r{rc};
+  for (const ConvDesc& c : d.convs) {
+    for (int p = 0; p < c.nParts; ++p) {
+      PackArgs a{};
+      a.kind = c.kind;
+      a.N = c.refN; a.C = c.refC; a.T = c.refT;
+      a.nOffset = p * c.refN;
+      a.Np = c.Np; a.Cp = c.Cp; a.Tp = c.Tp;
+      r.check(launch_unpack_wgrad(a, gblob + c.gW, gradFlat + c.wOff[p], rc.stream), "unpack: weight");
+      r.check(launch_unpack_vec(c.biasKind, gblob + c.gB + p * c.refN, c.refN, gradFlat + c.bOff[p],
+                                rc.stream), "unpack: bias");
+    }
+  }
+  for (const NormDesc& n : d.norms) {
+    for (int p = 0; p < n.nParts; ++p) {
+      r.check(launch_unpack_vec(n.vecKind, gblob + n.gGamma + p * n.n, n.n, gradFlat + n.gOff[p], rc.stream), "unpack: gamma");
+      r.check(launch_unpack_vec(n.vecKind, gblob + n.gBeta + p * n.n, n.n, gradFlat + n.bOff[p], rc.stream), "unpack: beta");
+    }
+  }
+  return r.ok ? 0 : 1;
+}
+
+// ================================================================================================
+// Generator
+namespace {
+
+struct GenDims {
+  int B, T, W1, W2, X1, X2;  // X1 = 2*W2 (up1 output width), X2 = 4*W2 (output frames)
+  GenDims(int b, int t) : B(b), T(t) {
+    W1 = (T + 1) / 2;
+    W2 = (W1 + 1) / 2;
+    X1 = 2 * W2;
+    X2 = 4 * W2;
+  }
+};
+
+struct GenSaved {
+  BfPair X15; float* z0;
+  BfPair A0; float* z1; Stat st1;
+  BfPair A1; float* z2; Stat st2;
+  BfPair A2; float* z3; Stat st3;
+  float* Rf[7]; BfPair R[7];
+  float* z4[6]; Stat st4[6]; BfPair H[6]; float* z5[6]; Stat st5[6];
+  float* z6; Stat st6; BfPair U0;
+  float* z7; Stat st7; BfPair U1;
+  float* z8; Stat st8; BfPair U2;
+  long long total;
+};
+
+GenSaved plan_gen_saved(const GenDims& d, void* base, std::vector<SavedEntry>* layout) {
+  Arena a(base);
+  a.layout = layout;
+  GenSaved s{};
+  const long long M0 = (long long)d.B * 80 * d.T, M1 = (long long)d.B * 40 * d.W1,
+                  M2 = (long long)d.B * 20 * d.W2, L = (long long)d.B * d.W2,
+                  M7 = (long long)d.B * 40 * d.X1, M8 = (long long)d.B * 80 * d.X2;
+  s.X15 = take_pair(a, M0 * 64, "X15");
+  s.z0 = a.takeT<float>(M0 * 256, "z0");
+  s.A0 = take_pair(a, parity_elems(d.B, 80, d.T, 128), "A0");
+  s.z1 = a.takeT<float>(M1 * 512, "z1");
+  s.st1 = take_stat(a, d.B * 512);
+  s.A1 = take_pair(a, parity_elems(d.B, 40, d.W1, 256), "A1");
+  s.z2 = a.takeT<float>(M2 * 512, "z2");
+  s.st2 = take_stat(a, d.B * 512);
+  s.A2 = take_pair(a, M2 * 256, "A2");
+  s.z3 = a.takeT<float>(L * 256, "z3");
+  s.st3 = take_stat(a, d.B * 256);
+  for (int i = 0; i < 7; ++i) {
+    s.Rf[i] = a.takeT<float>(L * 256, i == 0 ? "R0" : (i == 6 ? "R6" : nullptr));
+    s.R[i] = take_pair(a, L * 256, nullptr);
+  }
+  for (int i = 0; i < 6; ++i) {
+    s.z4[i] = a.takeT<float>(L * 1024, i == 0 ? "z4_0" : nullptr);
+    s.st4[i] = take_stat(a, d.B * 1024);
+    s.H[i] = take_pair(a, L * 512, nullptr);
+    s.z5[i] = a.takeT<float>(L * 256, i == 0 ? "z5_0" : nullptr);
+    s.st5[i] = take_stat(a, d.B * 256);
+  }
+  s.z6 = a.takeT<float>(M2 * 256, "z6");
+  s.st6 = take_stat(a, (long long)d.B * 20 * 256);
+  s.U0 = take_pair(a, M2 * 256, "U0");
+  s.z7 = a.takeT<float>(M2 * 1024, "z7");
+  s.st7 = take_stat(a, d.B * 256);
+  s.U1 = take_pair(a, M7 * 256, "U1");
+  s.z8 = a.takeT<float>(M7 * 512, "z8");
+  s.st8 = take_stat(a, d.B * 128);
+  s.U2 = take_pair(a, M8 * 128, "U2");
+  s.total = align_up(a.off, 256);
+  return s;
+}
+
+ActBuf abuf(BfPair p, float* f32, int nImg, int Y, int X, int C, int parity) {
+  return ActBuf{p.hi, p.lo, f32, nImg, Y, X, C, parity};
+}
+ActBuf gbuf(float* f32, int nImg, int Y, int X, int C, int parity) {
+  return ActBuf{nullptr, nullptr, f32, nImg, Y, X, C, parity};
+}
+
+}  // namespace
+
+long long generator_saved_bytes(int B, int T) { return plan_gen_saved(GenDims(B, T), nullptr, nullptr).total; }
+std::vector<SavedEntry> generator_saved_layout(int B, int T) {
+  std::vector<SavedEntry> v;
+  plan_gen_saved(GenDims(B, T), nullptr, &v);
+  return v;
+}
+long long generator_fwd_ws_bytes(int B, int T) {
+  GenDims d(B, T);
+  return align_up((long long)B * 80 * d.X2 * 128 * 4, 256) + 256;
+}
+
+int generator_forward(const void* packed, const float* x, const float* mask, int B, int T,
+                      float* out, void* saved, void* ws, const RunCfg& rc) {
+  const ModelDesc& md = generator_desc();
+  const GenDims d(B, T);
+  GenSaved s = plan_gen_saved(d, saved, nullptr);
+  Weights W(packed, md);
+  Run r{rc};
+  cudaStream_t st = rc.stream;
+  const auto& cv = md.convs;
+  const auto& nm = md.norms;
+
+  // parity-split buffers have a padding column/row when the extent is odd: keep it zero
+  if (d.T & 1) {
+    r.check(launch_fill_zero(s.A0.hi, parity_elems(B, 80, d.T, 128) * 2, st), "zero A0");
+    r.check(launch_fill_zero(s.A0.lo, parity_elems(B, 80, d.T, 128) * 2, st), "zero A0");
+  }
+  if (d.W1 & 1) {
+    r.check(launch_fill_zero(s.A1.hi, parity_elems(B, 40, d.W1, 256) * 2, st), "zero A1");
+    r.check(launch_fill_zero(s.A1.lo, parity_elems(B, 40, d.W1, 256) * 2, st), "zero A1");
+  }
+
+  // stem: stack(x*mask, mask) -> 5x15 conv || gates -> a * sigmoid(g)            model.py:241-242
+  r.check(launch_prep_g(x, mask, B, T, s.X15.hi, s.X15.lo, st), "prep_g");
+  run_conv(r, plain_op(s.X15.hi, s.X15.lo, B, 80, T, 64), W.fwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, 1),
+           B, 80, T, plain_out(s.z0, 80, T, 256), W.bias(cv[G_STEM]), nullptr, "G stem conv");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedNoNorm, s.z0, 256, 80, T, Stat{nullptr, nullptr}, 0,
+                                              nullptr, nullptr, 1, nullptr,
+                                              abuf(s.A0, nullptr, B, 80, T, 128, 1)), st), "G stem glu");
+  // downSample1 / downSample2: 5x5 stride 2 conv || gates, IN, gated GLU         model.py:245-246
+  run_conv(r, parity_op(s.A0.hi, s.A0.lo, B, 80, T, 128), W.fwd(cv[G_DS1]), taps_s2_fwd(5, 2), B, 40,
+           d.W1, plain_out(s.z1, 40, d.W1, 512), W.bias(cv[G_DS1]), nullptr, "G ds1 conv");
+  if (r.ok) r.check(launch_stats(s.z1, 512, 40 * d.W1, B, 1, s.st1.mean, s.st1.rstd, st), "G ds1 stats");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z1, 512, 40, d.W1, s.st1, 512, W.gamma(nm[GN_DS1]),
+                                              W.beta(nm[GN_DS1]), 1, nullptr,
+                                              abuf(s.A1, nullptr, B, 40, d.W1, 256, 1)), st), "G ds1 glu");
+  run_conv(r, parity_op(s.A1.hi, s.A1.lo, B, 40, d.W1, 256), W.fwd(cv[G_DS2]), taps_s2_fwd(5, 2), B,
+           20, d.W2, plain_out(s.z2, 20, d.W2, 512), W.bias(cv[G_DS2]), nullptr, "G ds2 conv");
+  if (r.ok) r.check(launch_stats(s.z2, 512, 20 * d.W2, B, 1, s.st2.mean, s.st2.rstd, st), "G ds2 stats");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[GN_DS2]),
+                                              W.beta(nm[GN_DS2]), 1, nullptr,
+                                              abuf(s.A2, nullptr, B, 20, d.W2, 256, 0)), st), "G ds2 glu");
+  // 2D -> 1D: view (c*20+h), Conv1d k1 5120->256, IN1d                           model.py:249-255
+  run_conv(r, plain_op(s.A2.hi, s.A2.lo, B, 20, d.W2, 256), W.fwd(cv[G_2DTO1D]), taps_rows(20, 1), B,
+           1, d.W2, plain_out(s.z3, 1, d.W2, 256), W.bias(cv[G_2DTO1D]), nullptr, "G 2dto1d conv");
+  if (r.ok) r.check(launch_stats(s.z3, 256, d.W2, B, 1, s.st3.mean, s.st3.rstd, st), "G 2dto1d stats");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z3, 256, 1, d.W2, s.st3, 256, W.gamma(nm[GN_2DTO1D]),
+                                              W.beta(nm[GN_2DTO1D]), 1, nullptr,
+                                              abuf(s.R[0], s.Rf[0], B, 1, d.W2, 256, 0)), st), "G 2dto1d IN");
+  // six gated 1-D residual blocks                                                model.py:258-263
+  const TapList k3 = taps_s1(1, 3, 0, 1, 1);
+  for (int i = 0; i < 6; ++i) {
+    const ConvDesc& ca = cv[G_RES0 + 2 * i];
+    const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
+    const NormDesc& na = nm[GN_RES0 + 2 * i];
+    const NormDesc& nb = nm[GN_RES0 + 2 * i + 1];
+    run_conv(r, plain_op(s.R[i].hi, s.R[i].lo, B, 1, d.W2, 256), W.fwd(ca), k3, B, 1, d.W2,
+             plain_out(s.z4[i], 1, d.W2, 1024), W.bias(ca), nullptr, "G res conv a");
+    if (r.ok) r.check(launch_stats(s.z4[i], 1024, d.W2, B, 1, s.st4[i].mean, s.st4[i].rstd, st), "G res stats a");
+    if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z4[i], 1024, 1, d.W2, s.st4[i], 1024, W.gamma(na),
+                                                W.beta(na), 1, nullptr,
+                                                abuf(s.H[i], nullptr, B, 1, d.W2, 512, 0)), st), "G res glu");
+    run_conv(r, plain_op(s.H[i].hi, s.H[i].lo, B, 1, d.W2, 512), W.fwd(cb), k3, B, 1, d.W2,
+             plain_out(s.z5[i], 1, d.W2, 256), W.bias(cb), nullptr, "G res conv b");
+    if (r.ok) r.check(launch_stats(s.z5[i], 256, d.W2, B, 1, s.st5[i].mean, s.st5[i].rstd, st), "G res stats b");
+    if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z5[i], 256, 1, d.W2, s.st5[i], 256, W.gamma(nb),
+                                                W.beta(nb), 1, s.Rf[i],
+                                                abuf(s.R[i + 1], s.Rf[i + 1], B, 1, d.W2, 256, 0)), st), "G res add");
+  }
+  // 1D -> 2D: Conv1d k1 256->5120, IN1d over time per (c,h) row, view (256,20,W)   model.py:266-271
+  {
+    OutAddr o{s.z6, (long long)20 * d.W2 * 256, 0, 256, 256, (long long)d.W2 * 256};
+    run_conv(r, plain_op(s.R[6].hi, s.R[6].lo, B, 1, d.W2, 256), W.fwd(cv[G_1DTO2D]), taps_one(), B, 1,
+             d.W2, o, W.bias(cv[G_1DTO2D]), nullptr, "G 1dto2d conv");
+  }
+  if (r.ok) r.check(launch_stats(s.z6, 256, d.W2, B * 20, 1, s.st6.mean, s.st6.rstd, st), "G 1dto2d stats");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z6, 256, 1, d.W2, s.st6, 256, W.gamma(nm[GN_1DTO2D]),
+                                              W.beta(nm[GN_1DTO2D]), 20, nullptr,
+                                              abuf(s.U0, nullptr, B * 20, 1, d.W2, 256, 0)), st), "G 1dto2d IN");
+  // upSample1 / upSample2: 5x5 conv, PixelShuffle(2), IN, swish                  model.py:274-275
+  const TapList k55 = taps_s1(5, 5, 2, 2, 1);
+  run_conv(r, plain_op(s.U0.hi, s.U0.lo, B, 20, d.W2, 256), W.fwd(cv[G_UP1]), k55, B, 20, d.W2,
+           plain_out(s.z7, 20, d.W2, 1024), W.bias(cv[G_UP1]), nullptr, "G up1 conv");
+  if (r.ok) r.check(launch_stats(s.z7, 1024, 20 * d.W2, B, 4, s.st7.mean, s.st7.rstd, st), "G up1 stats");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z7, 1024, 20, d.W2, s.st7, 256, W.gamma(nm[GN_UP1]),
+                                              W.beta(nm[GN_UP1]), 1, nullptr,
+                                              abuf(s.U1, nullptr, B, 40, d.X1, 256, 0)), st), "G up1 act");
+  run_conv(r, plain_op(s.U1.hi, s.U1.lo, B, 40, d.X1, 256), W.fwd(cv[G_UP2]), k55, B, 40, d.X1,
+           plain_out(s.z8, 40, d.X1, 512), W.bias(cv[G_UP2]), nullptr, "G up2 conv");
+  if (r.ok) r.check(launch_stats(s.z8, 512, 40 * d.X1, B, 4, s.st8.mean, s.st8.rstd, st), "G up2 stats");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z8, 512, 40, d.X1, s.st8, 128, W.gamma(nm[GN_UP2]),
+                                              W.beta(nm[GN_UP2]), 1, nullptr,
+                                              abuf(s.U2, nullptr, B, 80, d.X2, 128, 0)), st), "G up2 act");
+  // head: 5x15 conv 128->1 as per-tap GEMM + shifted sum                          model.py:278-279
+  Arena wa(ws);
+  float* P = wa.takeT<float>((long long)B * 80 * d.X2 * 128);
+  run_conv(r, plain_op(s.U2.hi, s.U2.lo, B, 80, d.X2, 128), W.fwd(cv[G_HEAD]), taps_one(), B, 80, d.X2,
+           plain_out(P, 80, d.X2, 128), nullptr, nullptr, "G head gemm");
+  if (r.ok) r.check(launch_head_g_fwd(P, W.bias(cv[G_HEAD]), B, 80, d.X2, out, st), "G head sum");
+  return r.ok ? 0 : 1;
+}
+
+long long generator_bwd_ws_bytes(int B, int T) {
+  GenDims d(B, T);
+  const long long M0 = (long long)B * 80 * d.T, M2 = (long long)B * 20 * d.W2, L = (long long)B * d.W2,
+                  M7 = (long long)B * 40 * d.X1, M8 = (long long)B * 80 * d.X2;
+  long long b = 0;
+  auto add = [&](long long bytes) { b = align_up(b, 256) + bytes; };
+  add(M8 * 128 * 2); add(M8 * 128 * 2);          // dP
+  add(M8 * 128 * 4);                             // dU2
+  add(M7 * 512 * 2); add(M7 * 512 * 2);          // dz8
+  add(M7 * 256 * 4);                             // dU1
+  add(M2 * 1024 * 2); add(M2 * 1024 * 2);        // dz7
+  add(M2 * 256 * 4);                             // dU0
+  add(M2 * 256 * 2); add(M2 * 256 * 2);          // dz6
+  for (int i = 0; i < 7; ++i) add(L * 256 * 4);  // dR
+  add(L * 256 * 2); add(L * 256 * 2);            // dz5
+  add(L * 512 * 4);                              // dH
+  add(L * 1024 * 2); add(L * 1024 * 2);          // dz4
+  add(L * 256 * 2); add(L * 256 * 2);            // dz3
+  add(M2 * 256 * 4);                             // dA2
+  add(M2 * 512 * 2); add(M2 * 512 * 2);          // dz2
+  add(parity_elems(B, 40, d.W1, 256) * 4);       // dA1
+  add((long long)B * 40 * d.W1 * 512 * 2); add((long long)B * 40 * d.W1 * 512 * 2);  // dz1
+  add(parity_elems(B, 80, d.T, 128) * 4);        // dA0
+  add(M0 * 256 * 2); add(M0 * 256 * 2);          // dz0
+  add(M0 * 64 * 4);                              // dX15
+  add((long long)B * 20 * 1024 * 4); add((long long)B * 20 * 1024 * 4);  // t1, t2
+  add(2 * 5120 * 4);                             // affine-grad sink
+  return align_up(b, 256) + 4096;
+}
+
+int generator_backward(const void* packed, const void* saved, const float* mask, const float* dout,
+                       int B, int T, float* dx, float* gblob, int needWgrad, void* ws,
+                       const RunCfg& rc) {
+  const ModelDesc& md = generator_desc();
+  const GenDims d(B, T);
+  GenSaved s = plan_gen_saved(d, const_cast<void*>(saved), nullptr);
+  Weights W(packed, md);
+  Run r{rc};
+  cudaStream_t st = rc.stream;
+  const auto& cv = md.convs;
+  const auto& nm = md.norms;
+  Arena a(ws);
+  const long long M0 = (long long)B * 80 * d.T, M2 = (long long)B * 20 * d.W2, L = (long long)B * d.W2,
+                  M7 = (long long)B * 40 * d.X1, M8 = (long long)B * 80 * d.X2;
+  const long long M1 = (long long)B * 40 * d.W1;
+  float* t1 = a.takeT<float>((long long)B * 20 * 1024);
+  float* t2 = a.takeT<float>((long long)B * 20 * 1024);
+  float* junk = a.takeT<float>(2 * 5120);  // sink for affine grads when the caller wants none
+  auto gW = [&](int ci) { return gblob + cv[ci].gW; };
+  auto gB = [&](int ci) -> float* { return needWgrad ? gblob + cv[ci].gB : nullptr; };
+  auto gGa = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gGamma : junk; };
+  auto gBe = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gBeta : junk + 5120; };
+  const TapList one = taps_one();
+
+  // ---- head                                                                    model.py:278
+  BfPair dP = take_pair(a, M8 * 128, nullptr);
+  r.check(launch_head_g_bwd(dout, B, 80, d.X2, dP.hi, dP.lo, gB(G_HEAD), st), "G head bwd");
+  float* dU2 = a.takeT<float>(M8 * 128);
+  run_conv(r, plain_op(dP.hi, dP.lo, B, 80, d.X2, 128), W.bwd(cv[G_HEAD]), one, B, 80, d.X2,
+           plain_out(dU2, 80, d.X2, 128), nullptr, nullptr, "G head dgrad");
+  if (needWgrad)
+    run_wgrad(r, plain_op(dP.hi, dP.lo, B, 80, d.X2, 128), plain_op(s.U2.hi, s.U2.lo, B, 80, d.X2, 128),
+              one, nullptr, B, 80, d.X2, gW(G_HEAD), "G head wgrad");
+  // ---- upSample2
+  const TapList k55f = taps_s1(5, 5, 2, 2, 1), k55b = taps_s1(5, 5, 2, 2, -1);
+  BfPair dz8 = take_pair(a, M7 * 512, nullptr);
+  run_bwd(r, mk_bwd(kINSwishShuffle, s.z8, 512, 40, d.X1, s.st8, 128, W.gamma(nm[GN_UP2]), W.beta(nm[GN_UP2]),
+                    1, gbuf(dU2, B, 80, d.X2, 128, 0), t1, t2, gGa(GN_UP2), gBe(GN_UP2), dz8, gB(G_UP2)),
+          "G up2 bwd");
+  float* dU1 = a.takeT<float>(M7 * 256);
+  run_conv(r, plain_op(dz8.hi, dz8.lo, B, 40, d.X1, 512), W.bwd(cv[G_UP2]), k55b, B, 40, d.X1,
+           plain_out(dU1, 40, d.X1, 256), nullptr, nullptr, "G up2 dgrad");
+  if (needWgrad)
+    run_wgrad(r, plain_op(dz8.hi, dz8.lo, B, 40, d.X1, 512), plain_op(s.U1.hi, s.U1.lo, B, 40, d.X1, 256),
+              k55f, nullptr, B, 40, d.X1, gW(G_UP2), "G up2 wgrad");
+  // ---- upSample1
+  BfPair dz7 = take_pair(a, M2 * 1024, nullptr);
+  run_bwd(r, mk_bwd(kINSwishShuffle, s.z7, 1024, 20, d.W2, s.st7, 256, W.gamma(nm[GN_UP1]), W.beta(nm[GN_UP1]),
+                    1, gbuf(dU1, B, 40, d.X1, 256, 0), t1, t2, gGa(GN_UP1), gBe(GN_UP1), dz7, gB(G_UP1)),
+          "G up1 bwd");
+  float* dU0 = a.takeT<float>(M2 * 256);
+  run_conv(r, plain_op(dz7.hi, dz7.lo, B, 20, d.W2, 1024), W.bwd(cv[G_UP1]), k55b, B, 20, d.W2,
+           plain_out(dU0, 20, d.W2, 256), nullptr, nullptr, "G up1 dgrad");
+  if (needWgrad)
+    run_wgrad(r, plain_op(dz7.hi, dz7.lo, B, 20, d.W2, 1024), plain_op(s.U0.hi, s.U0.lo, B, 20, d.W2, 256),
+              k55f, nullptr, B, 20, d.W2, gW(G_UP1), "G up1 wgrad");
+  // ---- 1D -> 2D
+  BfPair dz6 = take_pair(a, M2 * 256, nullptr);
+  run_bwd(r, mk_bwd(kINOnly, s.z6, 256, 1, d.W2, s.st6, 256, W.gamma(nm[GN_1DTO2D]), W.beta(nm[GN_1DTO2D]), 20,
+                    gbuf(dU0, B * 20, 1, d.W2, 256, 0), t1, t2, gGa(GN_1DTO2D), gBe(GN_1DTO2D), dz6, nullptr),
+          "G 1dto2d bwd");
+  float* dR[7];
+  for (int i = 0; i < 7; ++i) dR[i] = a.takeT<float>(L * 256);
+  const TapList rows20 = taps_rows(20, 1);
+  {
+    // dR6[(b,w), cin] = sum_h sum_c dz6[b,h,w,c] * W[c*20+h][cin]: 20 row taps over the (c,w,h) view
+    const ConvDesc& c = cv[G_1DTO2D];
+    WgtOperand wop{W.bf + c.dHi, W.bf + c.dLo, 256, c.Cd, 20};
+    run_conv(r, plain_op(dz6.hi, dz6.lo, B, 20, d.W2, 256), wop, rows20, B, 1, d.W2,
+             plain_out(dR[6], 1, d.W2, 256), nullptr, nullptr, "G 1dto2d dgrad");
+    if (needWgrad) {
+      TapList xt;  // x operand (R6) is not shifted; dz operand walks the 20 rows; slice = row
+      for (int h = 0; h < 20; ++h) xt.add(0, 0, 0, h);
+      run_wgrad(r, plain_op(dz6.hi, dz6.lo, B, 20, d.W2, 256), plain_op(s.R[6].hi, s.R[6].lo, B, 1, d.W2, 256),
+                xt, &rows20, B, 1, d.W2, gW(G_1DTO2D), "G 1dto2d wgrad");
+    }
+  }
+  // ---- residual blocks, reversed
+  const TapList k3f = taps_s1(1, 3, 0, 1, 1), k3b = taps_s1(1, 3, 0, 1, -1);
+  BfPair dz5 = take_pair(a, L * 256, nullptr);
+  float* dH = a.takeT<float>(L * 512);
+  BfPair dz4 = take_pair(a, L * 1024, nullptr);
+  for (int i = 5; i >= 0; --i) {
+    const ConvDesc& ca = cv[G_RES0 + 2 * i];
+    const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
+    const int na = GN_RES0 + 2 * i, nb = GN_RES0 + 2 * i + 1;
+    run_bwd(r, mk_bwd(kINOnly, s.z5[i], 256, 1, d.W2, s.st5[i], 256, W.gamma(nm[nb]), W.beta(nm[nb]), 1,
+                      gbuf(dR[i + 1], B, 1, d.W2, 256, 0), t1, t2, gGa(nb), gBe(nb), dz5, nullptr), "G res bwd b");
+    run_conv(r, plain_op(dz5.hi, dz5.lo, B, 1, d.W2, 256), W.bwd(cb), k3b, B, 1, d.W2,
+             plain_out(dH, 1, d.W2, 512), nullptr, nullptr, "G res dgrad b");
+    if (needWgrad)
+      run_wgrad(r, plain_op(dz5.hi, dz5.lo, B, 1, d.W2, 256), plain_op(s.H[i].hi, s.H[i].lo, B, 1, d.W2, 512),
+                k3f, nullptr, B, 1, d.W2, gblob + cb.gW, "G res wgrad b");
+    run_bwd(r, mk_bwd(kGatedIN, s.z4[i], 1024, 1, d.W2, s.st4[i], 1024, W.gamma(nm[na]), W.beta(nm[na]), 1,
+                      gbuf(dH, B, 1, d.W2, 512, 0), t1, t2, gGa(na), gBe(na), dz4, nullptr), "G res bwd a");
+    // dR[i] = dR[i+1] (skip connection) + dgrad
+    run_conv(r, plain_op(dz4.hi, dz4.lo, B, 1, d.W2, 1024), W.bwd(ca), k3b, B, 1, d.W2,
+             plain_out(dR[i], 1, d.W2, 256), nullptr, dR[i + 1], "G res dgrad a");
+    if (needWgrad)
+      run_wgrad(r, plain_op(dz4.hi, dz4.lo, B, 1, d.W2, 1024), plain_op(s.R[i].hi, s.R[i].lo, B, 1, d.W2, 256),
+                k3f, nullptr, B, 1, d.W2, gblob + ca.gW, "G res wgrad a");
+  }
+  // ---- 2D -> 1D
+  BfPair dz3 = take_pair(a, L * 256, nullptr);
+  run_bwd(r, mk_bwd(kINOnly, s.z3, 256, 1, d.W2, s.st3, 256, W.gamma(nm[GN_2DTO1D]), W.beta(nm[GN_2DTO1D]), 1,
+                    gbuf(dR[0], B, 1, d.W2, 256, 0), t1, t2, gGa(GN_2DTO1D), gBe(GN_2DTO1D), dz3, nullptr),
+          "G 2dto1d bwd");
+  float* dA2 = a.takeT<float>(M2 * 256);
+  {
+    // dA2[b,h,w,c] = sum_n dz3[(b,w), n] * W[n][c*20+h]: one tap, N = (h,c) = 5120 split back over h
+    const ConvDesc& c = cv[G_2DTO1D];
+    WgtOperand wop{W.bf + c.dHi, W.bf + c.dLo, 256, 5120, 1};
+    OutAddr o{dA2, (long long)20 * d.W2 * 256, 0, 256, 256, (long long)d.W2 * 256};
+    run_conv(r, plain_op(dz3.hi, dz3.lo, B, 1, d.W2, 256), wop, one, B, 1, d.W2, o, nullptr, nullptr,
+             "G 2dto1d dgrad");
+    if (needWgrad)
+      run_wgrad(r, plain_op(dz3.hi, dz3.lo, B, 1, d.W2, 256), plain_op(s.A2.hi, s.A2.lo, B, 20, d.W2, 256),
+                rows20, nullptr, B, 1, d.W2, gW(G_2DTO1D), "G 2dto1d wgrad");
+  }
+  // ---- downSample2
+  BfPair dz2 = take_pair(a, M2 * 512, nullptr);
+  run_bwd(r, mk_bwd(kGatedIN, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[GN_DS2]), W.beta(nm[GN_DS2]), 1,
+                    gbuf(dA2, B, 20, d.W2, 256, 0), t1, t2, gGa(GN_DS2), gBe(GN_DS2), dz2, nullptr), "G ds2 bwd");
+  float* dA1 = a.takeT<float>(parity_elems(B, 40, d.W1, 256));
+  {
+    const int Yp = 20, Xp = (d.W1 + 1) / 2;  // == output grid of ds2 (20 x W2)
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const int p = ph * 2 + pw;
+        OutAddr o{dA1 + (long long)p * Yp * Xp * 256, (long long)4 * Yp * Xp * 256, (long long)Xp * 256, 256, 256, 0};
+        run_conv(r, plain_op(dz2.hi, dz2.lo, B, 20, d.W2, 512), W.bwd(cv[G_DS2]), taps_s2_bwd(5, 2, ph, pw),
+                 B, Yp, Xp, o, nullptr, nullptr, "G ds2 dgrad");
+      }
+  }
+  if (needWgrad)
+    run_wgrad(r, plain_op(dz2.hi, dz2.lo, B, 20, d.W2, 512), parity_op(s.A1.hi, s.A1.lo, B, 40, d.W1, 256),
+              taps_s2_fwd(5, 2), nullptr, B, 20, d.W2, gW(G_DS2), "G ds2 wgrad");
+  // ---- downSample1
+  BfPair dz1 = take_pair(a, M1 * 512, nullptr);
+  run_bwd(r, mk_bwd(kGatedIN, s.z1, 512, 40, d.W1, s.st1, 512, W.gamma(nm[GN_DS1]), W.beta(nm[GN_DS1]), 1,
+                    gbuf(dA1, B, 40, d.W1, 256, 1), t1, t2, gGa(GN_DS1), gBe(GN_DS1), dz1, nullptr), "G ds1 bwd");
+  float* dA0 = a.takeT<float>(parity_elems(B, 80, d.T, 128));
+  {
+    const int Yp = 40, Xp = (d.T + 1) / 2;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const int p = ph * 2 + pw;
+        OutAddr o{dA0 + (long long)p * Yp * Xp * 128, (long long)4 * Yp * Xp * 128, (long long)Xp * 128, 128, 128, 0};
+        run_conv(r, plain_op(dz1.hi, dz1.lo, B, 40, d.W1, 512), W.bwd(cv[G_DS1]), taps_s2_bwd(5, 2, ph, pw),
+                 B, Yp, Xp, o, nullptr, nullptr, "G ds1 dgrad");
+      }
+  }
+  if (needWgrad)
+    run_wgrad(r, plain_op(dz1.hi, dz1.lo, B, 40, d.W1, 512), parity_op(s.A0.hi, s.A0.lo, B, 80, d.T, 128),
+              taps_s2_fwd(5, 2), nullptr, B, 40, d.W1, gW(G_DS1), "G ds1 wgrad");
+  // ---- stem
+  BfPair dz0 = take_pair(a, M0 * 256, nullptr);
+  run_bwd(r, mk_bwd(kGatedNoNorm, s.z0, 256, 80, d.T, Stat{nullptr, nullptr}, 0, nullptr, nullptr, 1,
+                    gbuf(dA0, B, 80, d.T, 128, 1), t1, t2, nullptr, nullptr, dz0, gB(G_STEM)),
+          "G stem bwd");
+  if (needWgrad)
+    run_wgrad(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 256), plain_op(s.X15.hi, s.X15.lo, B, 80, d.T, 64),
+              taps_s1(5, 1, 2, 0, 1), nullptr, B, 80, d.T, gW(G_STEM), "G stem wgrad");
+  if (dx) {
+    float* dX15 = a.takeT<float>(M0 * 64);
+    run_conv(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 256), W.bwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, -1), B, 80,
+             d.T, plain_out(dX15, 80, d.T, 64), nullptr, nullptr, "G stem dgrad");
+    if (r.ok) r.check(launch_col2im_g(dX15, mask, B, d.T, dx, st), "G col2im");
+  }
+  return r.ok ? 0 : 1;
+}
+
+// ================================================================================================
+// Discriminator
+namespace {
+
+struct DisDims {
+  int B, T, W1, W2, W3;
+  DisDims(int b, int t) : B(b), T(t) {
+    W1 = (T + 1) / 2;
+    W2 = (W1 + 1) / 2;
+    W3 = (W2 + 1) / 2;
+  }
+};
+struct DisSaved {
+  BfPair Xd; float* z0;
+  BfPair D0; float* z1; Stat st1;
+  BfPair D1; float* z2; Stat st2;
+  BfPair D2; float* z3; Stat st3;
+  BfPair D3;
+  long long total;
+};
+DisSaved plan_dis_saved(const DisDims& d, void* base, std::vector<SavedEntry>* layout) {
+  Arena a(base);
+  a.layout = layout;
+  DisSaved s{};
+  const long long M0 = (long long)d.B * 80 * d.T, M1 = (long long)d.B * 40 * d.W1,
+                  M2 = (long long)d.B * 20 * d.W2, M3 = (long long)d.B * 10 * d.W3;
+  s.Xd = take_pair(a, M0 * 64, "Xd");
+  s.z0 = a.takeT<float>(M0 * 128, "z0");
+  s.D0 = take_pair(a, parity_elems(d.B, 80, d.T, 128), "D0");
+  s.z1 = a.takeT<float>(M1 * 256, "z1");
+  s.st1 = take_stat(a, d.B * 256);
+  s.D1 = take_pair(a, parity_elems(d.B, 40, d.W1, 256), "D1");
+  s.z2 = a.takeT<float>(M2 * 512, "z2");
+  s.st2 = take_stat(a, d.B * 512);
+  s.D2 = take_pair(a, parity_elems(d.B, 20, d.W2, 512), "D2");
+  s.z3 = a.takeT<float>(M3 * 1024, "z3");
+  s.st3 = take_stat(a, d.B * 1024);
+  s.D3 = take_pair(a, M3 * 1024, "D3");
+  s.total = align_up(a.off, 256);
+  return s;
+}
+}  // namespace
+
+long long discriminator_saved_bytes(int B, int T) { return plan_dis_saved(DisDims(B, T), nullptr, nullptr).total; }
+std::vector<SavedEntry> discriminator_saved_layout(int B, int T) {
+  std::vector<SavedEntry> v;
+  plan_dis_saved(DisDims(B, T), nullptr, &v);
+  return v;
+}
+long long discriminator_fwd_ws_bytes(int B, int T) {
+  DisDims d(B, T);
+  return align_up((long long)B * 10 * d.W3 * 128 * 4, 256) + 256;
+}
+
+int discriminator_forward(const void* packed, const float* x, int B, int T, float* out, void* saved,
+                          void* ws, const RunCfg& rc) {
+  const ModelDesc& md = discriminator_desc();
+  const DisDims d(B, T);
+  DisSaved s = plan_dis_saved(d, saved, nullptr);
+  Weights W(packed, md);
+  Run r{rc};
+  cudaStream_t st = rc.stream;
+  const auto& cv = md.convs;
+  const auto& nm = md.norms;
+  if (d.T & 1) {
+    r.check(launch_fill_zero(s.D0.hi, parity_elems(B, 80, d.T, 128) * 2, st), "zero D0");
+    r.check(launch_fill_zero(s.D0.lo, parity_elems(B, 80, d.T, 128) * 2, st), "zero D0");
+  }
+  if (d.W1 & 1) {
+    r.check(launch_fill_zero(s.D1.hi, parity_elems(B, 40, d.W1, 256) * 2, st), "zero D1");
+    r.check(launch_fill_zero(s.D1.lo, parity_elems(B, 40, d.W1, 256) * 2, st), "zero D1");
+  }
+  if (d.W2 & 1) {
+    r.check(launch_fill_zero(s.D2.hi, parity_elems(B, 20, d.W2, 512) * 2, st), "zero D2");
+    r.check(launch_fill_zero(s.D2.lo, parity_elems(B, 20, d.W2, 512) * 2, st), "zero D2");
+  }
+  // convLayer1: 3x3 conv 1->128 + swish                                           model.py:290-295,344
+  r.check(launch_prep_d(x, B, T, s.Xd.hi, s.Xd.lo, st), "prep_d");
+  run_conv(r, plain_op(s.Xd.hi, s.Xd.lo, B, 80, T, 64), W.fwd(cv[D_STEM]), taps_one(), B, 80, T,
+           plain_out(s.z0, 80, T, 128), W.bias(cv[D_STEM]), nullptr, "D stem conv");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kSwishNoNorm, s.z0, 128, 80, T, Stat{nullptr, nullptr}, 0, nullptr,
+                                              nullptr, 1, nullptr, abuf(s.D0, nullptr, B, 80, T, 128, 1)), st), "D stem act");
+  // downSample1..3: 3x3 stride 2 conv + IN + swish                                 model.py:345-347
+  const TapList k33 = taps_s2_fwd(3, 1);
+  run_conv(r, parity_op(s.D0.hi, s.D0.lo, B, 80, T, 128), W.fwd(cv[D_DS1]), k33, B, 40, d.W1,
+           plain_out(s.z1, 40, d.W1, 256), W.bias(cv[D_DS1]), nullptr, "D ds1 conv");
+  if (r.ok) r.check(launch_stats(s.z1, 256, 40 * d.W1, B, 1, s.st1.mean, s.st1.rstd, st), "D ds1 stats");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z1, 256, 40, d.W1, s.st1, 256, W.gamma(nm[DN_DS1]),
+                                              W.beta(nm[DN_DS1]), 1, nullptr, abuf(s.D1, nullptr, B, 40, d.W1, 256, 1)), st), "D ds1 act");
+  run_conv(r, parity_op(s.D1.hi, s.D1.lo, B, 40, d.W1, 256), W.fwd(cv[D_DS2]), k33, B, 20, d.W2,
+           plain_out(s.z2, 20, d.W2, 512), W.bias(cv[D_DS2]), nullptr, "D ds2 conv");
+  if (r.ok) r.check(launch_stats(s.z2, 512, 20 * d.W2, B, 1, s.st2.mean, s.st2.rstd, st), "D ds2 stats");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[DN_DS2]),
+                                              W.beta(nm[DN_DS2]), 1, nullptr, abuf(s.D2, nullptr, B, 20, d.W2, 512, 1)), st), "D ds2 act");
+  run_conv(r, parity_op(s.D2.hi, s.D2.lo, B, 20, d.W2, 512), W.fwd(cv[D_DS3]), k33, B, 10, d.W3,
+           plain_out(s.z3, 10, d.W3, 1024), W.bias(cv[D_DS3]), nullptr, "D ds3 conv");
+  if (r.ok) r.check(launch_stats(s.z3, 1024, 10 * d.W3, B, 1, s.st3.mean, s.st3.rstd, st), "D ds3 stats");
+  if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z3, 1024, 10, d.W3, s.st3, 1024, W.gamma(nm[DN_DS3]),
+                                              W.beta(nm[DN_DS3]), 1, nullptr, abuf(s.D3, nullptr, B, 10, d.W3, 1024, 0)), st), "D ds3 act");
+  // outputConvLayer 1x3 1024->1 + sigmoid                                          model.py:323-327,348
+  Arena wa(ws);
+  float* P = wa.takeT<float>((long long)B * 10 * d.W3 * 128);
+  run_conv(r, plain_op(s.D3.hi, s.D3.lo, B, 10, d.W3, 1024), W.fwd(cv[D_HEAD]), taps_one(), B, 10, d.W3,
+           plain_out(P, 10, d.W3, 128), nullptr, nullptr, "D head gemm");
+  if (r.ok) r.check(launch_head_d_fwd(P, W.bias(cv[D_HEAD]), B, 10, d.W3, out, st), "D head sum");
+  return r.ok ? 0 : 1;
+}
+
+long long discriminator_bwd_ws_bytes(int B, int T) {
+  DisDims d(B, T);
+  const long long M0 = (long long)B * 80 * d.T, M1 = (long long)B * 40 * d.W1, M2 = (long long)B * 20 * d.W2,
+                  M3 = (long long)B * 10 * d.W3;
+  long long b = 0;
+  auto add = [&](long long bytes) { b = align_up(b, 256) + bytes; };
+  add((long long)B * 1024 * 4); add((long long)B * 1024 * 4);  // t1, t2
+  add(2 * 1024 * 4);                                           // affine-grad sink
+  add(M3 * 128 * 2); add(M3 * 128 * 2);                        // dP
+  add(M3 * 1024 * 4);                                          // dD3
+  add(M3 * 1024 * 2); add(M3 * 1024 * 2);                      // dz3
+  add(parity_elems(B, 20, d.W2, 512) * 4);                     // dD2
+  add(M2 * 512 * 2); add(M2 * 512 * 2);                        // dz2
+  add(parity_elems(B, 40, d.W1, 256) * 4);                     // dD1
+  add(M1 * 256 * 2); add(M1 * 256 * 2);                        // dz1
+  add(parity_elems(B, 80, d.T, 128) * 4);                      // dD0
+  add(M0 * 128 * 2); add(M0 * 128 * 2);                        // dz0
+  add(M0 * 64 * 4);                                            // dXd
+  return align_up(b, 256) + 4096;
+}
+
+int discriminator_backward(const void* packed, const void* saved, const float* out, const float* dout,
+                           int B, int T, float* dx, float* gblob, int needWgrad, void* ws,
+                           const RunCfg& rc) {
+  const ModelDesc& md = discriminator_desc();
+  const DisDims d(B, T);
+  DisSaved s = plan_dis_saved(d, const_cast<void*>(saved), nullptr);
+  Weights W(packed, md);
+  Run r{rc};
+  cudaStream_t st = rc.stream;
+  const auto& cv = md.convs;
+  const auto& nm = md.norms;
+  Arena a(ws);
+  const long long M0 = (long long)B * 80 * d.T, M1 = (long long)B * 40 * d.W1, M2 = (long long)B * 20 * d.W2,
+                  M3 = (long long)B * 10 * d.W3;
+  float* t1 = a.takeT<float>((long long)B * 1024);
+  float* t2 = a.takeT<float>((long long)B * 1024);
+  float* junk = a.takeT<float>(2 * 1024);
+  auto gW = [&](int ci) { return gblob + cv[ci].gW; };
+  auto gB = [&](int ci) -> float* { return needWgrad ? gblob + cv[ci].gB : nullptr; };
+  auto gGa = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gGamma : junk; };
+  auto gBe = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gBeta : junk + 1024; };
+  const TapList one = taps_one();
+  const TapList k33 = taps_s2_fwd(3, 1);
+
+  BfPair dP = take_pair(a, M3 * 128, nullptr);
+  r.check(launch_head_d_bwd(dout, out, B, 10, d.W3, dP.hi, dP.lo, gB(D_HEAD), st), "D head bwd");
+  float* dD3 = a.takeT<float>(M3 * 1024);
+  run_conv(r, plain_op(dP.hi, dP.lo, B, 10, d.W3, 128), W.bwd(cv[D_HEAD]), one, B, 10, d.W3,
+           plain_out(dD3, 10, d.W3, 1024), nullptr, nullptr, "D head dgrad");
+  if (needWgrad)
+    run_wgrad(r, plain_op(dP.hi, dP.lo, B, 10, d.W3, 128), plain_op(s.D3.hi, s.D3.lo, B, 10, d.W3, 1024), one,
+              nullptr, B, 10, d.W3, gW(D_HEAD), "D head wgrad");
+
+  struct Lvl { int ci, ni, Nz, Cin, Yo, Xo, Yi, Xi; const float* z; Stat st; BfPair xin; };
+  // ds3: z3 [B,10,W3,1024] <- D2 (20 x W2, 512);  ds2: z2 [B,20,W2,512] <- D1 (40 x W1, 256);
+  // ds1: z1 [B,40,W1,256] <- D0 (80 x T, 128)
+  Lvl lv[3] = {{D_DS3, DN_DS3, 1024, 512, 10, d.W3, 20, d.W2, s.z3, s.st3, s.D2},
+               {D_DS2, DN_DS2, 512, 256, 20, d.W2, 40, d.W1, s.z2, s.st2, s.D1},
+               {D_DS1, DN_DS1, 256, 128, 40, d.W1, 80, d.T, s.z1, s.st1, s.D0}};
+  float* dAct = dD3;   // gradient w.r.t. the level's activation output
+  int dActParity = 0;
+  for (int l = 0; l < 3; ++l) {
+    const Lvl& v = lv[l];
+    const long long Mo = (long long)B * v.Yo * v.Xo;
+    BfPair dz = take_pair(a, Mo * v.Nz, nullptr);
+    run_bwd(r, mk_bwd(kINSwish, v.z, v.Nz, v.Yo, v.Xo, v.st, v.Nz, W.gamma(nm[v.ni]), W.beta(nm[v.ni]), 1,
+                      gbuf(dAct, B, v.Yo, v.Xo, v.Nz, dActParity), t1, t2, gGa(v.ni), gBe(v.ni), dz, nullptr),
+            "D ds bwd");
+    float* dIn = a.takeT<float>(parity_elems(B, v.Yi, v.Xi, v.Cin));
+    const int Yp = (v.Yi + 1) / 2, Xp = (v.Xi + 1) / 2;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const int p = ph * 2 + pw;
+        OutAddr o{dIn + (long long)p * Yp * Xp * v.Cin, (long long)4 * Yp * Xp * v.Cin, (long long)Xp * v.Cin,
+                  v.Cin, v.Cin, 0};
+        run_conv(r, plain_op(dz.hi, dz.lo, B, v.Yo, v.Xo, v.Nz), W.bwd(cv[v.ci]), taps_s2_bwd(3, 1, ph, pw), B,
+                 Yp, Xp, o, nullptr, nullptr, "D ds dgrad");
+      }
+    if (needWgrad)
+      run_wgrad(r, plain_op(dz.hi, dz.lo, B, v.Yo, v.Xo, v.Nz), parity_op(v.xin.hi, v.xin.lo, B, v.Yi, v.Xi, v.Cin),
+                k33, nullptr, B, v.Yo, v.Xo, gW(v.ci), "D ds wgrad");
+    dAct = dIn;
+    dActParity = 1;
+  }
+  // stem
+  BfPair dz0 = take_pair(a, M0 * 128, nullptr);
+  run_bwd(r, mk_bwd(kSwishNoNorm, s.z0, 128, 80, d.T, Stat{nullptr, nullptr}, 0, nullptr, nullptr, 1,
+                    gbuf(dAct, B, 80, d.T, 128, 1), t1, t2, nullptr, nullptr, dz0, gB(D_STEM)),
+          "D stem bwd");
+  if (needWgrad)
+    run_wgrad(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 128), plain_op(s.Xd.hi, s.Xd.lo, B, 80, d.T, 64), one, nullptr,
+              B, 80, d.T, gW(D_STEM), "D stem wgrad");
+  if (dx) {
+    float* dXd = a.takeT<float>(M0 * 64);
+    run_conv(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 128), W.bwd(cv[D_STEM]), one, B, 80, d.T,
+             plain_out(dXd, 80, d.T, 64), nullptr, nullptr, "D stem dgrad");
+    if (r.ok) r.check(launch_col2im_d(dXd, B, d.T, dx, st), "D col2im");
+  }
+  (void)M1; (void)M2;
+  return r.ok ? 0 : 1;
+}
+
+}  // namespace mcgvc

@@ -1,0 +1,89 @@
+// Network-level description of the two models on the hot path and the host-side orchestration of
+// their forward / backward passes (one C call = one whole Generator or Discriminator pass on a
+// CUDA stream).  Reference: mask_cyclegan_vc/model.py:106-349.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "gemm_types.cuh"
+#include "layers.cuh"
+
+namespace mcgvc {
+
+// One tensor-core convolution (possibly the fusion of a conv and its gate conv, which read the
+// same input) and where its reference parameters / engine-layout copies / gradients live.
+struct ConvDesc {
+  std::string name;
+  int nParts;                 // 1, or 2 for conv || gates
+  long long wOff[2], bOff[2]; // float offsets in the reference-order flat parameter buffer
+  int refN, refC, refT;       // reference dims per part ([N][C][T])
+  int kind;                   // PackKind
+  int biasKind;               // VecKind
+  int Np, Cp, Tp, Cd;         // engine dims; Cd = GEMM-N of the data-gradient layout (0: none)
+  long long fHi, fLo, dHi, dLo;  // bf16 element offsets in the packed weight blob
+  long long biasEng;          // float offset in the packed small-vector area
+  long long gW, gB;           // float offsets in the engine-layout gradient blob
+};
+struct NormDesc {
+  std::string name;
+  int nParts;
+  long long gOff[2], bOff[2];
+  int n;                      // channels per part
+  int vecKind;
+  int Nstat;                  // nParts * n, or n/20 for the HC20 layer (affPeriod 20)
+  int affPeriod;
+  long long gammaEng, betaEng;   // float offsets in the packed small-vector area
+  long long gGamma, gBeta;       // float offsets in the gradient blob
+};
+
+struct ModelDesc {
+  std::vector<ConvDesc> convs;
+  std::vector<NormDesc> norms;
+  long long paramCount;       // floats in the reference-order flat buffer
+  long long packedBf16;       // bf16 elements in the packed blob (weights)
+  long long packedF32;        // floats in the packed blob (small vectors), placed after the bf16 area
+  long long gradFloats;       // floats in the engine-layout gradient blob
+  long long packed_bytes() const { return packedBf16 * 2 + packedF32 * 4; }
+};
+
+const ModelDesc& generator_desc();
+const ModelDesc& discriminator_desc();
+
+struct RunCfg {
+  cudaStream_t stream;
+  int backend;   // 0 = tcgen05/TMA kernels, 1 = SIMT checking kernels
+  int nPass;     // 3 = split-bf16 (parity mode), 1 = bf16 (fast mode)
+};
+
+// sizes (bytes) of the per-call buffers the caller provides
+long long generator_saved_bytes(int B, int T);
+long long generator_fwd_ws_bytes(int B, int T);
+long long generator_bwd_ws_bytes(int B, int T);
+long long discriminator_saved_bytes(int B, int T);
+long long discriminator_fwd_ws_bytes(int B, int T);
+long long discriminator_bwd_ws_bytes(int B, int T);
+
+int pack_model(const ModelDesc& d, const float* params, void* packed, const RunCfg& rc);
+int unpack_grads(const ModelDesc& d, const float* gblob, float* gradFlat, const RunCfg& rc);
+
+int generator_forward(const void* packed, const float* x, const float* mask, int B, int T,
+                      float* out, void* saved, void* ws, const RunCfg& rc);
+int generator_backward(const void* packed, const void* saved, const float* mask, const float* dout,
+                       int B, int T, float* dx, float* gblob, int needWgrad, void* ws,
+                       const RunCfg& rc);
+int discriminator_forward(const void* packed, const float* x, int B, int T, float* out, void* saved,
+                          void* ws, const RunCfg& rc);
+int discriminator_backward(const void* packed, const void* saved, const float* out,
+                           const float* dout, int B, int T, float* dx, float* gblob, int needWgrad,
+                           void* ws, const RunCfg& rc);
+
+// debug: named offsets (bytes) of tensors inside the saved blob, for layer-by-layer parity tests
+struct SavedEntry {
+  std::string name;
+  long long offset, bytes;
+};
+std::vector<SavedEntry> generator_saved_layout(int B, int T);
+std::vector<SavedEntry> discriminator_saved_layout(int B, int T);
+
+}  // namespace mcgvc

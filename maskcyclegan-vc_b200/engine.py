@@ -1,0 +1,201 @@
+"""ctypes binding of libmcgvc.so (C ABI in include/mcgvc.h).
+
+Raw device pointers and a cudaStream_t go down; nothing here falls back to PyTorch arithmetic.  If
+the shared library is missing or the tensors are not CUDA tensors, calls fail loudly.
+"""
+import ctypes
+import os
+
+import torch
+
+GENERATOR = 0
+DISCRIMINATOR = 1
+BACKEND_TCGEN05 = 0
+BACKEND_SIMT = 1
+PRECISION_PARITY = 3   # split-bf16 x3 (default; meets the 1e-3 parity gate)
+PRECISION_FAST = 1     # single bf16 pass
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcgvc.so")
+_lib = None
+
+_c_ll = ctypes.c_longlong
+_c_vp = ctypes.c_void_p
+_c_int = ctypes.c_int
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libmcgvc.so once.  Raises if it has not been built (see __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise EngineError(
+            "libmcgvc.so not found at %s: build it with `make -C maskcyclegan-vc_b200/csrc` "
+            "(or __graft_entry__.build()); there is no fallback path" % _LIB_PATH)
+    l = ctypes.CDLL(_LIB_PATH)
+    l.mcgvc_last_error.restype = ctypes.c_char_p
+    for name in ("mcgvc_param_count", "mcgvc_packed_bytes", "mcgvc_grad_blob_floats"):
+        getattr(l, name).restype = _c_ll
+        getattr(l, name).argtypes = [_c_int]
+    for name in ("mcgvc_saved_bytes", "mcgvc_fwd_workspace_bytes", "mcgvc_bwd_workspace_bytes"):
+        getattr(l, name).restype = _c_ll
+        getattr(l, name).argtypes = [_c_int, _c_int, _c_int]
+    l.mcgvc_pack_weights.argtypes = [_c_int, _c_vp, _c_vp, _c_vp]
+    l.mcgvc_unpack_grads.argtypes = [_c_int, _c_vp, _c_vp, _c_vp]
+    l.mcgvc_generator_forward.argtypes = [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]
+    l.mcgvc_generator_backward.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp,
+                                           _c_int, _c_vp, _c_vp]
+    l.mcgvc_discriminator_forward.argtypes = [_c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]
+    l.mcgvc_discriminator_backward.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp,
+                                               _c_int, _c_vp, _c_vp]
+    l.mcgvc_saved_layout.argtypes = [_c_int, _c_int, _c_int, _c_int, ctypes.c_char_p, _c_int,
+                                     ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]
+    _lib = l
+    return l
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EngineError("%s failed: %s" % (what, lib().mcgvc_last_error().decode()))
+
+
+def _ptr(t):
+    return _c_vp(t.data_ptr()) if t is not None else _c_vp(0)
+
+
+def _stream():
+    return _c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise EngineError("%s must be a CUDA tensor: the engine has no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise EngineError("%s must be float32 (got %s)" % (name, t.dtype))
+
+
+def set_backend(backend):
+    _check(lib().mcgvc_set_backend(backend), "set_backend")
+
+
+def set_precision(n_pass):
+    _check(lib().mcgvc_set_precision(n_pass), "set_precision")
+
+
+def get_precision():
+    return lib().mcgvc_get_precision()
+
+
+def param_count(model):
+    return lib().mcgvc_param_count(model)
+
+
+def packed_bytes(model):
+    return lib().mcgvc_packed_bytes(model)
+
+
+def grad_blob_floats(model):
+    return lib().mcgvc_grad_blob_floats(model)
+
+
+def generator_out_frames(T):
+    return lib().mcgvc_generator_out_frames(T)
+
+
+def discriminator_out_frames(T):
+    return lib().mcgvc_discriminator_out_frames(T)
+
+
+def _bytes(n, device):
+    return torch.empty(int(n), dtype=torch.uint8, device=device)
+
+
+def pack_weights(model, flat_params):
+    _require_cuda(flat_params, "parameters")
+    l = lib()
+    l.mcgvc_set_device(flat_params.device.index)
+    packed = _bytes(l.mcgvc_packed_bytes(model), flat_params.device)
+    _check(l.mcgvc_pack_weights(model, _ptr(flat_params), _ptr(packed), _stream()), "pack_weights")
+    return packed
+
+
+def unpack_grads(model, grad_blob, flat_grad):
+    l = lib()
+    l.mcgvc_set_device(flat_grad.device.index)
+    _check(l.mcgvc_unpack_grads(model, _ptr(grad_blob), _ptr(flat_grad), _stream()), "unpack_grads")
+
+
+def generator_forward(packed, x, mask):
+    """x, mask: (B, 80, T) fp32 CUDA.  Returns (out (B, 80, T'), saved blob)."""
+    _require_cuda(x, "x")
+    _require_cuda(mask, "mask")
+    if x.dim() != 3 or x.shape[1] != 80 or mask.shape != x.shape:
+        raise EngineError("Generator expects x and mask of shape (B, 80, T); got %s and %s"
+                          % (tuple(x.shape), tuple(mask.shape)))
+    l = lib()
+    B, _, T = x.shape
+    l.mcgvc_set_device(x.device.index)
+    out = torch.empty(B, 80, l.mcgvc_generator_out_frames(T), dtype=torch.float32, device=x.device)
+    saved = _bytes(l.mcgvc_saved_bytes(GENERATOR, B, T), x.device)
+    ws = _bytes(l.mcgvc_fwd_workspace_bytes(GENERATOR, B, T), x.device)
+    _check(l.mcgvc_generator_forward(_ptr(packed), _ptr(x), _ptr(mask), B, T, _ptr(out), _ptr(saved),
+                                     _ptr(ws), _stream()), "generator_forward")
+    return out, saved
+
+
+def generator_backward(packed, saved, mask, dout, B, T, need_dx, grad_blob, need_wgrad):
+    l = lib()
+    l.mcgvc_set_device(dout.device.index)
+    dx = torch.empty(B, 80, T, dtype=torch.float32, device=dout.device) if need_dx else None
+    ws = _bytes(l.mcgvc_bwd_workspace_bytes(GENERATOR, B, T), dout.device)
+    _check(l.mcgvc_generator_backward(_ptr(packed), _ptr(saved), _ptr(mask), _ptr(dout), B, T, _ptr(dx),
+                                      _ptr(grad_blob), 1 if need_wgrad else 0, _ptr(ws), _stream()),
+           "generator_backward")
+    return dx
+
+
+def discriminator_forward(packed, x):
+    """x: (B, 80, T) fp32 CUDA.  Returns (out (B, 1, 10, ceil(T/8)), saved blob)."""
+    _require_cuda(x, "x")
+    if x.dim() != 3 or x.shape[1] != 80:
+        raise EngineError("Discriminator expects x of shape (B, 80, T); got %s" % (tuple(x.shape),))
+    l = lib()
+    B, _, T = x.shape
+    l.mcgvc_set_device(x.device.index)
+    out = torch.empty(B, 1, 10, l.mcgvc_discriminator_out_frames(T), dtype=torch.float32, device=x.device)
+    saved = _bytes(l.mcgvc_saved_bytes(DISCRIMINATOR, B, T), x.device)
+    ws = _bytes(l.mcgvc_fwd_workspace_bytes(DISCRIMINATOR, B, T), x.device)
+    _check(l.mcgvc_discriminator_forward(_ptr(packed), _ptr(x), B, T, _ptr(out), _ptr(saved), _ptr(ws),
+                                         _stream()), "discriminator_forward")
+    return out, saved
+
+
+def discriminator_backward(packed, saved, out, dout, B, T, need_dx, grad_blob, need_wgrad):
+    l = lib()
+    l.mcgvc_set_device(dout.device.index)
+    dx = torch.empty(B, 80, T, dtype=torch.float32, device=dout.device) if need_dx else None
+    ws = _bytes(l.mcgvc_bwd_workspace_bytes(DISCRIMINATOR, B, T), dout.device)
+    _check(l.mcgvc_discriminator_backward(_ptr(packed), _ptr(saved), _ptr(out), _ptr(dout), B, T, _ptr(dx),
+                                          _ptr(grad_blob), 1 if need_wgrad else 0, _ptr(ws), _stream()),
+           "discriminator_backward")
+    return dx
+
+
+def saved_layout(model, B, T):
+    """[(name, byte offset, bytes)] of the named tensors inside a saved blob (tests only)."""
+    l = lib()
+    out = []
+    i = 0
+    while True:
+        name = ctypes.create_string_buffer(64)
+        off = _c_ll(0)
+        nb = _c_ll(0)
+        if l.mcgvc_saved_layout(model, B, T, i, name, 64, ctypes.byref(off), ctypes.byref(nb)) != 0:
+            break
+        out.append((name.value.decode(), off.value, nb.value))
+        i += 1
+    return out

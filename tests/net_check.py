@@ -1,0 +1,203 @@
+"""Whole-network parity report on a B200: engine Generator/Discriminator forward, layer-by-layer
+intermediates and all parameter / input gradients against the CPU oracle (same seed, same inputs).
+
+    python tests/net_check.py [--backend tc|simt|both] [--B 1] [--T 64]
+
+Prints one line per checked tensor; exits non-zero if a gate fails.  The pytest wrappers in
+tests/test_gpu_network.py call the same functions.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import maskcyclegan_oracle as O  # noqa: E402
+import mcgvc_loader  # noqa: E402
+
+PKG = mcgvc_loader.load()
+ENG = PKG.engine
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def saved_tensor(saved, layout, name, dtype, shape):
+    for n, off, nb in layout:
+        if n == name:
+            numel = int(np.prod(shape))
+            esz = 2 if dtype == torch.bfloat16 else 4
+            return saved[off:off + numel * esz].view(dtype).view(*shape)
+    raise KeyError(name)
+
+
+def from_parity(t, Y, X):
+    """[B,4,Yp,Xp,C] parity-split -> [B,Y,X,C]"""
+    B, _, Yp, Xp, C = t.shape
+    out = torch.zeros(B, 2 * Yp, 2 * Xp, C, dtype=t.dtype, device=t.device)
+    for ph in range(2):
+        for pw in range(2):
+            out[:, ph::2, pw::2] = t[:, ph * 2 + pw]
+    return out[:, :Y, :X]
+
+
+def build_models(seed=0):
+    torch.manual_seed(seed)
+    G = PKG.Generator()
+    D = PKG.Discriminator()
+    torch.manual_seed(seed)
+    gs = O.build_generator_state()
+    ds = O.build_discriminator_state()
+    return G.to("cuda"), D.to("cuda"), gs, ds
+
+
+def check_forward(G, D, gs, ds, B, T, verbose=True):
+    """Returns dict name -> relative error (engine vs oracle)."""
+    x, m, _, _ = O.synthetic_batch(B, T, seed=1234 + T + B, max_mask_len=min(25, max(2, T // 2)))
+    taps = {}
+    with torch.no_grad():
+        ref = O.generator_forward(gs, x, m, taps)
+        dtaps = {}
+        dref = O.discriminator_forward(ds, x, dtaps)
+    res = {}
+    xc, mc = x.cuda(), m.cuda()
+    packed = G._packed_weights()
+    out, saved = ENG.generator_forward(packed, xc, mc)
+    torch.cuda.synchronize()
+    layout = ENG.saved_layout(ENG.GENERATOR, B, T)
+    W1 = (T + 1) // 2
+    W2 = (W1 + 1) // 2
+    bf = torch.bfloat16
+
+    def nhwc(t):  # oracle NCHW -> NHWC
+        return t.permute(0, 2, 3, 1).contiguous()
+
+    A0 = from_parity(saved_tensor(saved, layout, "A0", bf, (B, 4, 40, (T + 1) // 2, 128)).float(), 80, T)
+    res["G.conv1(GLU)"] = relerr(A0, nhwc(taps["conv1"]))
+    A1 = from_parity(saved_tensor(saved, layout, "A1", bf, (B, 4, 20, (W1 + 1) // 2, 256)).float(), 40, W1)
+    res["G.downSample1"] = relerr(A1, nhwc(taps["downSample1"]))
+    A2 = saved_tensor(saved, layout, "A2", bf, (B, 20, W2, 256)).float()
+    res["G.downSample2"] = relerr(A2, nhwc(taps["downSample2"]))
+    R0 = saved_tensor(saved, layout, "R0", torch.float32, (B, W2, 256))
+    res["G.conv2dto1d"] = relerr(R0, taps["conv2dto1d"].permute(0, 2, 1))
+    R6 = saved_tensor(saved, layout, "R6", torch.float32, (B, W2, 256))
+    res["G.residualLayer6"] = relerr(R6, taps["residualLayer6"].permute(0, 2, 1))
+    U0 = saved_tensor(saved, layout, "U0", bf, (B, 20, W2, 256)).float()
+    res["G.conv1dto2d"] = relerr(U0, nhwc(taps["conv1dto2d"]))
+    U1 = saved_tensor(saved, layout, "U1", bf, (B, 40, 2 * W2, 256)).float()
+    res["G.upSample1"] = relerr(U1, nhwc(taps["upSample1"]))
+    U2 = saved_tensor(saved, layout, "U2", bf, (B, 80, 4 * W2, 128)).float()
+    res["G.upSample2"] = relerr(U2, nhwc(taps["upSample2"]))
+    res["G.out"] = relerr(out, ref)
+
+    dpacked = D._packed_weights()
+    dout, dsaved = ENG.discriminator_forward(dpacked, xc)
+    torch.cuda.synchronize()
+    dl = ENG.saved_layout(ENG.DISCRIMINATOR, B, T)
+    W3 = (W2 + 1) // 2
+    D0 = from_parity(saved_tensor(dsaved, dl, "D0", bf, (B, 4, 40, (T + 1) // 2, 128)).float(), 80, T)
+    res["D.convLayer1"] = relerr(D0, nhwc(dtaps["convLayer1"]))
+    D1 = from_parity(saved_tensor(dsaved, dl, "D1", bf, (B, 4, 20, (W1 + 1) // 2, 256)).float(), 40, W1)
+    res["D.downSample1"] = relerr(D1, nhwc(dtaps["downSample1"]))
+    D2 = from_parity(saved_tensor(dsaved, dl, "D2", bf, (B, 4, 10, (W2 + 1) // 2, 512)).float(), 20, W2)
+    res["D.downSample2"] = relerr(D2, nhwc(dtaps["downSample2"]))
+    D3 = saved_tensor(dsaved, dl, "D3", bf, (B, 10, W3, 1024)).float()
+    res["D.downSample3"] = relerr(D3, nhwc(dtaps["downSample3"]))
+    res["D.out"] = relerr(dout, dref)
+    if verbose:
+        for k, v in res.items():
+            print("  fwd %-20s rel err %.3e" % (k, v), flush=True)
+    return res
+
+
+def check_backward(G, D, gs, ds, B, T, verbose=True):
+    """config 2: loss = mean((1 - D(G(x, m)))^2); compares every parameter gradient and dx."""
+    x, m, _, _ = O.synthetic_batch(B, T, seed=77 + B)
+    gso = {k: v.clone().requires_grad_(True) for k, v in gs.items()}
+    dso = {k: v.clone().requires_grad_(True) for k, v in ds.items()}
+    xo = x.clone().requires_grad_(True)
+    fake = O.generator_forward(gso, xo, m)
+    d = O.discriminator_forward(dso, fake)
+    loss = torch.mean((1 - d) ** 2)
+    loss.backward()
+
+    for mod in (G, D):
+        mod.zero_grad(set_to_none=True)
+    xc = x.cuda().requires_grad_(True)
+    fake_e = G(xc, m.cuda())
+    d_e = D(fake_e)
+    loss_e = torch.mean((1 - d_e) ** 2)
+    loss_e.backward()
+    torch.cuda.synchronize()
+    res = {"loss": abs(loss_e.item() - loss.item()) / abs(loss.item()),
+           "fake": relerr(fake_e, fake), "dx": relerr(xc.grad, xo.grad)}
+
+    def cmp(mod, sd, tag):
+        flat_e, flat_o = [], []
+        worst = ("", 0.0)
+        # engine parameters() order vs oracle dict: match by name (aliases resolved)
+        named = dict(mod.named_parameters())
+        for name, p in named.items():
+            key = name.replace("convLayer.", "upSample2.") if name.startswith("convLayer.") else name
+            go = sd[key].grad
+            if go is None:
+                assert p.grad is None, "%s: engine produced a grad for an unused parameter" % name
+                continue
+            assert p.grad is not None, "%s: engine produced no grad" % name
+            ge = p.grad.detach().cpu()
+            flat_e.append(ge.flatten())
+            flat_o.append(go.flatten())
+            scale = go.norm().item()
+            e = (ge - go).norm().item() / max(scale, 1e-6)  # absolute floor: IN-fed conv biases have true grad 0
+            if verbose and (e > 1e-3):
+                print("    grad %-45s |g|=%.3e rel/abs-floored err %.3e" % (tag + name, scale, e))
+            if e > worst[1]:
+                worst = (name, e)
+        fe, fo = torch.cat(flat_e), torch.cat(flat_o)
+        return relerr(fe, fo), worst
+
+    res["G.grads(packed)"], wg = cmp(G, gso, "G.")
+    res["D.grads(packed)"], wd = cmp(D, dso, "D.")
+    if verbose:
+        for k, v in res.items():
+            print("  bwd %-20s rel err %.3e" % (k, v), flush=True)
+        print("  worst G tensor: %s %.3e | worst D tensor: %s %.3e" % (wg[0], wg[1], wd[0], wd[1]), flush=True)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backend", default="both")
+    ap.add_argument("--B", type=int, default=1)
+    ap.add_argument("--T", type=int, default=64)
+    ap.add_argument("--precision", type=int, default=3)
+    ap.add_argument("--skip-bwd", action="store_true")
+    args = ap.parse_args()
+    ENG.set_precision(args.precision)
+    G, D, gs, ds = build_models(0)
+    ok = True
+    tol = 1e-3 if args.precision == 3 else 5e-2
+    backends = ["simt", "tc"] if args.backend == "both" else [args.backend]
+    for be in backends:
+        ENG.set_backend(ENG.BACKEND_SIMT if be == "simt" else ENG.BACKEND_TCGEN05)
+        print("== backend %s, precision nPass=%d, B=%d T=%d" % (be, args.precision, args.B, args.T), flush=True)
+        r = check_forward(G, D, gs, ds, args.B, args.T)
+        ok &= r["G.out"] < tol and r["D.out"] < tol
+        if not args.skip_bwd:
+            rb = check_backward(G, D, gs, ds, args.B, args.T)
+            ok &= all(v < tol for v in rb.values())
+    ENG.set_backend(ENG.BACKEND_TCGEN05)
+    print("NET_CHECK", "PASS" if ok else "FAIL")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
