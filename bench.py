@@ -1,0 +1,347 @@
+"""Headline benchmark: mel-frames/sec of the full MaskCycleGAN-VC train step (train.py:186-299:
+10 Generator + 12 Discriminator forwards, two backwards, two Adam steps, gradient all-reduce when
+world > 1) on synthetic 80x64 mel batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
+`--impl reference` times the reference's algorithm on the host CPU (the oracle port of model.py +
+train.py step; the reference itself is Python and does not travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mel-frames/sec full CycleGAN train step (2G+2D fwd+bwd) 80x64"
+UNIT = "mel-frames/s"
+T_FRAMES = 64
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_tflops": d.get("bf16_tflops", 1590.0), "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "hbm_gbs": d.get("hbm_gbs", 6650.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def synthetic_batch_host(B, T, seed, max_mask_len=25):
+    """real_A/B ~ N(0,1); FIF masks as dataset/vc_dataset.py:51-55."""
+    g = torch.Generator().manual_seed(seed)
+    real_A = torch.randn(B, 80, T, generator=g)
+    real_B = torch.randn(B, 80, T, generator=g)
+    masks = []
+    for _ in range(2):
+        m = torch.ones(B, 80, T)
+        for b in range(B):
+            size = int(torch.randint(0, max_mask_len, (1,), generator=g))
+            start = int(torch.randint(0, T - size, (1,), generator=g))
+            m[b, :, start:start + size] = 0.0
+        masks.append(m)
+    return real_A, masks[0], real_B, masks[1]
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed regions (B200_PROFILING.md clocks line)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.proc = None
+        self.path = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self.path = tempfile.NamedTemporaryFile(prefix="mcgvc_clk_", suffix=".csv", delete=False).name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", uuid, "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx, pw = [], set(), None, []
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    parts = [p.strip() for p in line.split(",")]
+                    if len(parts) < 7:
+                        continue
+                    try:
+                        sm.append(float(parts[0]))
+                        mx = float(parts[1])
+                        pw.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # under load = top half of samples (the sampler also sees the idle edges)
+            top = sorted(sm)[len(sm) // 2:]
+            out.update({"sm_mhz": statistics.median(top), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                        "samples": len(sm), "power_w_max": max(pw) if pw else None})
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference Generator/Discriminator + train step on all host
+    threads, on a bounded sample of the same workload (batch 2 per step instead of 64)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import maskcyclegan_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.ref_batch
+    torch.manual_seed(0)
+    mods = [O.OracleGenerator(), O.OracleGenerator(), O.OracleDiscriminator(), O.OracleDiscriminator(),
+            O.OracleDiscriminator(), O.OracleDiscriminator()]
+    g_opt = torch.optim.Adam(list(mods[0].parameters()) + list(mods[1].parameters()), lr=2e-4, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam([p for m in mods[2:] for p in m.parameters()], lr=1e-4, betas=(0.5, 0.999))
+    batch = O.synthetic_batch(B, T_FRAMES, seed=1234)
+    steps = max(1, min(args.steps, args.ref_max_steps))
+    warm = max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        O.train_step(*mods, g_opt, d_opt, batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step(*mods, g_opt, d_opt, batch)
+    dt = (time.perf_counter() - t0) / steps
+    value = B * T_FRAMES / dt
+    sample = "oracle port of model.py+train.py:186-299, fp32, batch %d per step (bounded sample of the batch-64 workload), %d timed steps" % (B, steps)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "full MaskCycleGAN train step (train.py:186-299), 80x64, CPU", "batch_per_step": B, "frames": T_FRAMES},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(B, steps):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import maskcyclegan_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    mods = [O.OracleGenerator(), O.OracleGenerator(), O.OracleDiscriminator(), O.OracleDiscriminator(),
+            O.OracleDiscriminator(), O.OracleDiscriminator()]
+    g_opt = torch.optim.Adam(list(mods[0].parameters()) + list(mods[1].parameters()), lr=2e-4, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam([p for m in mods[2:] for p in m.parameters()], lr=1e-4, betas=(0.5, 0.999))
+    batch = O.synthetic_batch(B, T_FRAMES, seed=1234)
+    O.train_step(*mods, g_opt, d_opt, batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step(*mods, g_opt, d_opt, batch)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": B * T_FRAMES / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port, full train step at batch %d (bounded sample of batch-64 workload), 1 warm-up + %d timed steps, %.2f s/step" % (B, steps, dt)}
+
+
+# ------------------------------------------------------------------------------------------------
+def timed_steps(step_fn, n, world):
+    """barrier + synchronize on both sides, CUDA events on the current stream, max over ranks."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--impl", default="engine")
+    ap.add_argument("--precision", default="parity", choices=["parity", "fast"])
+    ap.add_argument("--lean", type=int, default=0)
+    ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--fast-steps", type=int, default=3, help="extra steps in the other precision mode (0 = skip)")
+    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--ref-max-steps", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import mcgvc_loader
+    pkg = mcgvc_loader.load()
+    eng = pkg.engine
+    from maskcyclegan_vc_b200 import trainstep as ts
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    B = args.batch
+    eng.lib()
+    eng.set_backend(eng.BACKEND_TCGEN05)
+    eng.set_precision(eng.PRECISION_PARITY if args.precision == "parity" else eng.PRECISION_FAST)
+    pkg.set_lean(bool(args.lean))
+
+    models = ts.build_models(pkg.Generator, pkg.Discriminator, dev, seed=0)
+    g_opt, d_opt = ts.build_optimizers(models)
+    sync = pkg.GradSync([models[:2], models[2:]]) if world > 1 else None
+
+    host = [t.pin_memory() for t in synthetic_batch_host(B, T_FRAMES, seed=1234 + rank)]
+    resident = [t.to(dev, non_blocking=True) for t in host]
+    h2d = sum(t.numel() * 4 for t in host)
+    losses = {}
+
+    def step_resident():
+        losses["g"], losses["d"] = ts.train_step(models, g_opt, d_opt, resident)
+
+    def step_e2e():
+        batch = [t.to(dev, non_blocking=True) for t in host]   # H2D from pinned memory, every step
+        g, d = ts.train_step(models, g_opt, d_opt, batch)
+        losses["gh"], losses["dh"] = g.item(), d.item()        # D2H read of the step's result (train.py:302-304)
+
+    for _ in range(W):
+        step_resident()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = eng.launch_count()
+    ms = timed_steps(step_resident, K, world)
+    launches = eng.launch_count() - l0
+    ms_e2e = timed_steps(step_e2e, K, world)
+    clocks = sampler.stop() if sampler else None
+
+    frames = world * B * T_FRAMES
+    value = frames * K / (ms * 1e-3)
+    e2e_value = frames * K / (ms_e2e * 1e-3)
+
+    # roofline: per-launch CUDA-event timing of the tensor-core kernels over extra steps
+    peaks = load_peaks()
+    eng.profile_enable(True)
+    for _ in range(max(args.profile_steps, 1)):
+        step_resident()
+    torch.cuda.synchronize()
+    prof = eng.profile_collect()
+    eng.profile_enable(False)
+    conv, wg = prof["conv"], prof["wgrad"]
+    peak = peaks["bf16_tflops_sustained"]
+    conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+    wg_tf = wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0
+    psteps = max(args.profile_steps, 1)
+    step_flops = (ts.STEP_FLOPS_LEAN_T64 if args.lean else ts.STEP_FLOPS_STRICT_T64) * B
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (implicit-GEMM fprop+dgrad, tcgen05)",
+                "achieved": conv_tf, "peak": peak, "unit": "TFLOP/s", "frac": conv_tf / peak,
+                "peak_source": "bf16_tflops_sustained, " + peaks["source"] + " (kernel timed inside a long step)",
+                "traffic": None,
+                "algorithmic_flops_per_launch": conv["flops"] / max(conv["launches"], 1),
+                "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
+                "launches_per_step": conv["launches"] / psteps,
+                "share_of_step": (conv["ms"] / psteps) / (ms / K),
+                "wgrad_kernel": {"achieved": wg_tf, "frac": wg_tf / peak, "launches_per_step": wg["launches"] / psteps,
+                                 "share_of_step": (wg["ms"] / psteps) / (ms / K)},
+                "whole_step": {"algorithmic_tflops": step_flops / (ms / K * 1e-3) / 1e12,
+                               "frac": step_flops / (ms / K * 1e-3) / 1e12 / peak},
+                "note": "parity mode issues 3 bf16 MMAs per algorithmic MAC (split-bf16); achieved counts algorithmic FLOPs once"
+                if args.precision == "parity" else "single bf16 pass"}
+
+    other = None
+    if args.fast_steps > 0:
+        other_mode = "fast" if args.precision == "parity" else "parity"
+        eng.set_precision(eng.PRECISION_FAST if other_mode == "fast" else eng.PRECISION_PARITY)
+        for _ in range(2):
+            step_resident()
+        ms_o = timed_steps(step_resident, args.fast_steps, world)
+        other = {"precision": other_mode, "value": frames * args.fast_steps / (ms_o * 1e-3), "unit": UNIT,
+                 "ms_per_step": ms_o / args.fast_steps,
+                 "note": "bf16 single pass: G output ~1e-2 rel. error vs fp32 reference (outside the 1e-3 gate); reported for context only"
+                 if other_mode == "fast" else "split-bf16 x3"}
+        eng.set_precision(eng.PRECISION_PARITY if args.precision == "parity" else eng.PRECISION_FAST)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.cpu_batch, args.cpu_steps)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 split (fp32 accumulate, fp32 activations/stats)" if args.precision == "parity" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "full MaskCycleGAN train step (train.py:186-299: 10 G fwd + 12 D fwd, 2 backward, 2 Adam), batch %d per GPU, 80x%d mel (BASELINE configs[3])" % (B, T_FRAMES),
+                       "batch_per_gpu": B, "global_batch": B * world, "frames": T_FRAMES,
+                       "precision_mode": args.precision, "lean": bool(args.lean),
+                       "parallelism": "dp%d" % world,
+                       "l2": "inputs larger than L2: ~%.1f GB of activations touched per step vs 126 MB L2" % (24.0 * B / 64.0),
+                       "grad_allreduce": "one NCCL all-reduce per optimizer step on the packed gradient arena" if world > 1 else "none (1 GPU)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "other_precision": other,
+            "losses_last_step": {"g": float(losses["gh"]), "d": float(losses["dh"])},
+        }
+        if sync is not None:
+            line["config"]["allreduces"] = sync.reductions
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,14 @@ int mcgvc_discriminator_backward(const void* packed, const void* saved, const fl
                                  const float* dout, int batch, int frames, float* dx,
                                  float* grad_blob, int need_wgrad, void* workspace, void* stream);
 
+/* Accounting for bench.py: number of kernels this library has launched so far, and optional
+ * per-launch CUDA-event timing of the two tensor-core kernels.  mcgvc_profile_collect synchronises
+ * and fills out6 = {conv ms, conv algorithmic FLOPs, conv launches, wgrad ms, wgrad FLOPs, wgrad
+ * launches} accumulated since the previous collect. */
+long long mcgvc_launch_count(void);
+int mcgvc_profile_enable(int on);
+int mcgvc_profile_collect(double* out6);
+
 /* Introspection for layer-by-layer parity tests: the index-th named tensor inside the saved blob.
  * Returns 0 and fills name/offset/bytes, or 1 when index is past the end. */
 int mcgvc_saved_layout(int model, int batch, int frames, int index, char* name, int name_cap,

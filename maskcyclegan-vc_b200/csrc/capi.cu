@@ -98,6 +98,16 @@ int mcgvc_discriminator_backward(const void* packed, const void* saved, const fl
   return discriminator_backward(packed, saved, out, dout, B, T, dx, gblob, need_wgrad, ws, cfg(stream));
 }
 
+long long mcgvc_launch_count(void) { return launch_count(); }
+int mcgvc_profile_enable(int on) { profile_enable(on != 0); return 0; }
+int mcgvc_profile_collect(double* out6) {
+  KernelProfile c, w;
+  profile_collect(&c, &w);
+  out6[0] = c.ms; out6[1] = c.flops; out6[2] = (double)c.launches;
+  out6[3] = w.ms; out6[4] = w.flops; out6[5] = (double)w.launches;
+  return 0;
+}
+
 int mcgvc_saved_layout(int model, int B, int T, int index, char* name, int name_cap,
                        long long* offset, long long* bytes) {
   if (!shape_ok(B, T)) return 1;

@@ -18,10 +18,13 @@
 #include "gemm_types.cuh"
 #include "ptx.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <cuda_bf16.h>
+#include <mutex>
+#include <vector>
 
 namespace mcgvc {
 
@@ -34,6 +37,61 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch accounting and optional per-launch event timing
+static std::atomic<long long> g_launches{0};
+cudaError_t launched() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+long long launch_count() { return g_launches.load(); }
+
+namespace {
+struct ProfRec { cudaEvent_t a, b; int kind; double flops; };
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+bool g_prof_on = false;
+std::mutex g_prof_mu;
+cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+void profile_enable(bool on) { g_prof_on = on; }
+bool profile_enabled() { return g_prof_on; }
+void profile_begin(int kind, double flops, cudaStream_t s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{get_event(), get_event(), kind, flops};
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+void profile_end(cudaStream_t s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, s);
+}
+void profile_collect(KernelProfile* conv, KernelProfile* wgrad) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  KernelProfile k[2] = {{0, 0, 0}, {0, 0, 0}};
+  for (ProfRec& r : g_prof) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      k[r.kind].ms += ms;
+      k[r.kind].flops += r.flops;
+      k[r.kind].launches += 1;
+    }
+    g_event_pool.push_back(r.a);
+    g_event_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  if (conv) *conv = k[0];
+  if (wgrad) *wgrad = k[1];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,8 +422,10 @@ static cudaError_t launch_conv_tc_t(const ConvGeom& g, cudaStream_t stream) {
   }
   const int total = (g.w.N / BLOCK_N) * g.tilesX * g.tilesY * g.tilesB;
   const int grid = total < num_sms() ? total : num_sms();
+  profile_begin(0, g.algoFlops, stream);
   conv_tc_kernel<BLOCK_N, NPASS><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
-  return cudaGetLastError();
+  profile_end(stream);
+  return launched();
 }
 
 // BLOCK_N selection: widest tile that divides N and nSplit (256 halves B-operand smem traffic per
@@ -447,7 +507,7 @@ cudaError_t launch_conv_simt(const ConvGeom& g, cudaStream_t stream) {
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   conv_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>(g);
-  return cudaGetLastError();
+  return launched();
 }
 
 }  // namespace mcgvc

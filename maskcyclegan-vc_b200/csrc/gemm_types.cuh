@@ -49,6 +49,7 @@ struct ConvGeom {
   const float* bias;    // [N] or null
   const float* addsrc;  // same addressing as out, or null
   int nPass;            // 1 = bf16 (hi only), 3 = split-bf16 (hi*hi + hi*lo + lo*hi)
+  double algoFlops;     // algorithmic FLOPs of this launch (real conv MACs x 2), for profiling
 };
 
 // Weight-gradient GEMM:  dW[w_t][n][c] += sum over positions (b,y,x) in this CTA's K-slice of
@@ -68,6 +69,7 @@ struct WgradGeom {
   int splitK;
   float* dw;             // [T][N][C] fp32, accumulated with atomics
   int nPass;
+  double algoFlops;
 };
 
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);
@@ -78,6 +80,22 @@ cudaError_t launch_wgrad_simt(const WgradGeom& g, cudaStream_t stream);
 // Fill tile counts / box shape for a position grid (B, Y, X): picks BX*BY*BB == boxPositions
 // minimising padded work. Returns false if impossible.
 bool choose_box(int B, int Y, int X, int boxPositions, int* BX, int* BY, int* BB);
+
+// Every kernel launch in the library goes through launched(): counts it and returns the launch status.
+cudaError_t launched();
+long long launch_count();
+
+// Optional per-launch CUDA-event timing of the two tensor-core kernels (bench.py roofline).
+struct KernelProfile {
+  double ms;          // summed launch durations
+  double flops;       // summed algorithmic FLOPs
+  long long launches;
+};
+void profile_enable(bool on);
+bool profile_enabled();
+void profile_begin(int kind, double flops, cudaStream_t s);  // kind 0 = conv, 1 = wgrad
+void profile_end(cudaStream_t s);
+void profile_collect(KernelProfile* conv, KernelProfile* wgrad);  // synchronises, then resets
 
 const char* last_error();
 void set_error(const char* fmt, ...);

@@ -96,7 +96,7 @@ cudaError_t launch_stats(const float* z, int Nz, int P, int nImg, int groups, fl
   const int Nstat = Nz / groups;
   dim3 grid((Nstat + 31) / 32, nImg);
   stats_kernel<<<grid, 256, 0, s>>>(z, Nz, P, groups, Nstat, mean, rstd);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -195,7 +195,7 @@ cudaError_t launch_apply_fwd(const ApplyArgs& a, cudaStream_t s) {
     case kINSwishShuffle: apply_fwd_kernel<kINSwishShuffle><<<g, 256, 0, s>>>(a); break;
     default: set_error("apply_fwd: bad mode %d", a.mode); return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
+  return launched();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -286,7 +286,7 @@ cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
     case kSwishNoNorm: return cudaSuccess;  // nothing to reduce
     default: set_error("apply_bwd_reduce: bad mode %d", a.mode); return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
+  return launched();
 }
 
 // Backward, pass 2: dz = rstd*gamma*(dy - t1/Np - xhat*t2/Np) split into bf16 hi/lo (operand of the
@@ -409,7 +409,7 @@ cudaError_t launch_apply_bwd(const ApplyBwdArgs& a, cudaStream_t s) {
     case kINSwishShuffle: apply_bwd_kernel<kINSwishShuffle><<<g, 256, 0, s>>>(a); break;
     default: set_error("apply_bwd: bad mode %d", a.mode); return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
+  return launched();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -445,7 +445,7 @@ cudaError_t launch_prep_g(const float* x, const float* mask, int B, int T, __nv_
                           __nv_bfloat16* lo, cudaStream_t s) {
   const long long total = (long long)B * 80 * T * 16;
   prep_g_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, mask, B, T, hi, lo);
-  return cudaGetLastError();
+  return launched();
 }
 
 // Discriminator stem (model.py:290-294): Xd[b,h,w, kh*3+kw] = x[b,h+kh-1,w+kw-1]; 9 of 64 channels.
@@ -474,7 +474,7 @@ cudaError_t launch_prep_d(const float* x, int B, int T, __nv_bfloat16* hi, __nv_
                           cudaStream_t s) {
   const long long total = (long long)B * 80 * T * 16;
   prep_d_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, B, T, hi, lo);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -505,7 +505,7 @@ __global__ void head_g_fwd_kernel(const float* __restrict__ P, const float* __re
 cudaError_t launch_head_g_fwd(const float* P, const float* bias, int B, int Y, int X, float* out,
                               cudaStream_t s) {
   head_g_fwd_kernel<<<grid_for((long long)B * Y * X, 128), 128, 0, s>>>(P, bias, B, Y, X, out);
-  return cudaGetLastError();
+  return launched();
 }
 
 // dP[(b,y',x'), t=(kh,kw)] = dout[b, y'-kh+2, x'-kw+7]; columns >= 75 are zero.  dbias += sum dout.
@@ -541,7 +541,7 @@ cudaError_t launch_head_g_bwd(const float* dout, int B, int Y, int X, __nv_bfloa
                               __nv_bfloat16* lo, float* dbias, cudaStream_t s) {
   head_g_bwd_kernel<<<grid_for((long long)B * Y * X * 32, 256), 256, 0, s>>>(dout, B, Y, X, hi, lo,
                                                                            dbias);
-  return cudaGetLastError();
+  return launched();
 }
 
 // Discriminator head (model.py:323-327,348): 1x3 conv, pad (0,1), then sigmoid.
@@ -563,7 +563,7 @@ __global__ void head_d_fwd_kernel(const float* __restrict__ P, const float* __re
 cudaError_t launch_head_d_fwd(const float* P, const float* bias, int B, int Y, int X, float* out,
                               cudaStream_t s) {
   head_d_fwd_kernel<<<grid_for((long long)B * Y * X, 128), 128, 0, s>>>(P, bias, B, Y, X, out);
-  return cudaGetLastError();
+  return launched();
 }
 __global__ void head_d_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                   int B, int Y, int X, __nv_bfloat16* __restrict__ hi,
@@ -600,7 +600,7 @@ cudaError_t launch_head_d_bwd(const float* dout, const float* out, int B, int Y,
                               __nv_bfloat16* hi, __nv_bfloat16* lo, float* dbias, cudaStream_t s) {
   head_d_bwd_kernel<<<grid_for((long long)B * Y * X * 32, 256), 256, 0, s>>>(dout, out, B, Y, X, hi,
                                                                            lo, dbias);
-  return cudaGetLastError();
+  return launched();
 }
 
 // Stem input gradients: fold the operand gradient back onto the input grid.
@@ -623,7 +623,7 @@ __global__ void col2im_g_kernel(const float* __restrict__ dX, const float* __res
 cudaError_t launch_col2im_g(const float* dX15, const float* mask, int B, int T, float* dx,
                             cudaStream_t s) {
   col2im_g_kernel<<<grid_for((long long)B * 80 * T, 128), 128, 0, s>>>(dX15, mask, B, T, dx);
-  return cudaGetLastError();
+  return launched();
 }
 //   Discriminator: dx[b,h,w] = sum_{kh,kw} dXd[(b,h-kh+1,w-kw+1), kh*3+kw]
 __global__ void col2im_d_kernel(const float* __restrict__ dX, int B, int T, float* __restrict__ dx) {
@@ -647,7 +647,7 @@ __global__ void col2im_d_kernel(const float* __restrict__ dX, int B, int T, floa
 }
 cudaError_t launch_col2im_d(const float* dXd, int B, int T, float* dx, cudaStream_t s) {
   col2im_d_kernel<<<grid_for((long long)B * 80 * T, 128), 128, 0, s>>>(dXd, B, T, dx);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -694,7 +694,7 @@ __global__ void pack_weight_kernel(const PackArgs a) {
 cudaError_t launch_pack_weight(const PackArgs& a, cudaStream_t s) {
   const long long total = (long long)a.N * a.C * a.T;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launched();
 }
 
 __global__ void unpack_wgrad_kernel(const PackArgs a, const float* __restrict__ dw,
@@ -714,7 +714,7 @@ cudaError_t launch_unpack_wgrad(const PackArgs& a, const float* dw_engine, float
                                 cudaStream_t s) {
   const long long total = (long long)a.N * a.C * a.T;
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, dw_engine, dref);
-  return cudaGetLastError();
+  return launched();
 }
 
 __device__ __forceinline__ int vec_map(int kind, int i, int n) {
@@ -734,11 +734,11 @@ __global__ void unpack_vec_kernel(int kind, const float* __restrict__ eng, int n
 }
 cudaError_t launch_pack_vec(int kind, const float* ref, int n, float* eng, cudaStream_t s) {
   pack_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(kind, ref, n, eng);
-  return cudaGetLastError();
+  return launched();
 }
 cudaError_t launch_unpack_vec(int kind, const float* eng, int n, float* dref, cudaStream_t s) {
   unpack_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(kind, eng, n, dref);
-  return cudaGetLastError();
+  return launched();
 }
 
 cudaError_t launch_fill_zero(void* p, size_t bytes, cudaStream_t s) {

@@ -308,7 +308,8 @@ OutAddr plain_out(float* out, int Y, int X, int N) {
 }
 
 void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& taps, int oB, int oY,
-              int oX, const OutAddr& o, const float* bias, const float* addsrc, const char* what) {
+              int oX, const OutAddr& o, const float* bias, const float* addsrc, const char* what,
+              double algoFrac = 1.0) {
   if (!r.ok) return;
   ConvGeom g{};
   g.a = a;
@@ -324,11 +325,13 @@ void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& t
   g.sB = o.sB; g.sY = o.sY; g.sX = o.sX; g.nSplit = o.nSplit; g.sNhi = o.sNhi;
   g.out = o.out; g.bias = bias; g.addsrc = addsrc;
   g.nPass = r.rc.nPass;
+  g.algoFlops = 2.0 * oB * oY * oX * (double)w.N * taps.n * a.C * algoFrac;
   r.check(r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream), what);
 }
 
 void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList& xtaps,
-               const TapList* ztaps, int pB, int pY, int pX, float* dw, const char* what) {
+               const TapList* ztaps, int pB, int pY, int pX, float* dw, const char* what,
+               double algoFrac = 1.0) {
   if (!r.ok) return;
   WgradGeom g{};
   g.dz = dz;
@@ -355,6 +358,7 @@ void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList&
   g.splitK = (int)sk;
   g.dw = dw;
   g.nPass = r.rc.nPass;
+  g.algoFlops = 2.0 * pB * pY * pX * (double)g.N * g.C * xtaps.n * algoFrac;
   r.check(r.rc.backend == 0 ? launch_wgrad_tc(g, r.rc.stream) : launch_wgrad_simt(g, r.rc.stream), what);
 }
 
@@ -588,7 +592,7 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   // stem: stack(x*mask, mask) -> 5x15 conv || gates -> a * sigmoid(g)            model.py:241-242
   r.check(launch_prep_g(x, mask, B, T, s.X15.hi, s.X15.lo, st), "prep_g");
   run_conv(r, plain_op(s.X15.hi, s.X15.lo, B, 80, T, 64), W.fwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, 1),
-           B, 80, T, plain_out(s.z0, 80, T, 256), W.bias(cv[G_STEM]), nullptr, "G stem conv");
+           B, 80, T, plain_out(s.z0, 80, T, 256), W.bias(cv[G_STEM]), nullptr, "G stem conv", 150.0 / 320.0);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedNoNorm, s.z0, 256, 80, T, Stat{nullptr, nullptr}, 0,
                                               nullptr, nullptr, 1, nullptr,
                                               abuf(s.A0, nullptr, B, 80, T, 128, 1)), st), "G stem glu");
@@ -660,7 +664,7 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   Arena wa(ws);
   float* P = wa.takeT<float>((long long)B * 80 * d.X2 * 128);
   run_conv(r, plain_op(s.U2.hi, s.U2.lo, B, 80, d.X2, 128), W.fwd(cv[G_HEAD]), taps_one(), B, 80, d.X2,
-           plain_out(P, 80, d.X2, 128), nullptr, nullptr, "G head gemm");
+           plain_out(P, 80, d.X2, 128), nullptr, nullptr, "G head gemm", 75.0 / 128.0);
   if (r.ok) r.check(launch_head_g_fwd(P, W.bias(cv[G_HEAD]), B, 80, d.X2, out, st), "G head sum");
   return r.ok ? 0 : 1;
 }
@@ -724,10 +728,10 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   r.check(launch_head_g_bwd(dout, B, 80, d.X2, dP.hi, dP.lo, gB(G_HEAD), st), "G head bwd");
   float* dU2 = a.takeT<float>(M8 * 128);
   run_conv(r, plain_op(dP.hi, dP.lo, B, 80, d.X2, 128), W.bwd(cv[G_HEAD]), one, B, 80, d.X2,
-           plain_out(dU2, 80, d.X2, 128), nullptr, nullptr, "G head dgrad");
+           plain_out(dU2, 80, d.X2, 128), nullptr, nullptr, "G head dgrad", 75.0 / 128.0);
   if (needWgrad)
     run_wgrad(r, plain_op(dP.hi, dP.lo, B, 80, d.X2, 128), plain_op(s.U2.hi, s.U2.lo, B, 80, d.X2, 128),
-              one, nullptr, B, 80, d.X2, gW(G_HEAD), "G head wgrad");
+              one, nullptr, B, 80, d.X2, gW(G_HEAD), "G head wgrad", 75.0 / 128.0);
   // ---- upSample2
   const TapList k55f = taps_s1(5, 5, 2, 2, 1), k55b = taps_s1(5, 5, 2, 2, -1);
   BfPair dz8 = take_pair(a, M7 * 512, nullptr);
@@ -857,11 +861,11 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
           "G stem bwd");
   if (needWgrad)
     run_wgrad(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 256), plain_op(s.X15.hi, s.X15.lo, B, 80, d.T, 64),
-              taps_s1(5, 1, 2, 0, 1), nullptr, B, 80, d.T, gW(G_STEM), "G stem wgrad");
+              taps_s1(5, 1, 2, 0, 1), nullptr, B, 80, d.T, gW(G_STEM), "G stem wgrad", 150.0 / 320.0);
   if (dx) {
     float* dX15 = a.takeT<float>(M0 * 64);
     run_conv(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 256), W.bwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, -1), B, 80,
-             d.T, plain_out(dX15, 80, d.T, 64), nullptr, nullptr, "G stem dgrad");
+             d.T, plain_out(dX15, 80, d.T, 64), nullptr, nullptr, "G stem dgrad", 150.0 / 320.0);
     if (r.ok) r.check(launch_col2im_g(dX15, mask, B, d.T, dx, st), "G col2im");
   }
   return r.ok ? 0 : 1;
@@ -946,7 +950,7 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
   // convLayer1: 3x3 conv 1->128 + swish                                           model.py:290-295,344
   r.check(launch_prep_d(x, B, T, s.Xd.hi, s.Xd.lo, st), "prep_d");
   run_conv(r, plain_op(s.Xd.hi, s.Xd.lo, B, 80, T, 64), W.fwd(cv[D_STEM]), taps_one(), B, 80, T,
-           plain_out(s.z0, 80, T, 128), W.bias(cv[D_STEM]), nullptr, "D stem conv");
+           plain_out(s.z0, 80, T, 128), W.bias(cv[D_STEM]), nullptr, "D stem conv", 9.0 / 64.0);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kSwishNoNorm, s.z0, 128, 80, T, Stat{nullptr, nullptr}, 0, nullptr,
                                               nullptr, 1, nullptr, abuf(s.D0, nullptr, B, 80, T, 128, 1)), st), "D stem act");
   // downSample1..3: 3x3 stride 2 conv + IN + swish                                 model.py:345-347
@@ -970,7 +974,7 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
   Arena wa(ws);
   float* P = wa.takeT<float>((long long)B * 10 * d.W3 * 128);
   run_conv(r, plain_op(s.D3.hi, s.D3.lo, B, 10, d.W3, 1024), W.fwd(cv[D_HEAD]), taps_one(), B, 10, d.W3,
-           plain_out(P, 10, d.W3, 128), nullptr, nullptr, "D head gemm");
+           plain_out(P, 10, d.W3, 128), nullptr, nullptr, "D head gemm", 3.0 / 128.0);
   if (r.ok) r.check(launch_head_d_fwd(P, W.bias(cv[D_HEAD]), B, 10, d.W3, out, st), "D head sum");
   return r.ok ? 0 : 1;
 }
@@ -1024,10 +1028,10 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
   r.check(launch_head_d_bwd(dout, out, B, 10, d.W3, dP.hi, dP.lo, gB(D_HEAD), st), "D head bwd");
   float* dD3 = a.takeT<float>(M3 * 1024);
   run_conv(r, plain_op(dP.hi, dP.lo, B, 10, d.W3, 128), W.bwd(cv[D_HEAD]), one, B, 10, d.W3,
-           plain_out(dD3, 10, d.W3, 1024), nullptr, nullptr, "D head dgrad");
+           plain_out(dD3, 10, d.W3, 1024), nullptr, nullptr, "D head dgrad", 3.0 / 128.0);
   if (needWgrad)
     run_wgrad(r, plain_op(dP.hi, dP.lo, B, 10, d.W3, 128), plain_op(s.D3.hi, s.D3.lo, B, 10, d.W3, 1024), one,
-              nullptr, B, 10, d.W3, gW(D_HEAD), "D head wgrad");
+              nullptr, B, 10, d.W3, gW(D_HEAD), "D head wgrad", 3.0 / 128.0);
 
   struct Lvl { int ci, ni, Nz, Cin, Yo, Xo, Yi, Xi; const float* z; Stat st; BfPair xin; };
   // ds3: z3 [B,10,W3,1024] <- D2 (20 x W2, 512);  ds2: z2 [B,20,W2,512] <- D1 (40 x W1, 256);
@@ -1067,11 +1071,11 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
           "D stem bwd");
   if (needWgrad)
     run_wgrad(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 128), plain_op(s.Xd.hi, s.Xd.lo, B, 80, d.T, 64), one, nullptr,
-              B, 80, d.T, gW(D_STEM), "D stem wgrad");
+              B, 80, d.T, gW(D_STEM), "D stem wgrad", 9.0 / 64.0);
   if (dx) {
     float* dXd = a.takeT<float>(M0 * 64);
     run_conv(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 128), W.bwd(cv[D_STEM]), one, B, 80, d.T,
-             plain_out(dXd, 80, d.T, 64), nullptr, nullptr, "D stem dgrad");
+             plain_out(dXd, 80, d.T, 64), nullptr, nullptr, "D stem dgrad", 9.0 / 64.0);
     if (r.ok) r.check(launch_col2im_d(dXd, B, d.T, dx, st), "D col2im");
   }
   (void)M1; (void)M2;

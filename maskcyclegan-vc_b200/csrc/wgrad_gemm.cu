@@ -229,9 +229,11 @@ static cudaError_t launch_wgrad_tc_t(const WgradGeom& g, cudaStream_t stream) {
     attr_set = true;
   }
   const long long grid = (long long)g.nTaps * (g.N / 128) * (g.C / CTILE) * g.splitK;
+  profile_begin(1, g.algoFlops, stream);
   wgrad_tc_kernel<CTILE, NPASS><<<(unsigned)grid, 256, Cfg::kSmemBytes, stream>>>(tmZh, tmZl, tmXh,
                                                                                  tmXl, g);
-  return cudaGetLastError();
+  profile_end(stream);
+  return launched();
 }
 
 cudaError_t launch_wgrad_tc(const WgradGeom& g, cudaStream_t stream) {
@@ -294,7 +296,7 @@ cudaError_t launch_wgrad_simt(const WgradGeom& g, cudaStream_t stream) {
   const long long total = (long long)g.nTaps * g.N * g.C;
   const int threads = 128;
   wgrad_simt_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(g);
-  return cudaGetLastError();
+  return launched();
 }
 
 }  // namespace mcgvc

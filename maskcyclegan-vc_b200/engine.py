@@ -199,3 +199,22 @@ def saved_layout(model, B, T):
         out.append((name.value.decode(), off.value, nb.value))
         i += 1
     return out
+
+
+def launch_count():
+    """Number of kernels libmcgvc.so has launched in this process so far."""
+    l = lib()
+    l.mcgvc_launch_count.restype = _c_ll
+    return l.mcgvc_launch_count()
+
+
+def profile_enable(on):
+    lib().mcgvc_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """{'conv': {ms, flops, launches}, 'wgrad': {...}} accumulated since the last collect."""
+    buf = (ctypes.c_double * 6)()
+    lib().mcgvc_profile_collect(buf)
+    return {"conv": {"ms": buf[0], "flops": buf[1], "launches": int(buf[2])},
+            "wgrad": {"ms": buf[3], "flops": buf[4], "launches": int(buf[5])}}

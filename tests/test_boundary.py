@@ -1,0 +1,100 @@
+"""CPU: the drop-in boundary (module protocol, state_dict wire format, C ABI surface)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import maskcyclegan_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.engine.lib()
+    header = open(os.path.join(ROOT, "include", "mcgvc.h")).read()
+    names = sorted(set(re.findall(r"\b(mcgvc_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libmcgvc.so does not export %s" % n
+
+
+def test_model_tables_match_reference_counts(pkg):
+    e = pkg.engine
+    assert e.param_count(e.GENERATOR) == 24537729
+    assert e.param_count(e.DISCRIMINATOR) == 16691713
+    assert e.generator_out_frames(64) == 64 and e.generator_out_frames(65) == 68 and e.generator_out_frames(97) == 100
+    assert e.discriminator_out_frames(64) == 8 and e.discriminator_out_frames(65) == 9
+
+
+def test_state_dict_wire_format_and_seeded_init(pkg):
+    torch.manual_seed(11)
+    G, D = pkg.Generator(), pkg.Discriminator()
+    torch.manual_seed(11)
+    gs, ds = O.build_generator_state(), O.build_discriminator_state()
+    want = O.reference_state_dict_keys_generator(gs)
+    sd = G.state_dict()
+    assert list(sd.keys()) == list(want.keys()) and len(sd) == 114
+    assert all(torch.equal(sd[k], want[k]) for k in want)
+    assert sd["convLayer.0.weight"].data_ptr() == sd["upSample2.0.weight"].data_ptr()
+    dsd = D.state_dict()
+    assert list(dsd.keys()) == list(ds.keys()) and len(dsd) == 20
+    assert all(torch.equal(dsd[k], ds[k]) for k in ds)
+    assert type(G).__name__ == "Generator" and type(D).__name__ == "Discriminator"
+    with pytest.raises(AttributeError):
+        G.module  # model_saver.py:58-63 relies on this
+
+
+def test_parameters_are_views_of_one_flat_buffer_and_survive_to(pkg):
+    G = pkg.Generator(torch.Size([80, 64]), 256)
+    params = list(G.parameters())
+    assert len(params) == 110
+    assert sum(p.numel() for p in params) == G._flat.numel()
+    base = G._flat.data_ptr()
+    off = 0
+    for p in params:
+        assert p.data_ptr() == base + 4 * off
+        off += p.numel()
+    ids = [id(p) for p in params]
+    sd_before = {k: v.clone() for k, v in G.state_dict().items()}
+    assert G.to("cpu") is G                       # ModelSaver.save round trip (model_saver.py:64,74)
+    assert [id(p) for p in G.parameters()] == ids  # optimizer references stay valid
+    assert all(torch.equal(v, sd_before[k]) for k, v in G.state_dict().items())
+    assert next(G.parameters()).data_ptr() == G._flat.data_ptr()
+    G2 = pkg.Generator()
+    G2.load_state_dict(sd_before, strict=True)
+    assert all(torch.equal(v, sd_before[k]) for k, v in G2.state_dict().items())
+    assert G2.conv1.weight.data_ptr() == G2._flat.data_ptr()
+
+
+def test_no_cpu_fallback(pkg):
+    G, D = pkg.Generator(), pkg.Discriminator()
+    x = torch.zeros(1, 80, 64)
+    with pytest.raises(pkg.engine.EngineError):
+        G(x, torch.ones_like(x))
+    with pytest.raises(pkg.engine.EngineError):
+        D(x)
+    with pytest.raises(ValueError):
+        pkg.Generator((64, 64), 256)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "maskcyclegan-vc_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "maskcyclegan_oracle" not in src and "oracle/" not in src, f
+
+
+def test_shim_overrides_reference_module_path():
+    import subprocess
+    import sys
+    shim = os.path.join(ROOT, "maskcyclegan-vc_b200", "shim")
+    code = ("import mask_cyclegan_vc.model as m, sys; "
+            "print(m.__file__); print(m.Generator.__module__)")
+    env = dict(os.environ, PYTHONPATH=shim + os.pathsep + "/root/reference")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+    assert "shim" in out.splitlines()[0]
+    assert "maskcyclegan_vc_b200" in out.splitlines()[1]
