@@ -22,12 +22,13 @@ extern "C" {
 #define MCGVC_BACKEND_TCGEN05 0   /* tcgen05 + TMA kernels (the product path) */
 #define MCGVC_BACKEND_SIMT 1      /* plain CUDA checking kernels (tests / debugging only) */
 #define MCGVC_PRECISION_PARITY 3  /* split-bf16 x3: Ah*Wh + Ah*Wl + Al*Wh, fp32 accumulate */
+#define MCGVC_PRECISION_MIXED 2   /* forward split-bf16 x3 (output parity), backward single bf16 */
 #define MCGVC_PRECISION_FAST 1    /* single bf16 pass */
 
 const char* mcgvc_last_error(void);
 int mcgvc_set_device(int device);
 int mcgvc_set_backend(int backend);
-int mcgvc_set_precision(int n_pass);
+int mcgvc_set_precision(int mode);
 int mcgvc_get_precision(void);
 
 /* Model geometry.  Replaces Generator.__init__ / Discriminator.__init__ bookkeeping

@@ -7,9 +7,13 @@
 using namespace mcgvc;
 
 static int g_backend = MCGVC_BACKEND_TCGEN05;
-static int g_npass = MCGVC_PRECISION_PARITY;
+static int g_precision = MCGVC_PRECISION_PARITY;
 
-static RunCfg cfg(void* stream) { return RunCfg{(cudaStream_t)stream, g_backend, g_npass}; }
+// parity: every GEMM split-bf16 x3; fast: every GEMM single bf16; mixed: forward x3, backward x1
+static RunCfg cfg(void* stream, bool backward = false) {
+  int np = g_precision == MCGVC_PRECISION_PARITY ? 3 : (g_precision == MCGVC_PRECISION_FAST ? 1 : (backward ? 1 : 3));
+  return RunCfg{(cudaStream_t)stream, g_backend, np};
+}
 static const ModelDesc* desc(int model) {
   if (model == MCGVC_GENERATOR) return &generator_desc();
   if (model == MCGVC_DISCRIMINATOR) return &discriminator_desc();
@@ -33,12 +37,15 @@ int mcgvc_set_backend(int backend) {
   g_backend = backend;
   return 0;
 }
-int mcgvc_set_precision(int n_pass) {
-  if (n_pass != 1 && n_pass != 3) { set_error("precision must be 1 or 3"); return 1; }
-  g_npass = n_pass;
+int mcgvc_set_precision(int mode) {
+  if (mode != MCGVC_PRECISION_PARITY && mode != MCGVC_PRECISION_FAST && mode != MCGVC_PRECISION_MIXED) {
+    set_error("precision must be MCGVC_PRECISION_PARITY (3), _MIXED (2) or _FAST (1)");
+    return 1;
+  }
+  g_precision = mode;
   return 0;
 }
-int mcgvc_get_precision(void) { return g_npass; }
+int mcgvc_get_precision(void) { return g_precision; }
 
 long long mcgvc_param_count(int model) { const ModelDesc* d = desc(model); return d ? d->paramCount : -1; }
 long long mcgvc_packed_bytes(int model) { const ModelDesc* d = desc(model); return d ? d->packed_bytes() : -1; }
@@ -82,7 +89,7 @@ int mcgvc_generator_backward(const void* packed, const void* saved, const float*
                              int need_wgrad, void* ws, void* stream) {
   if (!shape_ok(B, T)) return 1;
   if (!packed || !saved || !mask || !dout || !ws || (need_wgrad && !gblob)) { set_error("generator_backward: null pointer"); return 1; }
-  return generator_backward(packed, saved, mask, dout, B, T, dx, gblob, need_wgrad, ws, cfg(stream));
+  return generator_backward(packed, saved, mask, dout, B, T, dx, gblob, need_wgrad, ws, cfg(stream, true));
 }
 int mcgvc_discriminator_forward(const void* packed, const float* x, int B, int T, float* out,
                                 void* saved, void* ws, void* stream) {
@@ -95,7 +102,7 @@ int mcgvc_discriminator_backward(const void* packed, const void* saved, const fl
                                  int need_wgrad, void* ws, void* stream) {
   if (!shape_ok(B, T)) return 1;
   if (!packed || !saved || !out || !dout || !ws || (need_wgrad && !gblob)) { set_error("discriminator_backward: null pointer"); return 1; }
-  return discriminator_backward(packed, saved, out, dout, B, T, dx, gblob, need_wgrad, ws, cfg(stream));
+  return discriminator_backward(packed, saved, out, dout, B, T, dx, gblob, need_wgrad, ws, cfg(stream, true));
 }
 
 long long mcgvc_launch_count(void) { return launch_count(); }

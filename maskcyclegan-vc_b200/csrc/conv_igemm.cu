@@ -436,6 +436,8 @@ void set_force_block_n(int n) { g_force_block_n = n; }
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream) {
   int bn = 64;
   if (g.w.N % 128 == 0 && g.nSplit % 128 == 0) bn = 128;
+  // small position grids (the 1-D trunk): narrower tiles so that more SMs get a tile
+  if (bn == 128 && (long long)g.tilesX * g.tilesY * g.tilesB * (g.w.N / 128) < num_sms()) bn = 64;
   if (g_force_block_n == 256 && g.w.N % 256 == 0 && g.nSplit % 256 == 0) bn = 256;
   if (g_force_block_n == 64) bn = 64;
   if (g.nPass == 3) {

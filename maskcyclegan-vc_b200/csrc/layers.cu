@@ -46,56 +46,63 @@ __device__ __forceinline__ long long act_off(const ActBuf& a, int img, int y, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// InstanceNorm statistics: one CTA per (image, 32 stat channels); lanes = channels (128-byte rows),
-// warps stride over positions; two passes (mean, then centred second moment) like torch's CPU
-// instance_norm; biased variance, eps = 1e-5 inside the sqrt (reference nn.InstanceNorm defaults).
-__global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ z, int Nz, int P,
+// InstanceNorm statistics: one CTA per (image, 128 stat channels); each lane owns 4 consecutive
+// channels (512-byte coalesced row segments), 16 warps stride over positions with several loads in
+// flight.  Single pass with a per-channel shift (the plane's first element) so that the variance
+// E[(x-s)^2] - E[x-s]^2 does not cancel; biased variance, eps = 1e-5 inside the sqrt (reference
+// nn.InstanceNorm defaults).  `groups` > 1 pools the PixelShuffle sub-position column groups.
+__device__ __forceinline__ float4 ld4g(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+__global__ void __launch_bounds__(512) stats_kernel(const float* __restrict__ z, int Nz, int P,
                                                     int groups, int Nstat, float* __restrict__ mean,
                                                     float* __restrict__ rstd) {
-  __shared__ float red[8][33];
-  __shared__ float smean[32];
+  __shared__ float4 red[2][16][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int s = blockIdx.x * 32 + lane;
+  const int s4 = blockIdx.x * 128 + lane * 4;
   const int img = blockIdx.y;
-  const bool ok = s < Nstat;
-  const float* zb = z + (long long)img * P * Nz;
-  float acc = 0.f;
-  if (ok)
-    for (int p = warp; p < P; p += 8)
-      for (int g = 0; g < groups; ++g) acc += zb[(long long)p * Nz + g * Nstat + s];
-  red[warp][lane] = acc;
-  __syncthreads();
-  if (warp == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += red[w][lane];
-    smean[lane] = t / (float)((long long)P * groups);
+  const bool ok = s4 < Nstat;
+  const float* zb = z + (long long)img * P * Nz + s4;
+  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1, sh = a1;
+  if (ok) {
+    sh = ld4g(zb);
+    const int total = P * groups;
+#pragma unroll 4
+    for (int i = warp; i < total; i += 16) {
+      const int p = i / groups, g = i - p * groups;
+      const float4 v = ld4g(zb + (long long)p * Nz + g * Nstat);
+      const float dx = v.x - sh.x, dy = v.y - sh.y, dz = v.z - sh.z, dw = v.w - sh.w;
+      a1.x += dx; a1.y += dy; a1.z += dz; a1.w += dw;
+      a2.x = fmaf(dx, dx, a2.x); a2.y = fmaf(dy, dy, a2.y); a2.z = fmaf(dz, dz, a2.z); a2.w = fmaf(dw, dw, a2.w);
+    }
   }
-  __syncthreads();
-  const float m = smean[lane];
-  acc = 0.f;
-  if (ok)
-    for (int p = warp; p < P; p += 8)
-      for (int g = 0; g < groups; ++g) {
-        const float d = zb[(long long)p * Nz + g * Nstat + s] - m;
-        acc += d * d;
-      }
-  __syncthreads();
-  red[warp][lane] = acc;
+  red[0][warp][lane] = a1;
+  red[1][warp][lane] = a2;
   __syncthreads();
   if (warp == 0 && ok) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += red[w][lane];
-    const float var = t / (float)((long long)P * groups);
-    mean[(long long)img * Nstat + s] = m;
-    rstd[(long long)img * Nstat + s] = rsqrtf(var + 1e-5f);
+    float4 t1 = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t1;
+    for (int w = 0; w < 16; ++w) {
+      const float4 u = red[0][w][lane], q = red[1][w][lane];
+      t1.x += u.x; t1.y += u.y; t1.z += u.z; t1.w += u.w;
+      t2.x += q.x; t2.y += q.y; t2.z += q.z; t2.w += q.w;
+    }
+    const float inv = 1.f / (float)((long long)P * groups);
+    float4 m, r;
+    const float mx = t1.x * inv, my = t1.y * inv, mz = t1.z * inv, mw = t1.w * inv;
+    m.x = sh.x + mx; m.y = sh.y + my; m.z = sh.z + mz; m.w = sh.w + mw;
+    r.x = rsqrtf(fmaxf(t2.x * inv - mx * mx, 0.f) + 1e-5f);
+    r.y = rsqrtf(fmaxf(t2.y * inv - my * my, 0.f) + 1e-5f);
+    r.z = rsqrtf(fmaxf(t2.z * inv - mz * mz, 0.f) + 1e-5f);
+    r.w = rsqrtf(fmaxf(t2.w * inv - mw * mw, 0.f) + 1e-5f);
+    *reinterpret_cast<float4*>(mean + (long long)img * Nstat + s4) = m;
+    *reinterpret_cast<float4*>(rstd + (long long)img * Nstat + s4) = r;
   }
 }
 
 cudaError_t launch_stats(const float* z, int Nz, int P, int nImg, int groups, float* mean,
                          float* rstd, cudaStream_t s) {
   const int Nstat = Nz / groups;
-  dim3 grid((Nstat + 31) / 32, nImg);
-  stats_kernel<<<grid, 256, 0, s>>>(z, Nz, P, groups, Nstat, mean, rstd);
+  dim3 grid((Nstat + 127) / 128, nImg);
+  stats_kernel<<<grid, 512, 0, s>>>(z, Nz, P, groups, Nstat, mean, rstd);
   return launched();
 }
 
@@ -208,25 +215,36 @@ __device__ __forceinline__ float swish_grad(float yv) {
   return sg * (1.f + yv * (1.f - sg));
 }
 
+__device__ __forceinline__ float4 swish_grad4(float4 y) {
+  return make_float4(swish_grad(y.x), swish_grad(y.y), swish_grad(y.z), swish_grad(y.w));
+}
+__device__ __forceinline__ void acc4(float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+__device__ __forceinline__ void fma4(float4& a, const float4& u, const float4& v) {
+  a.x = fmaf(u.x, v.x, a.x); a.y = fmaf(u.y, v.y, a.y); a.z = fmaf(u.z, v.z, a.z); a.w = fmaf(u.w, v.w, a.w);
+}
+
+// One CTA per (image, 128 channels c, position split); lane owns 4 channels, 8 warps stride over the
+// split's positions; partial sums are added atomically into t1/t2 (zeroed by the launcher).
 template <int MODE>
 __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArgs a) {
-  __shared__ float red[4][8][33];
+  __shared__ float4 red[4][8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = a.dA.C;
-  const int c = blockIdx.x * 32 + lane;
+  const int c = blockIdx.x * 128 + lane * 4;
   const int img = blockIdx.y;
   const bool ok = c < C;
-  float s1a = 0.f, s2a = 0.f, s1g = 0.f, s2g = 0.f;
+  float4 s1a = make_float4(0.f, 0.f, 0.f, 0.f), s2a = s1a, s1g = s1a, s2g = s1a;
   if (ok) {
-    const long long so = (long long)img * a.Nstat, ao = (long long)(img % a.affPeriod) * a.Nstat;
-    const float ma = a.mean[so + c], ra = a.rstd[so + c], ga = a.gamma[ao + c], ba = a.beta[ao + c];
-    float mg = 0.f, rg = 0.f, gg = 0.f, bg = 0.f;
-    if (MODE == kGatedIN) {
-      mg = a.mean[so + C + c]; rg = a.rstd[so + C + c]; gg = a.gamma[ao + C + c]; bg = a.beta[ao + C + c];
-    }
+    const Norm4 na = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, c);
+    Norm4 ng = na;
+    if (MODE == kGatedIN) ng = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, C + c);
     const int P = a.dA.Y * a.dA.X;
-    for (int p = warp; p < P; p += 8) {
-      const int y = p / a.dA.X, x = p % a.dA.X;
+    const int per = (P + gridDim.z - 1) / gridDim.z;
+    const int pBeg = blockIdx.z * per;
+    const int pEnd = pBeg + per < P ? pBeg + per : P;
+#pragma unroll 2
+    for (int p = pBeg + warp; p < pEnd; p += 8) {
+      const int y = p / a.dA.X, x = p - y * a.dA.X;
       long long zrow;
       int col = c;
       if (MODE == kINSwishShuffle) {
@@ -236,21 +254,23 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
         zrow = ((long long)img * a.zY + y) * a.zX + x;
       }
       const float* zr = a.z + zrow * a.Nz;
-      const float d = a.dA.f32[act_off(a.dA, img, y, x) + c];
-      const float xh = (zr[col] - ma) * ra;
+      const float4 d = ld4(a.dA.f32 + act_off(a.dA, img, y, x) + c);
+      const float4 xh = xhat4(ld4(zr + col), na);
       if (MODE == kGatedIN) {
-        const float xg = (zr[C + c] - mg) * rg;
-        const float ya = fmaf(xh, ga, ba), yg = fmaf(xg, gg, bg);
-        const float sg = sigmoidf_(yg);
-        const float dya = d * sg;
-        const float dyg = d * ya * sg * (1.f - sg);
-        s1a += dya; s2a += dya * xh;
-        s1g += dyg; s2g += dyg * xg;
+        const float4 xg = xhat4(ld4(zr + C + c), ng);
+        const float4 ya = affine4(xh, na), yg = affine4(xg, ng);
+        const float4 sg = make_float4(sigmoidf_(yg.x), sigmoidf_(yg.y), sigmoidf_(yg.z), sigmoidf_(yg.w));
+        const float4 dya = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
+        const float4 dyg = make_float4(d.x * ya.x * sg.x * (1.f - sg.x), d.y * ya.y * sg.y * (1.f - sg.y),
+                                       d.z * ya.z * sg.z * (1.f - sg.z), d.w * ya.w * sg.w * (1.f - sg.w));
+        acc4(s1a, dya); fma4(s2a, dya, xh);
+        acc4(s1g, dyg); fma4(s2g, dyg, xg);
       } else if (MODE == kINOnly) {
-        s1a += d; s2a += d * xh;
+        acc4(s1a, d); fma4(s2a, d, xh);
       } else {  // kINSwish, kINSwishShuffle
-        const float dy = d * swish_grad(fmaf(xh, ga, ba));
-        s1a += dy; s2a += dy * xh;
+        const float4 g = swish_grad4(affine4(xh, na));
+        const float4 dy = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+        acc4(s1a, dy); fma4(s2a, dy, xh);
       }
     }
   }
@@ -258,25 +278,46 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
   red[2][warp][lane] = s1g; red[3][warp][lane] = s2g;
   __syncthreads();
   if (warp == 0 && ok) {
-    float t[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < 4; ++k)
-      for (int w = 0; w < 8; ++w) t[k] += red[k][w][lane];
+    float4 t[4];
+    for (int k = 0; k < 4; ++k) {
+      t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int w = 0; w < 8; ++w) acc4(t[k], red[k][w][lane]);
+    }
     const long long so = (long long)img * a.Nstat, ao = (long long)(img % a.affPeriod) * a.Nstat;
-    a.t1[so + c] = t[0];
-    a.t2[so + c] = t[1];
-    atomicAdd(a.dbeta + ao + c, t[0]);
-    atomicAdd(a.dgamma + ao + c, t[1]);
+    const float* b0 = reinterpret_cast<const float*>(&t[0]);
+    const float* g0 = reinterpret_cast<const float*>(&t[1]);
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(a.t1 + so + c + i, b0[i]);
+      atomicAdd(a.t2 + so + c + i, g0[i]);
+      atomicAdd(a.dbeta + ao + c + i, b0[i]);
+      atomicAdd(a.dgamma + ao + c + i, g0[i]);
+    }
     if (MODE == kGatedIN) {
-      a.t1[so + C + c] = t[2];
-      a.t2[so + C + c] = t[3];
-      atomicAdd(a.dbeta + ao + C + c, t[2]);
-      atomicAdd(a.dgamma + ao + C + c, t[3]);
+      const float* b1 = reinterpret_cast<const float*>(&t[2]);
+      const float* g1 = reinterpret_cast<const float*>(&t[3]);
+      for (int i = 0; i < 4; ++i) {
+        atomicAdd(a.t1 + so + C + c + i, b1[i]);
+        atomicAdd(a.t2 + so + C + c + i, g1[i]);
+        atomicAdd(a.dbeta + ao + C + c + i, b1[i]);
+        atomicAdd(a.dgamma + ao + C + c + i, g1[i]);
+      }
     }
   }
 }
 
 cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
-  dim3 grid((a.dA.C + 31) / 32, a.dA.nImg);
+  if (a.mode == kGatedNoNorm || a.mode == kSwishNoNorm) return cudaSuccess;  // nothing to reduce
+  const int cg = (a.dA.C + 127) / 128;
+  const int P = a.dA.Y * a.dA.X;
+  int splits = (4 * 148 + cg * a.dA.nImg - 1) / (cg * a.dA.nImg);
+  if (splits > P / 64) splits = P / 64;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  dim3 grid(cg, a.dA.nImg, splits);
+  const size_t tbytes = (size_t)a.dA.nImg * a.Nstat * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(a.t1, 0, tbytes, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(a.t2, 0, tbytes, s);
+  if (e != cudaSuccess) return e;
   switch (a.mode) {
     case kGatedIN: apply_bwd_reduce_kernel<kGatedIN><<<grid, 256, 0, s>>>(a); break;
     case kINOnly: apply_bwd_reduce_kernel<kINOnly><<<grid, 256, 0, s>>>(a); break;

@@ -53,7 +53,7 @@ const ModelDesc& discriminator_desc();
 struct RunCfg {
   cudaStream_t stream;
   int backend;   // 0 = tcgen05/TMA kernels, 1 = SIMT checking kernels
-  int nPass;     // 3 = split-bf16 (parity mode), 1 = bf16 (fast mode)
+  int nPass;     // passes used by the call: 3 = split-bf16, 1 = bf16 (capi picks it per direction)
 };
 
 // sizes (bytes) of the per-call buffers the caller provides

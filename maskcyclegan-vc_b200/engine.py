@@ -13,6 +13,7 @@ DISCRIMINATOR = 1
 BACKEND_TCGEN05 = 0
 BACKEND_SIMT = 1
 PRECISION_PARITY = 3   # split-bf16 x3 (default; meets the 1e-3 parity gate)
+PRECISION_MIXED = 2    # forward split-bf16 x3, backward single bf16 pass
 PRECISION_FAST = 1     # single bf16 pass
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcgvc.so")
@@ -82,8 +83,8 @@ def set_backend(backend):
     _check(lib().mcgvc_set_backend(backend), "set_backend")
 
 
-def set_precision(n_pass):
-    _check(lib().mcgvc_set_precision(n_pass), "set_precision")
+def set_precision(mode):
+    _check(lib().mcgvc_set_precision(mode), "set_precision")
 
 
 def get_precision():
