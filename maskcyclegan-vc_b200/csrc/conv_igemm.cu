@@ -21,6 +21,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_bf16.h>
 #include <mutex>
@@ -433,7 +434,17 @@ static cudaError_t launch_conv_tc_t(const ConvGeom& g, cudaStream_t stream) {
 static int g_force_block_n = 0;
 void set_force_block_n(int n) { g_force_block_n = n; }
 
+static int env_block_n() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCGVC_BLOCK_N");  // tuning override: 64 / 128 / 256
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream) {
+  if (g_force_block_n == 0 && env_block_n() != 0) g_force_block_n = env_block_n();
   int bn = 64;
   if (g.w.N % 128 == 0 && g.nSplit % 128 == 0) bn = 128;
   // small position grids (the 1-D trunk): narrower tiles so that more SMs get a tile
