@@ -377,6 +377,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+static int g_force_block_n = 0;
+void set_force_block_n(int n) { g_force_block_n = n; }
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -429,10 +432,286 @@ static cudaError_t launch_conv_tc_t(const ConvGeom& g, cudaStream_t stream) {
   return launched();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256-position x BLOCK_N tile per pair of CTAs on neighbouring
+// SMs.  Each CTA stages its own 128-position activation box and HALF of the weight rows, so the
+// operand bytes every SM pulls from L2 (and reads from shared memory) per MMA are halved versus
+// the single-CTA kernel -- the limiter measured in profiles/r01_ncu_full_summary.md.  The leader
+// CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 with M = 256; accumulator rows 0-127 live
+// in the leader's TMEM, rows 128-255 in the peer's; each CTA's epilogue drains its own half.
+template <int BLOCK_N, int NPASS>
+struct Conv2Cfg {
+  static constexpr int kABytes = kTileM * kBlockK * 2;          // 16 KB (this CTA's 128 positions)
+  static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;   // this CTA's half of the weight rows
+  static constexpr int kStageBytes = (kABytes + kBBytes) * (NPASS == 3 ? 2 : 1);
+  static constexpr int kStagesRaw = (222 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(kStages >= 2, "need at least two pipeline stages");
+  static_assert(kTmemCols >= 32 && kTmemCols <= 512, "TMEM columns");
+};
+
+template <int BLOCK_N, int NPASS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                const __grid_constant__ ConvGeom g) {
+  using Cfg = Conv2Cfg<BLOCK_N, NPASS>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                      // used in the leader only (2 arrivals + 2x tx bytes)
+  uint64_t* empty = bars + kStages;           // per CTA, released by the leader's multicast commit
+  uint64_t* tfull = bars + 2 * kStages;       // per CTA
+  uint64_t* tempty = bars + 2 * kStages + 2;  // leader only: 4 epilogue warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmAh);
+    ptx::prefetch_tmap(&tmWh);
+    if (NPASS == 3) {
+      ptx::prefetch_tmap(&tmAl);
+      ptx::prefetch_tmap(&tmWl);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 2);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], 8);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();   // barriers of BOTH CTAs initialised before any remote arrive / multicast
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nTiles = g.w.N / BLOCK_N;
+  const int mTiles = g.tilesX * g.tilesY * g.tilesB;
+  const int pairM = (mTiles + 1) / 2;
+  const int totalTiles = nTiles * pairM;
+  const int numK = g.nTaps * g.cBlocks;
+  const int pairIdx = blockIdx.x >> 1;
+  const int numPairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pairIdx; tile < totalTiles; tile += numPairs) {
+      const int nt = tile % nTiles;
+      int mt = (tile / nTiles) * 2 + (int)rank;
+      int x0, y0, b0;
+      if (mt < mTiles) {
+        const int tx = mt % g.tilesX;
+        mt /= g.tilesX;
+        x0 = tx * g.BX; y0 = (mt % g.tilesY) * g.BY; b0 = (mt / g.tilesY) * g.BB;
+      } else {          // odd tile count: the peer's half of the last pair is all padding (zero fill)
+        x0 = 0; y0 = 0; b0 = g.tilesB * g.BB;
+      }
+      const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+      for (int t = 0; t < g.nTaps; ++t) {
+        const Tap tap = g.taps[t];
+        for (int cb = 0; cb < g.cBlocks; ++cb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+          ptx::tma_load_5d_2sm(st, &tmAh, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
+                               tap.plane, b0);
+          ptx::tma_load_3d_2sm(st + Cfg::kABytes, &tmWh, &full[stage], cb * kBlockK, n0, tap.w);
+          if (NPASS == 3) {
+            uint8_t* lo = st + Cfg::kABytes + Cfg::kBBytes;
+            ptx::tma_load_5d_2sm(lo, &tmAl, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
+                                 tap.plane, b0);
+            ptx::tma_load_3d_2sm(lo + Cfg::kABytes, &tmWl, &full[stage], cb * kBlockK, n0, tap.w);
+          }
+          if (!leader) ptx::mbar_arrive_remote(&full[stage], 0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kTileM, BLOCK_N, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = pairIdx; tile < totalTiles; tile += numPairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ptx::mbar_wait(&tempty[acc], aphase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < numK; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sA = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sB = sA + Cfg::kABytes;
+        const uint32_t sAl = sB + Cfg::kBBytes;
+        const uint32_t sBl = sAl + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t dAh = ptx::umma_smem_desc_sw128(sA + k * 32, 0, 1024);
+          const uint64_t dBh = ptx::umma_smem_desc_sw128(sB + k * 32, 0, 1024);
+          ptx::umma_bf16_2cta(d_tmem, dAh, dBh, idesc, (kb | k) != 0);
+          if (NPASS == 3) {
+            const uint64_t dAl = ptx::umma_smem_desc_sw128(sAl + k * 32, 0, 1024);
+            const uint64_t dBl = ptx::umma_smem_desc_sw128(sBl + k * 32, 0, 1024);
+            ptx::umma_bf16_2cta(d_tmem, dAh, dBl, idesc, 1);
+            ptx::umma_bf16_2cta(d_tmem, dAl, dBh, idesc, 1);
+          }
+        }
+        ptx::umma_commit_2cta(&empty[stage], 0x3);
+        if (kb == numK - 1) ptx::umma_commit_2cta(&tfull[acc], 0x3);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int it = 0;
+    for (int tile = pairIdx; tile < totalTiles; tile += numPairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int nt = tile % nTiles;
+      int mt = (tile / nTiles) * 2 + (int)rank;
+      const bool real = mt < mTiles;
+      const int tx = mt % g.tilesX;
+      mt /= g.tilesX;
+      const int ty = mt % g.tilesY;
+      const int tb = mt / g.tilesY;
+      const int n0 = nt * BLOCK_N;
+      const int bx = row % g.BX;
+      const int by = (row / g.BX) % g.BY;
+      const int bb = row / (g.BX * g.BY);
+      const int x = tx * g.BX + bx, y = ty * g.BY + by, b = tb * g.BB + bb;
+      const bool valid = real && (x < g.oX) && (y < g.oY) && (b < g.oB);
+      const long long off = (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
+                            (long long)(n0 / g.nSplit) * g.sNhi + (n0 % g.nSplit);
+      float* orow = g.out + off;
+      const float* arow = g.addsrc ? g.addsrc + off : nullptr;
+
+      ptx::mbar_wait(&tfull[acc], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int j = 0; j < BLOCK_N / 32; ++j) {
+        uint32_t v[32];
+        ptx::tmem_ld32(taddr + j * 32, v);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[i + 0]);
+            o.y = __uint_as_float(v[i + 1]);
+            o.z = __uint_as_float(v[i + 2]);
+            o.w = __uint_as_float(v[i + 3]);
+            if (g.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j * 32 + i));
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            }
+            if (arow) {
+              const float4 av = *reinterpret_cast<const float4*>(arow + j * 32 + i);
+              o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w;
+            }
+            *reinterpret_cast<float4*>(orow + j * 32 + i) = o;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(&tempty[acc]);
+        else ptx::mbar_arrive_remote(&tempty[acc], 0);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();   // neither CTA may retire (smem / TMEM) while its peer still uses it
+  if (warp == 2) ptx::tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+}
+
+template <int BLOCK_N, int NPASS>
+static cudaError_t launch_conv_tc2_t(const ConvGeom& g, cudaStream_t stream) {
+  using Cfg = Conv2Cfg<BLOCK_N, NPASS>;
+  if (!check_conv_geom(g, BLOCK_N)) return cudaErrorInvalidValue;
+  CUtensorMap tmAh, tmAl, tmWh, tmWl;
+  if (!make_act_tmap(&tmAh, g.a.hi, g.a, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_wgt_tmap(&tmWh, g.w.hi, g.w, BLOCK_N / 2)) return cudaErrorInvalidValue;
+  if (NPASS == 3) {
+    if (!make_act_tmap(&tmAl, g.a.lo, g.a, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+    if (!make_wgt_tmap(&tmWl, g.w.lo, g.w, BLOCK_N / 2)) return cudaErrorInvalidValue;
+  } else {
+    tmAl = tmAh;
+    tmWl = tmWh;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, NPASS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("conv2: smem attr: %s", cudaGetErrorString(e)); return e; }
+    attr_set = true;
+  }
+  const int mTiles = g.tilesX * g.tilesY * g.tilesB;
+  const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2);
+  const int maxPairs = num_sms() / 2;
+  const int pairs = total < maxPairs ? total : maxPairs;
+  profile_begin(0, g.algoFlops, stream);
+  conv_tc2_kernel<BLOCK_N, NPASS><<<2 * pairs, 256, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
+  profile_end(stream);
+  return launched();
+}
+
+// CTA-pair kernel selection: on by default for layers with enough tiles to fill the chip
+// (MCGVC_CTA2=0 falls back to the single-CTA kernel everywhere, for A/B measurements).
+static int env_cta2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCGVC_CTA2");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+static int g_force_cta2 = -1;
+void set_force_cta2(int v) { g_force_cta2 = v; }
+
+static bool try_launch_conv_tc2(const ConvGeom& g, cudaStream_t stream, cudaError_t* err) {
+  const int want = g_force_cta2 >= 0 ? g_force_cta2 : env_cta2();
+  if (!want) return false;
+  if (g.w.N % 128 || g.nSplit % 128) return false;
+  int bn = (g.w.N % 256 == 0 && g.nSplit % 256 == 0) ? 256 : 128;
+  if (g_force_block_n == 128) bn = 128;
+  const int mTiles = g.tilesX * g.tilesY * g.tilesB;
+  const long long pairTiles = (long long)(g.w.N / bn) * ((mTiles + 1) / 2);
+  if (g_force_cta2 < 0 && pairTiles < num_sms() / 2) return false;   // small layers: 1-CTA kernel
+  if (g.nPass == 3) *err = bn == 256 ? launch_conv_tc2_t<256, 3>(g, stream) : launch_conv_tc2_t<128, 3>(g, stream);
+  else *err = bn == 256 ? launch_conv_tc2_t<256, 1>(g, stream) : launch_conv_tc2_t<128, 1>(g, stream);
+  return true;
+}
+
 // BLOCK_N selection: widest tile that divides N and nSplit (256 halves B-operand smem traffic per
 // MMA; 64 exists for the narrow data-gradient outputs of the two stem layers).
-static int g_force_block_n = 0;
-void set_force_block_n(int n) { g_force_block_n = n; }
 
 static int env_block_n() {
   static int v = -1;
@@ -445,6 +724,10 @@ static int env_block_n() {
 
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream) {
   if (g_force_block_n == 0 && env_block_n() != 0) g_force_block_n = env_block_n();
+  {
+    cudaError_t e2 = cudaSuccess;
+    if (try_launch_conv_tc2(g, stream, &e2)) return e2;
+  }
   int bn = 64;
   if (g.w.N % 128 == 0 && g.nSplit % 128 == 0) bn = 128;
   // small position grids (the 1-D trunk): narrower tiles so that more SMs get a tile

@@ -5,7 +5,7 @@
 
 using namespace mcgvc;
 
-namespace mcgvc { void set_force_block_n(int n); }
+namespace mcgvc { void set_force_block_n(int n); void set_force_cta2(int v); }
 
 extern "C" {
 
@@ -33,10 +33,13 @@ int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY,
   }
   g.sB = sB; g.sY = sY; g.sX = sX; g.nSplit = nSplit; g.sNhi = sNhi;
   g.out = out; g.bias = bias; g.addsrc = addsrc; g.nPass = nPass;
+  // backend: 0 = tcgen05 single-CTA, 1 = SIMT checker, 2 = tcgen05 CTA-pair (cta_group::2)
   set_force_block_n(blockN);
-  cudaError_t e = backend == 0 ? launch_conv_tc(g, (cudaStream_t)stream)
-                               : launch_conv_simt(g, (cudaStream_t)stream);
+  set_force_cta2(backend == 2 ? 1 : 0);
+  cudaError_t e = backend == 1 ? launch_conv_simt(g, (cudaStream_t)stream)
+                               : launch_conv_tc(g, (cudaStream_t)stream);
   set_force_block_n(0);
+  set_force_cta2(-1);
   if (e != cudaSuccess) {
     if (!last_error()[0]) set_error("conv launch: %s", cudaGetErrorString(e));
     return 1;

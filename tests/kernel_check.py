@@ -97,13 +97,17 @@ def conv_case(lib, name, B, P, Y, X, C, N, taps, oB, oY, oX, nPass, blockN, with
     if addsrc is not None:
         ref = ref + addsrc.double()
     res = {}
-    for backend, bname in ((1, "simt"), (0, "tc")):
+    backends = [(1, "simt"), (0, "tc")]
+    if N % 128 == 0:
+        backends.append((2, "tc2"))   # CTA-pair kernel (cta_group::2)
+    for backend, bname in backends:
         out = run_conv(lib, Ah, Al, Wh, Wl, taps, oB, oY, oX, nPass, backend, blockN, bias, addsrc)
         nan = torch.isnan(out).sum().item()
         res[bname] = (relerr(torch.nan_to_num(out), ref), nan)
     ok = all(e < 2e-5 and n == 0 for e, n in res.values())
+    tc2 = f"| tc2 err={res['tc2'][0]:.2e} nan={res['tc2'][1]} " if "tc2" in res else ""
     print(f"[conv ] {name:34s} nPass={nPass} blockN={blockN:3d} simt err={res['simt'][0]:.2e} nan={res['simt'][1]} "
-          f"| tc err={res['tc'][0]:.2e} nan={res['tc'][1]} {'OK' if ok else 'FAIL'}", flush=True)
+          f"| tc err={res['tc'][0]:.2e} nan={res['tc'][1]} {tc2}{'OK' if ok else 'FAIL'}", flush=True)
     return ok
 
 
