@@ -5,7 +5,7 @@
 
 using namespace mcgvc;
 
-namespace mcgvc { void set_force_block_n(int n); void set_force_cta2(int v); }
+namespace mcgvc { void set_force_block_n(int n); void set_force_cta2(int v); void set_force_wgrad_cta2(int v); }
 
 extern "C" {
 
@@ -73,8 +73,10 @@ int mcgvc_debug_wgrad(const void* z_hi, const void* z_lo, int zC, int zX, int zY
     g.ztaps[t].w = 0;
   }
   g.N = zC; g.C = xC; g.cTile = cTile; g.splitK = splitK; g.dw = dw; g.nPass = nPass;
-  cudaError_t e = backend == 0 ? launch_wgrad_tc(g, (cudaStream_t)stream)
-                               : launch_wgrad_simt(g, (cudaStream_t)stream);
+  set_force_wgrad_cta2(backend == 2 ? 1 : 0);
+  cudaError_t e = backend == 1 ? launch_wgrad_simt(g, (cudaStream_t)stream)
+                               : launch_wgrad_tc(g, (cudaStream_t)stream);
+  set_force_wgrad_cta2(-1);
   if (e != cudaSuccess) {
     if (!last_error()[0]) set_error("wgrad launch: %s", cudaGetErrorString(e));
     return 1;

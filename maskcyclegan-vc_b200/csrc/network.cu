@@ -4,6 +4,7 @@
 #include "network.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 
 namespace mcgvc {
@@ -349,13 +350,29 @@ void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList&
   }
   g.N = dz.C;
   g.C = x.C;
-  g.cTile = x.C % 128 == 0 ? 128 : 64;
-  const long long outTiles = (long long)xtaps.n * (g.N / 128) * (g.C / g.cTile);
+  // channel tile: the widest that divides C (256-wide tiles halve the dz re-reads per MMA)
+  g.cTile = x.C % 256 == 0 ? 256 : (x.C % 128 == 0 ? 128 : 64);
+  {
+    static int envct = -1;  // tuning override: MCGVC_WGRAD_CTILE=128 caps the channel tile
+    if (envct < 0) { const char* e = getenv("MCGVC_WGRAD_CTILE"); envct = e ? atoi(e) : 0; }
+    if (envct == 128 && g.cTile == 256) g.cTile = 128;
+  }
+  // split-K: pick the split whose CTA count fills whole waves of the 148 SMs best (a partial last
+  // wave costs a full wave of time), with a mild penalty per extra split for the atomic merge
+  const long long units = (long long)xtaps.n * (g.N / 128) * (g.C / g.cTile);
   const long long posTiles = (long long)g.tilesX * g.tilesY * g.tilesB;
-  long long sk = (2 * 148 + outTiles - 1) / outTiles;
-  if (sk > posTiles / 4) sk = posTiles / 4;
-  if (sk < 1) sk = 1;
-  g.splitK = (int)sk;
+  long long maxSplit = posTiles / 8;
+  if (maxSplit > 32) maxSplit = 32;
+  if (maxSplit < 1) maxSplit = 1;
+  int bestSk = 1;
+  double bestCost = 1e30;
+  for (long long sk = 1; sk <= maxSplit; ++sk) {
+    const double waves = (double)(units * sk) / 148.0;
+    const double rounds = (double)((units * sk + 147) / 148);
+    const double cost = rounds / waves * (1.0 + 0.01 * (double)sk) + (waves < 1.0 ? 1.0 / waves : 0.0);
+    if (cost < bestCost - 1e-9) { bestCost = cost; bestSk = (int)sk; }
+  }
+  g.splitK = bestSk;
   g.dw = dw;
   g.nPass = r.rc.nPass;
   g.algoFlops = 2.0 * pB * pY * pX * (double)g.N * g.C * xtaps.n * algoFrac;

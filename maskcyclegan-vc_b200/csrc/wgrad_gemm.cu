@@ -15,6 +15,8 @@
 #include "gemm_types.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace mcgvc {
 
 bool make_act_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int BX, int BY, int BB);
@@ -236,8 +238,229 @@ static cudaError_t launch_wgrad_tc_t(const WgradGeom& g, cudaStream_t stream) {
   return launched();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2, M = 256 gradient rows per pair).  Each CTA stages its own 128
+// rows of dz and HALF of the x channels of the tile, halving the operand bytes per SM per MMA.
+template <int CTILE, int NPASS>
+struct Wgrad2Cfg {
+  static constexpr int kZBytes = 2 * kChunkBytes;                   // this CTA's 128 n rows
+  static constexpr int kXBytes = (CTILE / 128) * kChunkBytes;       // this CTA's CTILE/2 channels
+  static constexpr int kStageBytes = (kZBytes + kXBytes) * (NPASS == 3 ? 2 : 1);
+  static constexpr int kStagesRaw = (222 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = CTILE;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(CTILE == 128 || CTILE == 256, "pair tile is 128 or 256 channels wide");
+};
+
+template <int CTILE, int NPASS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
+                 const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                 const __grid_constant__ WgradGeom g) {
+  using Cfg = Wgrad2Cfg<CTILE, NPASS>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int cTiles = g.C / CTILE;
+  const int nTiles = g.N / 256;
+  int w = blockIdx.x >> 1;
+  const int split = w % g.splitK;
+  w /= g.splitK;
+  const int ct = w % cTiles;
+  w /= cTiles;
+  const int nt = w % nTiles;
+  const int t = w / nTiles;
+  const Tap tap = g.taps[t];
+  const Tap ztap = g.ztaps[t];
+  const int n0 = nt * 256 + (int)rank * 128;            // this CTA's gradient rows
+  const int c0 = ct * CTILE;                            // pair's channel tile
+  const int cLoad = c0 + (int)rank * (CTILE / 2);       // this CTA's half of the x channels
+
+  const int posTiles = g.tilesX * g.tilesY * g.tilesB;
+  const int per = (posTiles + g.splitK - 1) / g.splitK;
+  const int kBegin = split * per;
+  const int kEnd = (kBegin + per < posTiles) ? kBegin + per : posTiles;
+  const int numK = kEnd - kBegin;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmZh);
+    ptx::prefetch_tmap(&tmXh);
+    if (NPASS == 3) {
+      ptx::prefetch_tmap(&tmZl);
+      ptx::prefetch_tmap(&tmXl);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 2);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(tfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (numK > 0) {
+    if (warp == 0 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kBegin; kt < kEnd; ++kt) {
+        int m = kt;
+        const int tx = m % g.tilesX;
+        m /= g.tilesX;
+        const int ty = m % g.tilesY;
+        const int tb = m / g.tilesY;
+        const int x0 = tx * g.BX, y0 = ty * g.BY, b0 = tb * g.BB;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          ptx::tma_load_5d_2sm(st + j * kChunkBytes, &tmZh, &full[stage], n0 + j * 64, x0 + ztap.dx,
+                               y0 + ztap.dy, 0, b0);
+#pragma unroll
+        for (int j = 0; j < CTILE / 128; ++j)
+          ptx::tma_load_5d_2sm(st + Cfg::kZBytes + j * kChunkBytes, &tmXh, &full[stage],
+                               cLoad + j * 64, x0 + tap.dx, y0 + tap.dy, tap.plane, b0);
+        if (NPASS == 3) {
+          uint8_t* lo = st + Cfg::kZBytes + Cfg::kXBytes;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            ptx::tma_load_5d_2sm(lo + j * kChunkBytes, &tmZl, &full[stage], n0 + j * 64,
+                                 x0 + ztap.dx, y0 + ztap.dy, 0, b0);
+#pragma unroll
+          for (int j = 0; j < CTILE / 128; ++j)
+            ptx::tma_load_5d_2sm(lo + Cfg::kZBytes + j * kChunkBytes, &tmXl, &full[stage],
+                                 cLoad + j * 64, x0 + tap.dx, y0 + tap.dy, tap.plane, b0);
+        }
+        if (!leader) ptx::mbar_arrive_remote(&full[stage], 0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1 && lane == 0 && leader) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, CTILE, 1, 1);
+      constexpr uint32_t kLbo = kChunkBytes;
+      constexpr uint32_t kSbo = 1024;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < numK; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sZ = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sX = sZ + Cfg::kZBytes;
+        const uint32_t sZl = sX + Cfg::kXBytes;
+        const uint32_t sXl = sZl + Cfg::kZBytes;
+#pragma unroll
+        for (int k = 0; k < kWgBlockPos / 16; ++k) {
+          const uint64_t dZh = ptx::umma_smem_desc_sw128(sZ + k * 2048, kLbo, kSbo);
+          const uint64_t dXh = ptx::umma_smem_desc_sw128(sX + k * 2048, kLbo, kSbo);
+          ptx::umma_bf16_2cta(tmem_base, dZh, dXh, idesc, (kb | k) != 0);
+          if (NPASS == 3) {
+            const uint64_t dZl = ptx::umma_smem_desc_sw128(sZl + k * 2048, kLbo, kSbo);
+            const uint64_t dXl = ptx::umma_smem_desc_sw128(sXl + k * 2048, kLbo, kSbo);
+            ptx::umma_bf16_2cta(tmem_base, dZh, dXl, idesc, 1);
+            ptx::umma_bf16_2cta(tmem_base, dZl, dXh, idesc, 1);
+          }
+        }
+        ptx::umma_commit_2cta(&empty[stage], 0x3);
+        if (kb == numK - 1) ptx::umma_commit_2cta(tfull, 0x3);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp >= 4) {
+      const int quad = warp & 3;
+      const int n = n0 + quad * 32 + lane;
+      float* drow = g.dw + ((long long)tap.w * g.N + n) * g.C + c0;
+      ptx::mbar_wait(tfull, 0);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+      for (int j = 0; j < CTILE / 32; ++j) {
+        uint32_t v[32];
+        ptx::tmem_ld32(taddr + j * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          red_add_v4(drow + j * 32 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                     __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 2) ptx::tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+}
+
+template <int CTILE, int NPASS>
+static cudaError_t launch_wgrad_tc2_t(const WgradGeom& g, cudaStream_t stream) {
+  using Cfg = Wgrad2Cfg<CTILE, NPASS>;
+  CUtensorMap tmZh, tmZl, tmXh, tmXl;
+  if (!make_act_tmap(&tmZh, g.dz.hi, g.dz, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_act_tmap(&tmXh, g.x.hi, g.x, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (NPASS == 3) {
+    if (!make_act_tmap(&tmZl, g.dz.lo, g.dz, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+    if (!make_act_tmap(&tmXl, g.x.lo, g.x, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  } else {
+    tmZl = tmZh;
+    tmXl = tmXh;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc2_kernel<CTILE, NPASS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("wgrad2: smem attr: %s", cudaGetErrorString(e)); return e; }
+    attr_set = true;
+  }
+  const long long pairs = (long long)g.nTaps * (g.N / 256) * (g.C / CTILE) * g.splitK;
+  profile_begin(1, g.algoFlops, stream);
+  wgrad_tc2_kernel<CTILE, NPASS><<<(unsigned)(2 * pairs), 256, Cfg::kSmemBytes, stream>>>(tmZh, tmZl, tmXh, tmXl, g);
+  profile_end(stream);
+  return launched();
+}
+
+static int env_wg_cta2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCGVC_WGRAD_CTA2");   // 0 = single-CTA kernel everywhere (A/B measurements)
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+static int g_force_wg_cta2 = -1;
+void set_force_wgrad_cta2(int v) { g_force_wg_cta2 = v; }
+
 cudaError_t launch_wgrad_tc(const WgradGeom& g, cudaStream_t stream) {
   if (!check_wgrad_geom(g)) return cudaErrorInvalidValue;
+  {
+    const int want = g_force_wg_cta2 >= 0 ? g_force_wg_cta2 : env_wg_cta2();
+    // pair tile: 256 gradient rows x (128 | 256) channels; cTile (64/128/256) keeps its meaning
+    // of "channels per work item", so the pair kernel needs cTile >= 128
+    if (want && g.N % 256 == 0 && g.cTile >= 128) {
+      if (g.nPass == 3) return g.cTile == 256 ? launch_wgrad_tc2_t<256, 3>(g, stream) : launch_wgrad_tc2_t<128, 3>(g, stream);
+      return g.cTile == 256 ? launch_wgrad_tc2_t<256, 1>(g, stream) : launch_wgrad_tc2_t<128, 1>(g, stream);
+    }
+  }
   if (g.nPass == 3) {
     if (g.cTile == 256) return launch_wgrad_tc_t<256, 3>(g, stream);
     if (g.cTile == 128) return launch_wgrad_tc_t<128, 3>(g, stream);

@@ -160,7 +160,10 @@ def wgrad_case(lib, name, zshape, xshape, taps, ztaps, pB, pY, pX, nPass, cTile,
         ref = ref_wgrad(Zh.double(), Xh.double(), taps, ztaps, pB, pY, pX)
     T = ref.shape[0]
     res = {}
-    for backend, bname in ((1, "simt"), (0, "tc")):
+    backends = [(1, "simt"), (0, "tc")]
+    if N % 256 == 0 and cTile >= 128:
+        backends.append((2, "tc2"))   # CTA-pair kernel
+    for backend, bname in backends:
         dw = torch.zeros(T, N, C, device="cuda")
         rc = lib.mcgvc_debug_wgrad(ptr(Zh), ptr(Zl), N, zX, zY, zB, ptr(Xh), ptr(Xl), C, xX, xY, xP,
                                    xB, pX, pY, pB, len(taps), taps_array(taps), taps_array(ztaps),
@@ -170,8 +173,9 @@ def wgrad_case(lib, name, zshape, xshape, taps, ztaps, pB, pY, pX, nPass, cTile,
         torch.cuda.synchronize()
         res[bname] = relerr(dw, ref)
     ok = all(e < 2e-5 for e in res.values())
+    tc2 = f"| tc2 err={res['tc2']:.2e} " if "tc2" in res else ""
     print(f"[wgrad] {name:34s} nPass={nPass} cTile={cTile:3d} splitK={splitK} simt err={res['simt']:.2e} "
-          f"| tc err={res['tc']:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+          f"| tc err={res['tc']:.2e} {tc2}{'OK' if ok else 'FAIL'}", flush=True)
     return ok
 
 
@@ -203,6 +207,10 @@ def all_cases(lib):
     ok &= wgrad_case(lib, "5x5 s1 B2 Y20 X16", (2, 20, 16, 128), (2, 1, 20, 16, 128), taps_5x5_s1(), z0 * 25, 2, 20, 16, 3, 128, 2)
     ok &= wgrad_case(lib, "5x5 s2 parity", (2, 20, 16, 128), (2, 4, 20, 16, 64), taps_kxk_s2(5, 2), z0 * 25, 2, 20, 16, 3, 64, 1)
     ok &= wgrad_case(lib, "odd B3 Y5 X17 3x3 s2", (3, 5, 9, 128), (3, 4, 5, 9, 64), taps_kxk_s2(3, 1), z0 * 9, 3, 5, 9, 3, 64, 2)
+    for nPass in (1, 3):
+        for ct in (128, 256):
+            ok &= wgrad_case(lib, "pair 5x5 s1 N512 C256", (2, 20, 16, 512), (2, 1, 20, 16, 256), taps_5x5_s1(), z0 * 25, 2, 20, 16, nPass, ct, 2)
+    ok &= wgrad_case(lib, "pair 5x5 s2 parity N256 C128 odd", (3, 10, 9, 256), (3, 4, 10, 9, 128), taps_kxk_s2(5, 2), z0 * 25, 3, 10, 9, 3, 128, 1)
     ok &= wgrad_case(lib, "ztaps (1dto2d style) 20 taps", (4, 20, 16, 256), (4, 1, 1, 16, 256),
                      [(0, 0, 0, h) for h in range(20)], [(0, h, 0, 0) for h in range(20)], 4, 1, 16, 3, 128, 1)
     return ok
