@@ -2,6 +2,7 @@
 #include "../../include/mcgvc.h"
 #include "network.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 using namespace mcgvc;
@@ -10,9 +11,53 @@ static int g_backend = MCGVC_BACKEND_TCGEN05;
 static int g_precision = MCGVC_PRECISION_PARITY;
 
 // parity: every GEMM split-bf16 x3; fast: every GEMM single bf16; mixed: forward x3, backward x1
+// Backward passes run on two engine-owned streams per device: a HIGH-priority main stream for the
+// critical path (layer kernels + data-gradient convs) and a low-priority side stream for the
+// weight-gradient GEMMs, which only feed the gradient blob and fill whatever SM time the main chain
+// leaves.  The caller's stream waits for both before the call returns control of the buffers
+// (stream-ordered), so the C ABI contract "work is enqueued on the caller's stream" still holds.
+// MCGVC_OVERLAP=0 runs everything on the caller's stream.
+struct DevStreams {
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t in = nullptr, out = nullptr;
+};
+static DevStreams* dev_streams() {
+  static DevStreams ds[64];
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("MCGVC_OVERLAP"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  DevStreams& d = ds[dev];
+  if (!d.main) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi is the numerically smallest = greatest priority
+    if (cudaStreamCreateWithPriority(&d.main, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&d.side, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&d.in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&d.out, cudaEventDisableTiming);
+  }
+  return &d;
+}
 static RunCfg cfg(void* stream, bool backward = false) {
   int np = g_precision == MCGVC_PRECISION_PARITY ? 3 : (g_precision == MCGVC_PRECISION_FAST ? 1 : (backward ? 1 : 3));
-  return RunCfg{(cudaStream_t)stream, g_backend, np};
+  return RunCfg{(cudaStream_t)stream, g_backend, np, nullptr};
+}
+// run a backward body on the engine streams, bracketed by event hand-offs with the caller's stream
+template <class F>
+static int run_backward(void* stream, F body) {
+  RunCfg rc = cfg(stream, true);
+  DevStreams* d = dev_streams();
+  if (!d) return body(rc);
+  cudaStream_t caller = (cudaStream_t)stream;
+  cudaEventRecord(d->in, caller);
+  cudaStreamWaitEvent(d->main, d->in, 0);
+  rc.stream = d->main;
+  rc.side = d->side;
+  const int rv = body(rc);               // joins the side stream into d->main before returning
+  cudaEventRecord(d->out, d->main);
+  cudaStreamWaitEvent(caller, d->out, 0);
+  return rv;
 }
 static const ModelDesc* desc(int model) {
   if (model == MCGVC_GENERATOR) return &generator_desc();
@@ -89,7 +134,7 @@ int mcgvc_generator_backward(const void* packed, const void* saved, const float*
                              int need_wgrad, void* ws, void* stream) {
   if (!shape_ok(B, T)) return 1;
   if (!packed || !saved || !mask || !dout || !ws || (need_wgrad && !gblob)) { set_error("generator_backward: null pointer"); return 1; }
-  return generator_backward(packed, saved, mask, dout, B, T, dx, gblob, need_wgrad, ws, cfg(stream, true));
+  return run_backward(stream, [&](const RunCfg& rc) { return generator_backward(packed, saved, mask, dout, B, T, dx, gblob, need_wgrad, ws, rc); });
 }
 int mcgvc_discriminator_forward(const void* packed, const float* x, int B, int T, float* out,
                                 void* saved, void* ws, void* stream) {
@@ -102,7 +147,7 @@ int mcgvc_discriminator_backward(const void* packed, const void* saved, const fl
                                  int need_wgrad, void* ws, void* stream) {
   if (!shape_ok(B, T)) return 1;
   if (!packed || !saved || !out || !dout || !ws || (need_wgrad && !gblob)) { set_error("discriminator_backward: null pointer"); return 1; }
-  return discriminator_backward(packed, saved, out, dout, B, T, dx, gblob, need_wgrad, ws, cfg(stream, true));
+  return run_backward(stream, [&](const RunCfg& rc) { return discriminator_backward(packed, saved, out, dout, B, T, dx, gblob, need_wgrad, ws, rc); });
 }
 
 long long mcgvc_launch_count(void) { return launch_count(); }

@@ -207,6 +207,26 @@ namespace {
 struct Run {
   RunCfg rc;
   bool ok = true;
+  bool forked = false;
+  cudaEvent_t ev = nullptr;
+  // weight-gradient GEMMs go to a side stream: they only feed the gradient blob, so they overlap
+  // with the bandwidth-bound layer kernels and data-gradient convs of the main chain
+  cudaStream_t wgrad_stream() {
+    if (!rc.side) return rc.stream;
+    if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaEventRecord(ev, rc.stream);          // everything the wgrad reads has been enqueued
+    cudaStreamWaitEvent(rc.side, ev, 0);
+    forked = true;
+    return rc.side;
+  }
+  void join() {
+    if (forked && rc.side) {
+      cudaEventRecord(ev, rc.side);
+      cudaStreamWaitEvent(rc.stream, ev, 0);
+      forked = false;
+    }
+    if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+  }
   void check(cudaError_t e, const char* what) {
     if (e != cudaSuccess && ok) {
       ok = false;
@@ -376,7 +396,8 @@ void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList&
   g.dw = dw;
   g.nPass = r.rc.nPass;
   g.algoFlops = 2.0 * pB * pY * pX * (double)g.N * g.C * xtaps.n * algoFrac;
-  r.check(r.rc.backend == 0 ? launch_wgrad_tc(g, r.rc.stream) : launch_wgrad_simt(g, r.rc.stream), what);
+  cudaStream_t ws = r.wgrad_stream();
+  r.check(r.rc.backend == 0 ? launch_wgrad_tc(g, ws) : launch_wgrad_simt(g, ws), what);
 }
 
 ActOperand plain_op(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int B, int Y, int X, int C) {
@@ -700,9 +721,8 @@ long long generator_bwd_ws_bytes(int B, int T) {
   add(M2 * 256 * 4);                             // dU0
   add(M2 * 256 * 2); add(M2 * 256 * 2);          // dz6
   for (int i = 0; i < 7; ++i) add(L * 256 * 4);  // dR
-  add(L * 256 * 2); add(L * 256 * 2);            // dz5
+  for (int i = 0; i < 6; ++i) { add(L * 256 * 2); add(L * 256 * 2); add(L * 1024 * 2); add(L * 1024 * 2); }  // dz5, dz4 per block
   add(L * 512 * 4);                              // dH
-  add(L * 1024 * 2); add(L * 1024 * 2);          // dz4
   add(L * 256 * 2); add(L * 256 * 2);            // dz3
   add(M2 * 256 * 4);                             // dA2
   add(M2 * 512 * 2); add(M2 * 512 * 2);          // dz2
@@ -795,10 +815,12 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   }
   // ---- residual blocks, reversed
   const TapList k3f = taps_s1(1, 3, 0, 1, 1), k3b = taps_s1(1, 3, 0, 1, -1);
-  BfPair dz5 = take_pair(a, L * 256, nullptr);
   float* dH = a.takeT<float>(L * 512);
-  BfPair dz4 = take_pair(a, L * 1024, nullptr);
   for (int i = 5; i >= 0; --i) {
+    // one dz pair per block: the weight-gradient GEMMs read them from the side stream while the
+    // main stream already works on the next block
+    BfPair dz5 = take_pair(a, L * 256, nullptr);
+    BfPair dz4 = take_pair(a, L * 1024, nullptr);
     const ConvDesc& ca = cv[G_RES0 + 2 * i];
     const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
     const int na = GN_RES0 + 2 * i, nb = GN_RES0 + 2 * i + 1;
@@ -885,6 +907,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
              d.T, plain_out(dX15, 80, d.T, 64), nullptr, nullptr, "G stem dgrad", 150.0 / 320.0);
     if (r.ok) r.check(launch_col2im_g(dX15, mask, B, d.T, dx, st), "G col2im");
   }
+  r.join();
   return r.ok ? 0 : 1;
 }
 
@@ -1096,6 +1119,7 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
     if (r.ok) r.check(launch_col2im_d(dXd, B, d.T, dx, st), "D col2im");
   }
   (void)M1; (void)M2;
+  r.join();
   return r.ok ? 0 : 1;
 }
 

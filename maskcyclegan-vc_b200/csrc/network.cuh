@@ -54,6 +54,7 @@ struct RunCfg {
   cudaStream_t stream;
   int backend;   // 0 = tcgen05/TMA kernels, 1 = SIMT checking kernels
   int nPass;     // passes used by the call: 3 = split-bf16, 1 = bf16 (capi picks it per direction)
+  cudaStream_t side;  // stream for the weight-gradient GEMMs of a backward pass, or null (same stream)
 };
 
 // sizes (bytes) of the per-call buffers the caller provides
