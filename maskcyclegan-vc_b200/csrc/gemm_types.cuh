@@ -50,6 +50,10 @@ struct ConvGeom {
   const float* addsrc;  // same addressing as out, or null
   int nPass;            // 1 = bf16 (hi only), 3 = split-bf16 (hi*hi + hi*lo + lo*hi)
   double algoFlops;     // algorithmic FLOPs of this launch (real conv MACs x 2), for profiling
+  // optional fused InstanceNorm statistics: per-(image, column) sums of z and z^2, [oB][N] each
+  float* statSum;
+  float* statSq;
+  int statSeg;          // lanes of an epilogue warp that share an image: min(32, BX*BY)
 };
 
 // Weight-gradient GEMM:  dW[w_t][n][c] += sum over positions (b,y,x) in this CTA's K-slice of

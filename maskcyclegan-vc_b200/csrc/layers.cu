@@ -106,6 +106,35 @@ cudaError_t launch_stats(const float* z, int Nz, int P, int nImg, int groups, fl
   return launched();
 }
 
+// Statistics accumulated by the conv epilogue (sums of z and z^2 per image and column): turn them
+// into mean / rstd, pooling `groups` column groups (PixelShuffle sub-positions) per stat channel.
+__global__ void stats_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sq,
+                                      int nImg, int Nz, int groups, float invCount,
+                                      float* __restrict__ mean, float* __restrict__ rstd) {
+  const int Nstat = Nz / groups;
+  const long long total = (long long)nImg * Nstat;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int s = (int)(idx % Nstat);
+  const long long img = idx / Nstat;
+  float s1 = 0.f, s2 = 0.f;
+  for (int g = 0; g < groups; ++g) {
+    s1 += sum[img * Nz + g * Nstat + s];
+    s2 += sq[img * Nz + g * Nstat + s];
+  }
+  const float m = s1 * invCount;
+  const float var = fmaxf(s2 * invCount - m * m, 0.f);
+  mean[idx] = m;
+  rstd[idx] = rsqrtf(var + 1e-5f);
+}
+cudaError_t launch_stats_finalize(const float* sum, const float* sq, int nImg, int Nz, int groups,
+                                  int countPerGroup, float* mean, float* rstd, cudaStream_t s) {
+  const long long total = (long long)nImg * (Nz / groups);
+  stats_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+      sum, sq, nImg, Nz, groups, 1.f / ((float)countPerGroup * groups), mean, rstd);
+  return launched();
+}
+
 // ------------------------------------------------------------------------------------------------
 // shared per-4-channel helpers
 struct Norm4 {
@@ -779,6 +808,97 @@ cudaError_t launch_pack_vec(int kind, const float* ref, int n, float* eng, cudaS
 }
 cudaError_t launch_unpack_vec(int kind, const float* eng, int n, float* dref, cudaStream_t s) {
   unpack_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(kind, eng, n, dref);
+  return launched();
+}
+
+
+// ---- table-driven packing: one launch per model ------------------------------------------------
+__device__ __forceinline__ PackArgs entry_args(const PackEntry& e) {
+  PackArgs a{};
+  a.kind = e.kind; a.N = e.N; a.C = e.C; a.T = e.T; a.nOffset = e.nOffset;
+  a.Np = e.Np; a.Cp = e.Cp; a.Tp = e.Tp; a.Cd = e.Cd;
+  return a;
+}
+__global__ void pack_weights_table_kernel(const __grid_constant__ PackTable t,
+                                          const float* __restrict__ params,
+                                          __nv_bfloat16* __restrict__ packed) {
+  const PackEntry& e = t.e[blockIdx.y];
+  const PackArgs a = entry_args(e);
+  const float* ref = params + e.refOff;
+  const long long total = (long long)e.N * e.C * e.T;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int tt = (int)(idx % e.T);
+    const int c = (int)((idx / e.T) % e.C);
+    const int n = (int)(idx / ((long long)e.T * e.C));
+    int tp, np, cp;
+    pack_map(a, n, c, tt, &tp, &np, &cp);
+    const float v = ref[idx];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const long long fo = ((long long)tp * e.Np + np) * e.Cp + cp;
+    packed[e.fHi + fo] = h;
+    packed[e.fLo + fo] = l;
+    if (e.dHi >= 0) {
+      const long long dO = (e.kind == kPack1dTo2d)
+                               ? ((long long)(np / 256) * e.Cd + cp) * 256 + (np % 256)
+                               : ((long long)tp * e.Cd + cp) * e.Np + np;
+      packed[e.dHi + dO] = h;
+      packed[e.dLo + dO] = l;
+    }
+  }
+}
+cudaError_t launch_pack_weights_table(const PackTable& t, const float* params, __nv_bfloat16* packed,
+                                      cudaStream_t s) {
+  dim3 grid(592, t.count);
+  pack_weights_table_kernel<<<grid, 256, 0, s>>>(t, params, packed);
+  return launched();
+}
+__global__ void unpack_wgrads_table_kernel(const __grid_constant__ PackTable t,
+                                           const float* __restrict__ gblob,
+                                           float* __restrict__ gradFlat) {
+  const PackEntry& e = t.e[blockIdx.y];
+  const PackArgs a = entry_args(e);
+  const float* dw = gblob + e.gW;
+  float* dref = gradFlat + e.refOff;
+  const long long total = (long long)e.N * e.C * e.T;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int tt = (int)(idx % e.T);
+    const int c = (int)((idx / e.T) % e.C);
+    const int n = (int)(idx / ((long long)e.T * e.C));
+    int tp, np, cp;
+    pack_map(a, n, c, tt, &tp, &np, &cp);
+    dref[idx] += dw[((long long)tp * e.Np + np) * e.Cp + cp];
+  }
+}
+cudaError_t launch_unpack_wgrads_table(const PackTable& t, const float* gblob, float* gradFlat,
+                                       cudaStream_t s) {
+  dim3 grid(592, t.count);
+  unpack_wgrads_table_kernel<<<grid, 256, 0, s>>>(t, gblob, gradFlat);
+  return launched();
+}
+__global__ void pack_vecs_table_kernel(const __grid_constant__ VecTable t,
+                                       const float* __restrict__ params, float* __restrict__ eng) {
+  const VecEntry& e = t.e[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += gridDim.x * blockDim.x)
+    eng[e.engOff + vec_map(e.kind, i, e.n)] = params[e.refOff + i];
+}
+__global__ void unpack_vecs_table_kernel(const __grid_constant__ VecTable t,
+                                         const float* __restrict__ eng, float* __restrict__ gradFlat) {
+  const VecEntry& e = t.e[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += gridDim.x * blockDim.x)
+    gradFlat[e.refOff + i] += eng[e.engOff + vec_map(e.kind, i, e.n)];
+}
+cudaError_t launch_pack_vecs_table(const VecTable& t, const float* params, float* eng, cudaStream_t s) {
+  dim3 grid(4, t.count);
+  pack_vecs_table_kernel<<<grid, 256, 0, s>>>(t, params, eng);
+  return launched();
+}
+cudaError_t launch_unpack_vecs_table(const VecTable& t, const float* eng, float* gradFlat,
+                                     cudaStream_t s) {
+  dim3 grid(4, t.count);
+  unpack_vecs_table_kernel<<<grid, 256, 0, s>>>(t, eng, gradFlat);
   return launched();
 }
 

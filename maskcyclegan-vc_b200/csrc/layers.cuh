@@ -64,6 +64,8 @@ struct ApplyBwdArgs {
 
 cudaError_t launch_stats(const float* z, int Nz, int P, int nImg, int groups, float* mean,
                          float* rstd, cudaStream_t s);
+cudaError_t launch_stats_finalize(const float* sum, const float* sq, int nImg, int Nz, int groups,
+                                  int countPerGroup, float* mean, float* rstd, cudaStream_t s);
 cudaError_t launch_apply_fwd(const ApplyArgs& a, cudaStream_t s);
 cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s);
 cudaError_t launch_apply_bwd(const ApplyBwdArgs& a, cudaStream_t s);
@@ -120,6 +122,32 @@ cudaError_t launch_unpack_wgrad(const PackArgs& a, const float* dw_engine, float
 enum VecKind { kVecIdent = 0, kVecShuffle = 1, kVecHC20 = 2 };
 cudaError_t launch_pack_vec(int kind, const float* ref, int n, float* eng, cudaStream_t s);
 cudaError_t launch_unpack_vec(int kind, const float* eng, int n, float* dref, cudaStream_t s);
+
+// Table-driven variants: one launch packs / unpacks every tensor of a model (blockIdx.y = entry).
+struct PackEntry {
+  int kind, N, C, T, nOffset, Np, Cp, Tp, Cd;
+  int refOff;             // float offset in the reference-order flat buffer
+  int fHi, fLo, dHi, dLo; // bf16 element offsets in the packed blob (dHi < 0: no data-gradient copy)
+  int gW;                 // float offset in the engine-layout gradient blob
+};
+struct PackTable {
+  int count;
+  PackEntry e[32];
+};
+struct VecEntry {
+  int kind, n, refOff, engOff;
+};
+struct VecTable {
+  int count;
+  VecEntry e[96];
+};
+cudaError_t launch_pack_weights_table(const PackTable& t, const float* params, __nv_bfloat16* packed,
+                                      cudaStream_t s);
+cudaError_t launch_unpack_wgrads_table(const PackTable& t, const float* gblob, float* gradFlat,
+                                       cudaStream_t s);
+cudaError_t launch_pack_vecs_table(const VecTable& t, const float* params, float* eng, cudaStream_t s);
+cudaError_t launch_unpack_vecs_table(const VecTable& t, const float* eng, float* gradFlat,
+                                     cudaStream_t s);
 
 cudaError_t launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
 

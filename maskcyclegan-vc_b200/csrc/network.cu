@@ -330,7 +330,7 @@ OutAddr plain_out(float* out, int Y, int X, int N) {
 
 void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& taps, int oB, int oY,
               int oX, const OutAddr& o, const float* bias, const float* addsrc, const char* what,
-              double algoFrac = 1.0) {
+              double algoFrac = 1.0, float* statSum = nullptr, float* statSq = nullptr) {
   if (!r.ok) return;
   ConvGeom g{};
   g.a = a;
@@ -347,8 +347,12 @@ void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& t
   g.out = o.out; g.bias = bias; g.addsrc = addsrc;
   g.nPass = r.rc.nPass;
   g.algoFlops = 2.0 * oB * oY * oX * (double)w.N * taps.n * a.C * algoFrac;
+  g.statSum = r.rc.backend == 0 ? statSum : nullptr;
+  g.statSq = statSq;
+  g.statSeg = g.BX * g.BY >= 32 ? 32 : g.BX * g.BY;
   r.check(r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream), what);
 }
+
 
 void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList& xtaps,
                const TapList* ztaps, int pB, int pY, int pX, float* dw, const char* what,
@@ -431,6 +435,31 @@ Stat take_stat(Arena& a, long long n) {
   return s;
 }
 
+// Convolution whose output feeds an InstanceNorm: the statistics come out of the conv epilogue
+// (tcgen05 backend) or from the stand-alone statistics kernel (SIMT checking backend, or
+// MCGVC_FUSED_STATS=0).  statImgs x statNz is the statistics grid over the conv's [oB][N] output.
+bool fused_stats_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MCGVC_FUSED_STATS"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+void run_conv_in(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& taps, int oB, int oY,
+                 int oX, const OutAddr& o, const float* bias, const char* what, float* ssum, float* ssq,
+                 int statImgs, int statNz, int groups, int planePositions, const Stat& st, const float* z) {
+  if (!r.ok) return;
+  const bool fused = r.rc.backend == 0 && fused_stats_enabled();
+  if (fused) {
+    const size_t bytes = (size_t)statImgs * statNz * sizeof(float);
+    r.check(cudaMemsetAsync(ssum, 0, bytes, r.rc.stream), what);
+    r.check(cudaMemsetAsync(ssq, 0, bytes, r.rc.stream), what);
+    run_conv(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0, ssum, ssq);
+    if (r.ok) r.check(launch_stats_finalize(ssum, ssq, statImgs, statNz, groups, planePositions, st.mean, st.rstd, r.rc.stream), what);
+  } else {
+    run_conv(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what);
+    if (r.ok) r.check(launch_stats(z, statNz, planePositions, statImgs, groups, st.mean, st.rstd, r.rc.stream), what);
+  }
+}
+
 ApplyArgs mk_apply(int mode, const float* z, int Nz, int zY, int zX, const Stat& st, int Nstat,
                    const float* gamma, const float* beta, int affPeriod, const float* residual,
                    ActBuf out) {
@@ -462,58 +491,57 @@ void run_bwd(Run& r, const ApplyBwdArgs& a, const char* what) {
 
 // ================================================================================================
 // packing
+namespace {
+PackTable make_pack_table(const ModelDesc& d) {
+  PackTable t{};
+  for (const ConvDesc& c : d.convs)
+    for (int p = 0; p < c.nParts; ++p) {
+      PackEntry& e = t.e[t.count++];
+      e.kind = c.kind; e.N = c.refN; e.C = c.refC; e.T = c.refT; e.nOffset = p * c.refN;
+      e.Np = c.Np; e.Cp = c.Cp; e.Tp = c.Tp; e.Cd = c.Cd;
+      e.refOff = (int)c.wOff[p];
+      e.fHi = (int)c.fHi; e.fLo = (int)c.fLo;
+      e.dHi = c.Cd ? (int)c.dHi : -1; e.dLo = c.Cd ? (int)c.dLo : -1;
+      e.gW = (int)c.gW;
+    }
+  return t;
+}
+// small vectors: engine offsets are into the packed fp32 area (pack) or the gradient blob (unpack)
+VecTable make_vec_table(const ModelDesc& d, bool grads) {
+  VecTable t{};
+  for (const ConvDesc& c : d.convs)
+    for (int p = 0; p < c.nParts; ++p)
+      t.e[t.count++] = VecEntry{c.biasKind, c.refN, (int)c.bOff[p], (int)((grads ? c.gB : c.biasEng) + p * c.refN)};
+  for (const NormDesc& n : d.norms)
+    for (int p = 0; p < n.nParts; ++p) {
+      t.e[t.count++] = VecEntry{n.vecKind, n.n, (int)n.gOff[p], (int)((grads ? n.gGamma : n.gammaEng) + p * n.n)};
+      t.e[t.count++] = VecEntry{n.vecKind, n.n, (int)n.bOff[p], (int)((grads ? n.gBeta : n.betaEng) + p * n.n)};
+    }
+  return t;
+}
+}  // namespace
+
 int pack_model(const ModelDesc& d, const float* params, void* packed, const RunCfg& rc) {
   Run r{rc};
   __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(packed);
   float* f32 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + d.packedBf16 * 2);
   // padding elements (unused taps / channels) must be zero
   r.check(launch_fill_zero(packed, (size_t)d.packed_bytes(), rc.stream), "pack: zero");
-  for (const ConvDesc& c : d.convs) {
-    for (int p = 0; p < c.nParts; ++p) {
-      PackArgs a{};
-      a.kind = c.kind;
-      a.ref = params + c.wOff[p];
-      a.N = c.refN; a.C = c.refC; a.T = c.refT;
-      a.nOffset = p * c.refN;
-      a.Np = c.Np; a.Cp = c.Cp; a.Tp = c.Tp;
-      a.f_hi = bf + c.fHi; a.f_lo = bf + c.fLo;
-      a.d_hi = c.Cd ? bf + c.dHi : nullptr;
-      a.d_lo = c.Cd ? bf + c.dLo : nullptr;
-      a.Cd = c.Cd;
-      r.check(launch_pack_weight(a, rc.stream), "pack: weight");
-      r.check(launch_pack_vec(c.biasKind, params + c.bOff[p], c.refN, f32 + c.biasEng + p * c.refN,
-                              rc.stream), "pack: bias");
-    }
-  }
-  for (const NormDesc& n : d.norms) {
-    for (int p = 0; p < n.nParts; ++p) {
-      r.check(launch_pack_vec(n.vecKind, params + n.gOff[p], n.n, f32 + n.gammaEng + p * n.n, rc.stream), "pack: gamma");
-      r.check(launch_pack_vec(n.vecKind, params + n.bOff[p], n.n, f32 + n.betaEng + p * n.n, rc.stream), "pack: beta");
-    }
-  }
+  const PackTable pt = make_pack_table(d);
+  const VecTable vt = make_vec_table(d, false);
+  if (pt.count > 32 || vt.count > 96) { set_error("pack tables too small"); return 1; }
+  r.check(launch_pack_weights_table(pt, params, bf, rc.stream), "pack: weights");
+  r.check(launch_pack_vecs_table(vt, params, f32, rc.stream), "pack: vectors");
   return r.ok ? 0 : 1;
 }
 
 int unpack_grads(const ModelDesc& d, const float* gblob, float* gradFlat, const RunCfg& rc) {
   Run r{rc};
-  for (const ConvDesc& c : d.convs) {
-    for (int p = 0; p < c.nParts; ++p) {
-      PackArgs a{};
-      a.kind = c.kind;
-      a.N = c.refN; a.C = c.refC; a.T = c.refT;
-      a.nOffset = p * c.refN;
-      a.Np = c.Np; a.Cp = c.Cp; a.Tp = c.Tp;
-      r.check(launch_unpack_wgrad(a, gblob + c.gW, gradFlat + c.wOff[p], rc.stream), "unpack: weight");
-      r.check(launch_unpack_vec(c.biasKind, gblob + c.gB + p * c.refN, c.refN, gradFlat + c.bOff[p],
-                                rc.stream), "unpack: bias");
-    }
-  }
-  for (const NormDesc& n : d.norms) {
-    for (int p = 0; p < n.nParts; ++p) {
-      r.check(launch_unpack_vec(n.vecKind, gblob + n.gGamma + p * n.n, n.n, gradFlat + n.gOff[p], rc.stream), "unpack: gamma");
-      r.check(launch_unpack_vec(n.vecKind, gblob + n.gBeta + p * n.n, n.n, gradFlat + n.bOff[p], rc.stream), "unpack: beta");
-    }
-  }
+  const PackTable pt = make_pack_table(d);
+  const VecTable vt = make_vec_table(d, true);
+  if (pt.count > 32 || vt.count > 96) { set_error("pack tables too small"); return 1; }
+  r.check(launch_unpack_wgrads_table(pt, gblob, gradFlat, rc.stream), "unpack: weights");
+  r.check(launch_unpack_vecs_table(vt, gblob, gradFlat, rc.stream), "unpack: vectors");
   return r.ok ? 0 : 1;
 }
 
@@ -603,7 +631,7 @@ std::vector<SavedEntry> generator_saved_layout(int B, int T) {
 }
 long long generator_fwd_ws_bytes(int B, int T) {
   GenDims d(B, T);
-  return align_up((long long)B * 80 * d.X2 * 128 * 4, 256) + 256;
+  return align_up((long long)B * 80 * d.X2 * 128 * 4, 256) + 2 * align_up((long long)B * 5120 * 4, 256) + 1024;
 }
 
 int generator_forward(const void* packed, const float* x, const float* mask, int B, int T,
@@ -616,6 +644,9 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   cudaStream_t st = rc.stream;
   const auto& cv = md.convs;
   const auto& nm = md.norms;
+  Arena wa(ws);
+  float* ssum = wa.takeT<float>((long long)B * 5120);   // conv-epilogue statistics accumulators
+  float* ssq = wa.takeT<float>((long long)B * 5120);
 
   // parity-split buffers have a padding column/row when the extent is odd: keep it zero
   if (d.T & 1) {
@@ -635,22 +666,22 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
                                               nullptr, nullptr, 1, nullptr,
                                               abuf(s.A0, nullptr, B, 80, T, 128, 1)), st), "G stem glu");
   // downSample1 / downSample2: 5x5 stride 2 conv || gates, IN, gated GLU         model.py:245-246
-  run_conv(r, parity_op(s.A0.hi, s.A0.lo, B, 80, T, 128), W.fwd(cv[G_DS1]), taps_s2_fwd(5, 2), B, 40,
-           d.W1, plain_out(s.z1, 40, d.W1, 512), W.bias(cv[G_DS1]), nullptr, "G ds1 conv");
-  if (r.ok) r.check(launch_stats(s.z1, 512, 40 * d.W1, B, 1, s.st1.mean, s.st1.rstd, st), "G ds1 stats");
+  run_conv_in(r, parity_op(s.A0.hi, s.A0.lo, B, 80, T, 128), W.fwd(cv[G_DS1]), taps_s2_fwd(5, 2), B, 40,
+              d.W1, plain_out(s.z1, 40, d.W1, 512), W.bias(cv[G_DS1]), "G ds1 conv", ssum, ssq, B, 512, 1,
+              40 * d.W1, s.st1, s.z1);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z1, 512, 40, d.W1, s.st1, 512, W.gamma(nm[GN_DS1]),
                                               W.beta(nm[GN_DS1]), 1, nullptr,
                                               abuf(s.A1, nullptr, B, 40, d.W1, 256, 1)), st), "G ds1 glu");
-  run_conv(r, parity_op(s.A1.hi, s.A1.lo, B, 40, d.W1, 256), W.fwd(cv[G_DS2]), taps_s2_fwd(5, 2), B,
-           20, d.W2, plain_out(s.z2, 20, d.W2, 512), W.bias(cv[G_DS2]), nullptr, "G ds2 conv");
-  if (r.ok) r.check(launch_stats(s.z2, 512, 20 * d.W2, B, 1, s.st2.mean, s.st2.rstd, st), "G ds2 stats");
+  run_conv_in(r, parity_op(s.A1.hi, s.A1.lo, B, 40, d.W1, 256), W.fwd(cv[G_DS2]), taps_s2_fwd(5, 2), B,
+              20, d.W2, plain_out(s.z2, 20, d.W2, 512), W.bias(cv[G_DS2]), "G ds2 conv", ssum, ssq, B, 512, 1,
+              20 * d.W2, s.st2, s.z2);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[GN_DS2]),
                                               W.beta(nm[GN_DS2]), 1, nullptr,
                                               abuf(s.A2, nullptr, B, 20, d.W2, 256, 0)), st), "G ds2 glu");
   // 2D -> 1D: view (c*20+h), Conv1d k1 5120->256, IN1d                           model.py:249-255
-  run_conv(r, plain_op(s.A2.hi, s.A2.lo, B, 20, d.W2, 256), W.fwd(cv[G_2DTO1D]), taps_rows(20, 1), B,
-           1, d.W2, plain_out(s.z3, 1, d.W2, 256), W.bias(cv[G_2DTO1D]), nullptr, "G 2dto1d conv");
-  if (r.ok) r.check(launch_stats(s.z3, 256, d.W2, B, 1, s.st3.mean, s.st3.rstd, st), "G 2dto1d stats");
+  run_conv_in(r, plain_op(s.A2.hi, s.A2.lo, B, 20, d.W2, 256), W.fwd(cv[G_2DTO1D]), taps_rows(20, 1), B,
+              1, d.W2, plain_out(s.z3, 1, d.W2, 256), W.bias(cv[G_2DTO1D]), "G 2dto1d conv", ssum, ssq, B, 256,
+              1, d.W2, s.st3, s.z3);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z3, 256, 1, d.W2, s.st3, 256, W.gamma(nm[GN_2DTO1D]),
                                               W.beta(nm[GN_2DTO1D]), 1, nullptr,
                                               abuf(s.R[0], s.Rf[0], B, 1, d.W2, 256, 0)), st), "G 2dto1d IN");
@@ -661,15 +692,15 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
     const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
     const NormDesc& na = nm[GN_RES0 + 2 * i];
     const NormDesc& nb = nm[GN_RES0 + 2 * i + 1];
-    run_conv(r, plain_op(s.R[i].hi, s.R[i].lo, B, 1, d.W2, 256), W.fwd(ca), k3, B, 1, d.W2,
-             plain_out(s.z4[i], 1, d.W2, 1024), W.bias(ca), nullptr, "G res conv a");
-    if (r.ok) r.check(launch_stats(s.z4[i], 1024, d.W2, B, 1, s.st4[i].mean, s.st4[i].rstd, st), "G res stats a");
+    run_conv_in(r, plain_op(s.R[i].hi, s.R[i].lo, B, 1, d.W2, 256), W.fwd(ca), k3, B, 1, d.W2,
+                plain_out(s.z4[i], 1, d.W2, 1024), W.bias(ca), "G res conv a", ssum, ssq, B, 1024, 1, d.W2,
+                s.st4[i], s.z4[i]);
     if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z4[i], 1024, 1, d.W2, s.st4[i], 1024, W.gamma(na),
                                                 W.beta(na), 1, nullptr,
                                                 abuf(s.H[i], nullptr, B, 1, d.W2, 512, 0)), st), "G res glu");
-    run_conv(r, plain_op(s.H[i].hi, s.H[i].lo, B, 1, d.W2, 512), W.fwd(cb), k3, B, 1, d.W2,
-             plain_out(s.z5[i], 1, d.W2, 256), W.bias(cb), nullptr, "G res conv b");
-    if (r.ok) r.check(launch_stats(s.z5[i], 256, d.W2, B, 1, s.st5[i].mean, s.st5[i].rstd, st), "G res stats b");
+    run_conv_in(r, plain_op(s.H[i].hi, s.H[i].lo, B, 1, d.W2, 512), W.fwd(cb), k3, B, 1, d.W2,
+                plain_out(s.z5[i], 1, d.W2, 256), W.bias(cb), "G res conv b", ssum, ssq, B, 256, 1, d.W2,
+                s.st5[i], s.z5[i]);
     if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z5[i], 256, 1, d.W2, s.st5[i], 256, W.gamma(nb),
                                                 W.beta(nb), 1, s.Rf[i],
                                                 abuf(s.R[i + 1], s.Rf[i + 1], B, 1, d.W2, 256, 0)), st), "G res add");
@@ -677,29 +708,27 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   // 1D -> 2D: Conv1d k1 256->5120, IN1d over time per (c,h) row, view (256,20,W)   model.py:266-271
   {
     OutAddr o{s.z6, (long long)20 * d.W2 * 256, 0, 256, 256, (long long)d.W2 * 256};
-    run_conv(r, plain_op(s.R[6].hi, s.R[6].lo, B, 1, d.W2, 256), W.fwd(cv[G_1DTO2D]), taps_one(), B, 1,
-             d.W2, o, W.bias(cv[G_1DTO2D]), nullptr, "G 1dto2d conv");
+    run_conv_in(r, plain_op(s.R[6].hi, s.R[6].lo, B, 1, d.W2, 256), W.fwd(cv[G_1DTO2D]), taps_one(), B, 1,
+                d.W2, o, W.bias(cv[G_1DTO2D]), "G 1dto2d conv", ssum, ssq, B * 20, 256, 1, d.W2, s.st6, s.z6);
   }
-  if (r.ok) r.check(launch_stats(s.z6, 256, d.W2, B * 20, 1, s.st6.mean, s.st6.rstd, st), "G 1dto2d stats");
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z6, 256, 1, d.W2, s.st6, 256, W.gamma(nm[GN_1DTO2D]),
                                               W.beta(nm[GN_1DTO2D]), 20, nullptr,
                                               abuf(s.U0, nullptr, B * 20, 1, d.W2, 256, 0)), st), "G 1dto2d IN");
   // upSample1 / upSample2: 5x5 conv, PixelShuffle(2), IN, swish                  model.py:274-275
   const TapList k55 = taps_s1(5, 5, 2, 2, 1);
-  run_conv(r, plain_op(s.U0.hi, s.U0.lo, B, 20, d.W2, 256), W.fwd(cv[G_UP1]), k55, B, 20, d.W2,
-           plain_out(s.z7, 20, d.W2, 1024), W.bias(cv[G_UP1]), nullptr, "G up1 conv");
-  if (r.ok) r.check(launch_stats(s.z7, 1024, 20 * d.W2, B, 4, s.st7.mean, s.st7.rstd, st), "G up1 stats");
+  run_conv_in(r, plain_op(s.U0.hi, s.U0.lo, B, 20, d.W2, 256), W.fwd(cv[G_UP1]), k55, B, 20, d.W2,
+              plain_out(s.z7, 20, d.W2, 1024), W.bias(cv[G_UP1]), "G up1 conv", ssum, ssq, B, 1024, 4,
+              20 * d.W2, s.st7, s.z7);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z7, 1024, 20, d.W2, s.st7, 256, W.gamma(nm[GN_UP1]),
                                               W.beta(nm[GN_UP1]), 1, nullptr,
                                               abuf(s.U1, nullptr, B, 40, d.X1, 256, 0)), st), "G up1 act");
-  run_conv(r, plain_op(s.U1.hi, s.U1.lo, B, 40, d.X1, 256), W.fwd(cv[G_UP2]), k55, B, 40, d.X1,
-           plain_out(s.z8, 40, d.X1, 512), W.bias(cv[G_UP2]), nullptr, "G up2 conv");
-  if (r.ok) r.check(launch_stats(s.z8, 512, 40 * d.X1, B, 4, s.st8.mean, s.st8.rstd, st), "G up2 stats");
+  run_conv_in(r, plain_op(s.U1.hi, s.U1.lo, B, 40, d.X1, 256), W.fwd(cv[G_UP2]), k55, B, 40, d.X1,
+              plain_out(s.z8, 40, d.X1, 512), W.bias(cv[G_UP2]), "G up2 conv", ssum, ssq, B, 512, 4,
+              40 * d.X1, s.st8, s.z8);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z8, 512, 40, d.X1, s.st8, 128, W.gamma(nm[GN_UP2]),
                                               W.beta(nm[GN_UP2]), 1, nullptr,
                                               abuf(s.U2, nullptr, B, 80, d.X2, 128, 0)), st), "G up2 act");
   // head: 5x15 conv 128->1 as per-tap GEMM + shifted sum                          model.py:278-279
-  Arena wa(ws);
   float* P = wa.takeT<float>((long long)B * 80 * d.X2 * 128);
   run_conv(r, plain_op(s.U2.hi, s.U2.lo, B, 80, d.X2, 128), W.fwd(cv[G_HEAD]), taps_one(), B, 80, d.X2,
            plain_out(P, 80, d.X2, 128), nullptr, nullptr, "G head gemm", 75.0 / 128.0);
@@ -962,7 +991,7 @@ std::vector<SavedEntry> discriminator_saved_layout(int B, int T) {
 }
 long long discriminator_fwd_ws_bytes(int B, int T) {
   DisDims d(B, T);
-  return align_up((long long)B * 10 * d.W3 * 128 * 4, 256) + 256;
+  return align_up((long long)B * 10 * d.W3 * 128 * 4, 256) + 2 * align_up((long long)B * 1024 * 4, 256) + 1024;
 }
 
 int discriminator_forward(const void* packed, const float* x, int B, int T, float* out, void* saved,
@@ -975,6 +1004,9 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
   cudaStream_t st = rc.stream;
   const auto& cv = md.convs;
   const auto& nm = md.norms;
+  Arena wa(ws);
+  float* ssum = wa.takeT<float>((long long)B * 1024);
+  float* ssq = wa.takeT<float>((long long)B * 1024);
   if (d.T & 1) {
     r.check(launch_fill_zero(s.D0.hi, parity_elems(B, 80, d.T, 128) * 2, st), "zero D0");
     r.check(launch_fill_zero(s.D0.lo, parity_elems(B, 80, d.T, 128) * 2, st), "zero D0");
@@ -995,23 +1027,22 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
                                               nullptr, 1, nullptr, abuf(s.D0, nullptr, B, 80, T, 128, 1)), st), "D stem act");
   // downSample1..3: 3x3 stride 2 conv + IN + swish                                 model.py:345-347
   const TapList k33 = taps_s2_fwd(3, 1);
-  run_conv(r, parity_op(s.D0.hi, s.D0.lo, B, 80, T, 128), W.fwd(cv[D_DS1]), k33, B, 40, d.W1,
-           plain_out(s.z1, 40, d.W1, 256), W.bias(cv[D_DS1]), nullptr, "D ds1 conv");
-  if (r.ok) r.check(launch_stats(s.z1, 256, 40 * d.W1, B, 1, s.st1.mean, s.st1.rstd, st), "D ds1 stats");
+  run_conv_in(r, parity_op(s.D0.hi, s.D0.lo, B, 80, T, 128), W.fwd(cv[D_DS1]), k33, B, 40, d.W1,
+              plain_out(s.z1, 40, d.W1, 256), W.bias(cv[D_DS1]), "D ds1 conv", ssum, ssq, B, 256, 1, 40 * d.W1,
+              s.st1, s.z1);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z1, 256, 40, d.W1, s.st1, 256, W.gamma(nm[DN_DS1]),
                                               W.beta(nm[DN_DS1]), 1, nullptr, abuf(s.D1, nullptr, B, 40, d.W1, 256, 1)), st), "D ds1 act");
-  run_conv(r, parity_op(s.D1.hi, s.D1.lo, B, 40, d.W1, 256), W.fwd(cv[D_DS2]), k33, B, 20, d.W2,
-           plain_out(s.z2, 20, d.W2, 512), W.bias(cv[D_DS2]), nullptr, "D ds2 conv");
-  if (r.ok) r.check(launch_stats(s.z2, 512, 20 * d.W2, B, 1, s.st2.mean, s.st2.rstd, st), "D ds2 stats");
+  run_conv_in(r, parity_op(s.D1.hi, s.D1.lo, B, 40, d.W1, 256), W.fwd(cv[D_DS2]), k33, B, 20, d.W2,
+              plain_out(s.z2, 20, d.W2, 512), W.bias(cv[D_DS2]), "D ds2 conv", ssum, ssq, B, 512, 1, 20 * d.W2,
+              s.st2, s.z2);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[DN_DS2]),
                                               W.beta(nm[DN_DS2]), 1, nullptr, abuf(s.D2, nullptr, B, 20, d.W2, 512, 1)), st), "D ds2 act");
-  run_conv(r, parity_op(s.D2.hi, s.D2.lo, B, 20, d.W2, 512), W.fwd(cv[D_DS3]), k33, B, 10, d.W3,
-           plain_out(s.z3, 10, d.W3, 1024), W.bias(cv[D_DS3]), nullptr, "D ds3 conv");
-  if (r.ok) r.check(launch_stats(s.z3, 1024, 10 * d.W3, B, 1, s.st3.mean, s.st3.rstd, st), "D ds3 stats");
+  run_conv_in(r, parity_op(s.D2.hi, s.D2.lo, B, 20, d.W2, 512), W.fwd(cv[D_DS3]), k33, B, 10, d.W3,
+              plain_out(s.z3, 10, d.W3, 1024), W.bias(cv[D_DS3]), "D ds3 conv", ssum, ssq, B, 1024, 1, 10 * d.W3,
+              s.st3, s.z3);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z3, 1024, 10, d.W3, s.st3, 1024, W.gamma(nm[DN_DS3]),
                                               W.beta(nm[DN_DS3]), 1, nullptr, abuf(s.D3, nullptr, B, 10, d.W3, 1024, 0)), st), "D ds3 act");
   // outputConvLayer 1x3 1024->1 + sigmoid                                          model.py:323-327,348
-  Arena wa(ws);
   float* P = wa.takeT<float>((long long)B * 10 * d.W3 * 128);
   run_conv(r, plain_op(s.D3.hi, s.D3.lo, B, 10, d.W3, 1024), W.fwd(cv[D_HEAD]), taps_one(), B, 10, d.W3,
            plain_out(P, 10, d.W3, 128), nullptr, nullptr, "D head gemm", 3.0 / 128.0);
