@@ -486,7 +486,10 @@ static cudaError_t launch_conv_tc_t(const ConvGeom& g, cudaStream_t stream) {
     tmAl = tmAh;
     tmWl = tmWh;
   }
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // cudaFuncSetAttribute is per device
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_done[dev_id & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, NPASS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -719,7 +722,10 @@ static cudaError_t launch_conv_tc2_t(const ConvGeom& g, cudaStream_t stream) {
     tmAl = tmAh;
     tmWl = tmWh;
   }
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // cudaFuncSetAttribute is per device
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_done[dev_id & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, NPASS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,

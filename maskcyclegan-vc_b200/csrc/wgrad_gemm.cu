@@ -222,7 +222,10 @@ static cudaError_t launch_wgrad_tc_t(const WgradGeom& g, cudaStream_t stream) {
     tmZl = tmZh;
     tmXl = tmXh;
   }
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // cudaFuncSetAttribute is per device
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_done[dev_id & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<CTILE, NPASS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -424,7 +427,10 @@ static cudaError_t launch_wgrad_tc2_t(const WgradGeom& g, cudaStream_t stream) {
     tmZl = tmZh;
     tmXl = tmXh;
   }
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // cudaFuncSetAttribute is per device
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_done[dev_id & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc2_kernel<CTILE, NPASS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
