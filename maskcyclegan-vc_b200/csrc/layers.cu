@@ -518,32 +518,146 @@ cudaError_t launch_prep_g(const float* x, const float* mask, int B, int T, __nv_
   return launched();
 }
 
-// Discriminator stem (model.py:290-294): Xd[b,h,w, kh*3+kw] = x[b,h+kh-1,w+kw-1]; 9 of 64 channels.
-__global__ void prep_d_kernel(const float* __restrict__ x, int B, int T,
-                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const long long total = (long long)B * 80 * T * 16;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(idx & 15) << 2;
-    const long long pos = idx >> 4;
+// Discriminator stem (model.py:290-295,344): 3x3 conv 1 -> 128 channels + swish.  With K = 9 this
+// is 4 FLOP/byte -- pure HBM work, so it runs on the CUDA cores, fused with the activation and the
+// parity-split bf16 hi/lo store (the tensor-core path would pad K to 64).  One warp per position,
+// each lane owns 4 output channels and keeps their 9 taps + bias in registers.  Weights come from
+// the packed blob ([128][64] bf16 hi/lo, tap = column), bias from the engine-order fp32 vector.
+struct StemW {
+  float w[4][9];
+  float b[4];
+};
+__device__ __forceinline__ StemW load_stem_w(const __nv_bfloat16* __restrict__ wh,
+                                             const __nv_bfloat16* __restrict__ wl,
+                                             const float* __restrict__ bias, int lane) {
+  StemW r;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int n = lane * 4 + c;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      r.w[c][t] = __bfloat162float(wh[n * 64 + t]) + __bfloat162float(wl[n * 64 + t]);
+    r.b[c] = bias[n];
+  }
+  return r;
+}
+__device__ __forceinline__ void load_patch(const float* __restrict__ x, long long b, int h, int w,
+                                           int T, float (&xv)[9]) {
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int hs = h + kh - 1, ws = w + kw - 1;
+      xv[kh * 3 + kw] = (hs >= 0 && hs < 80 && ws >= 0 && ws < T) ? __ldg(x + (b * 80 + hs) * T + ws) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) d_stem_fwd_kernel(const float* __restrict__ x, int B, int T,
+                                                         const __nv_bfloat16* __restrict__ wh,
+                                                         const __nv_bfloat16* __restrict__ wl,
+                                                         const float* __restrict__ bias, ActBuf out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const StemW sw = load_stem_w(wh, wl, bias, lane);
+  const long long total = (long long)B * 80 * T;
+  for (long long pos = warp; pos < total; pos += nwarps) {
     const int w = (int)(pos % T);
     const int h = (int)((pos / T) % 80);
     const long long b = pos / ((long long)T * 80);
-    float v[4];
+    float xv[9];
+    load_patch(x, b, h, w, T, xv);
+    float z[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int ch = c4 + i;
-      const int kh = ch / 3, kw = ch - kh * 3;
-      const int hs = h + kh - 1, ws = w + kw - 1;
-      v[i] = (ch < 9 && hs >= 0 && hs < 80 && ws >= 0 && ws < T) ? x[(b * 80 + hs) * T + ws] : 0.f;
+    for (int c = 0; c < 4; ++c) {
+      float acc = sw.b[c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], xv[t], acc);
+      z[c] = acc * sigmoidf_(acc);
     }
-    split_store4(hi, lo, pos * 64 + c4, make_float4(v[0], v[1], v[2], v[3]));
+    split_store4(out.hi, out.lo, act_off(out, (int)b, h, w) + lane * 4, make_float4(z[0], z[1], z[2], z[3]));
   }
 }
-cudaError_t launch_prep_d(const float* x, int B, int T, __nv_bfloat16* hi, __nv_bfloat16* lo,
-                          cudaStream_t s) {
-  const long long total = (long long)B * 80 * T * 16;
-  prep_d_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, B, T, hi, lo);
+cudaError_t launch_d_stem_fwd(const float* x, int B, int T, const __nv_bfloat16* wh,
+                              const __nv_bfloat16* wl, const float* bias, ActBuf out, cudaStream_t s) {
+  d_stem_fwd_kernel<<<148 * 8, 256, 0, s>>>(x, B, T, wh, wl, bias, out);
+  return launched();
+}
+
+// Backward of the stem: recompute z from x (9 MACs), dz = dA * swish'(z); weight / bias gradients
+// accumulate per lane, merge in shared memory and go to the engine-layout gradient blob
+// (dW[n][tap] at n*64 + tap); when the input needs a gradient, q[pos][tap] = sum_n dz[n] * w[n][tap]
+// is written for the 3x3 fold below.
+__global__ void __launch_bounds__(256) d_stem_bwd_kernel(const float* __restrict__ x, int B, int T,
+                                                         const __nv_bfloat16* __restrict__ wh,
+                                                         const __nv_bfloat16* __restrict__ wl,
+                                                         const float* __restrict__ bias, ActBuf dA,
+                                                         float* __restrict__ dW, float* __restrict__ dB,
+                                                         float* __restrict__ q) {
+  __shared__ float sacc[40 * 128];
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 40 * 128; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const StemW sw = load_stem_w(wh, wl, bias, lane);
+  float gw[4][9], gb[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    gb[c] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) gw[c][t] = 0.f;
+  }
+  const long long total = (long long)B * 80 * T;
+  for (long long pos = warp; pos < total; pos += nwarps) {
+    const int w = (int)(pos % T);
+    const int h = (int)((pos / T) % 80);
+    const long long b = pos / ((long long)T * 80);
+    float xv[9];
+    load_patch(x, b, h, w, T, xv);
+    const float4 d4 = ld4(dA.f32 + act_off(dA, (int)b, h, w) + lane * 4);
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+    float dz[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc = sw.b[c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], xv[t], acc);
+      dz[c] = d[c] * swish_grad(acc);
+      gb[c] += dz[c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) gw[c][t] = fmaf(dz[c], xv[t], gw[c][t]);
+    }
+    if (q) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float p = dz[0] * sw.w[0][t] + dz[1] * sw.w[1][t] + dz[2] * sw.w[2][t] + dz[3] * sw.w[3][t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == t) q[pos * 12 + t] = p;
+      }
+    }
+  }
+  if (dW) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = lane * 4 + c;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(&sacc[t * 128 + n], gw[c][t]);
+      atomicAdd(&sacc[9 * 128 + n], gb[c]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 10 * 128; i += blockDim.x) {
+      const int t = i / 128, n = i % 128;
+      if (t < 9) atomicAdd(dW + n * 64 + t, sacc[i]);
+      else atomicAdd(dB + n, sacc[i]);
+    }
+  }
+}
+cudaError_t launch_d_stem_bwd(const float* x, int B, int T, const __nv_bfloat16* wh,
+                              const __nv_bfloat16* wl, const float* bias, ActBuf dA, float* dW,
+                              float* dB, float* q, cudaStream_t s) {
+  d_stem_bwd_kernel<<<148 * 4, 256, 0, s>>>(x, B, T, wh, wl, bias, dA, dW, dB, q);
   return launched();
 }
 
@@ -695,8 +809,8 @@ cudaError_t launch_col2im_g(const float* dX15, const float* mask, int B, int T, 
   col2im_g_kernel<<<grid_for((long long)B * 80 * T, 128), 128, 0, s>>>(dX15, mask, B, T, dx);
   return launched();
 }
-//   Discriminator: dx[b,h,w] = sum_{kh,kw} dXd[(b,h-kh+1,w-kw+1), kh*3+kw]
-__global__ void col2im_d_kernel(const float* __restrict__ dX, int B, int T, float* __restrict__ dx) {
+//   Discriminator: dx[b,h,w] = sum_{kh,kw} q[(b,h-kh+1,w-kw+1)][kh*3+kw]   (q rows are 12 floats)
+__global__ void col2im_d_kernel(const float* __restrict__ q, int B, int T, float* __restrict__ dx) {
   const long long total = (long long)B * 80 * T;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -709,14 +823,14 @@ __global__ void col2im_d_kernel(const float* __restrict__ dX, int B, int T, floa
       if (hd < 0 || hd >= 80) continue;
       for (int kw = 0; kw < 3; ++kw) {
         const int wd = w - kw + 1;
-        if (wd >= 0 && wd < T) acc += dX[((b * 80 + hd) * T + wd) * 64 + kh * 3 + kw];
+        if (wd >= 0 && wd < T) acc += q[((b * 80 + hd) * T + wd) * 12 + kh * 3 + kw];
       }
     }
     dx[idx] = acc;
   }
 }
-cudaError_t launch_col2im_d(const float* dXd, int B, int T, float* dx, cudaStream_t s) {
-  col2im_d_kernel<<<grid_for((long long)B * 80 * T, 128), 128, 0, s>>>(dXd, B, T, dx);
+cudaError_t launch_col2im_d(const float* q, int B, int T, float* dx, cudaStream_t s) {
+  col2im_d_kernel<<<grid_for((long long)B * 80 * T, 128), 128, 0, s>>>(q, B, T, dx);
   return launched();
 }
 

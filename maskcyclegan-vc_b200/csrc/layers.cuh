@@ -73,8 +73,12 @@ cudaError_t launch_apply_bwd(const ApplyBwdArgs& a, cudaStream_t s);
 // stem operand builders
 cudaError_t launch_prep_g(const float* x, const float* mask, int B, int T, __nv_bfloat16* hi,
                           __nv_bfloat16* lo, cudaStream_t s);
-cudaError_t launch_prep_d(const float* x, int B, int T, __nv_bfloat16* hi, __nv_bfloat16* lo,
-                          cudaStream_t s);
+// Discriminator stem (3x3, 1 -> 128 channels, K = 9): direct CUDA-core kernels fused with swish
+cudaError_t launch_d_stem_fwd(const float* x, int B, int T, const __nv_bfloat16* wh,
+                              const __nv_bfloat16* wl, const float* bias, ActBuf out, cudaStream_t s);
+cudaError_t launch_d_stem_bwd(const float* x, int B, int T, const __nv_bfloat16* wh,
+                              const __nv_bfloat16* wl, const float* bias, ActBuf dA, float* dW,
+                              float* dB, float* q, cudaStream_t s);
 // heads: P is [B*Y*X][128] fp32 per-tap partial products
 cudaError_t launch_head_g_fwd(const float* P, const float* bias, int B, int Y, int X, float* out,
                               cudaStream_t s);
@@ -88,7 +92,7 @@ cudaError_t launch_head_d_bwd(const float* dout, const float* out, int B, int Y,
 // stem input gradients (col2im of the stem operand gradient)
 cudaError_t launch_col2im_g(const float* dX15, const float* mask, int B, int T, float* dx,
                             cudaStream_t s);
-cudaError_t launch_col2im_d(const float* dXd, int B, int T, float* dx, cudaStream_t s);
+cudaError_t launch_col2im_d(const float* q, int B, int T, float* dx, cudaStream_t s);
 
 // Weight packing.  Reference tensor is [N][C][T] fp32 (OIHW with T = KH*KW); `kind` selects how
 // engine coordinates (t', n', c') map onto it (see pack_map in layers.cu).

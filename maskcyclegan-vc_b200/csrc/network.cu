@@ -953,7 +953,7 @@ struct DisDims {
   }
 };
 struct DisSaved {
-  BfPair Xd; float* z0;
+  float* xin;     // copy of the input (the stem backward recomputes its pre-activation from it)
   BfPair D0; float* z1; Stat st1;
   BfPair D1; float* z2; Stat st2;
   BfPair D2; float* z3; Stat st3;
@@ -966,8 +966,7 @@ DisSaved plan_dis_saved(const DisDims& d, void* base, std::vector<SavedEntry>* l
   DisSaved s{};
   const long long M0 = (long long)d.B * 80 * d.T, M1 = (long long)d.B * 40 * d.W1,
                   M2 = (long long)d.B * 20 * d.W2, M3 = (long long)d.B * 10 * d.W3;
-  s.Xd = take_pair(a, M0 * 64, "Xd");
-  s.z0 = a.takeT<float>(M0 * 128, "z0");
+  s.xin = a.takeT<float>(M0, "xin");
   s.D0 = take_pair(a, parity_elems(d.B, 80, d.T, 128), "D0");
   s.z1 = a.takeT<float>(M1 * 256, "z1");
   s.st1 = take_stat(a, d.B * 256);
@@ -1019,12 +1018,10 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
     r.check(launch_fill_zero(s.D2.hi, parity_elems(B, 20, d.W2, 512) * 2, st), "zero D2");
     r.check(launch_fill_zero(s.D2.lo, parity_elems(B, 20, d.W2, 512) * 2, st), "zero D2");
   }
-  // convLayer1: 3x3 conv 1->128 + swish                                           model.py:290-295,344
-  r.check(launch_prep_d(x, B, T, s.Xd.hi, s.Xd.lo, st), "prep_d");
-  run_conv(r, plain_op(s.Xd.hi, s.Xd.lo, B, 80, T, 64), W.fwd(cv[D_STEM]), taps_one(), B, 80, T,
-           plain_out(s.z0, 80, T, 128), W.bias(cv[D_STEM]), nullptr, "D stem conv", 9.0 / 64.0);
-  if (r.ok) r.check(launch_apply_fwd(mk_apply(kSwishNoNorm, s.z0, 128, 80, T, Stat{nullptr, nullptr}, 0, nullptr,
-                                              nullptr, 1, nullptr, abuf(s.D0, nullptr, B, 80, T, 128, 1)), st), "D stem act");
+  // convLayer1: 3x3 conv 1->128 + swish, direct CUDA-core kernel (K = 9)        model.py:290-295,344
+  r.check(cudaMemcpyAsync(s.xin, x, (size_t)B * 80 * T * sizeof(float), cudaMemcpyDeviceToDevice, st), "D save x");
+  r.check(launch_d_stem_fwd(x, B, T, W.bf + cv[D_STEM].fHi, W.bf + cv[D_STEM].fLo, W.bias(cv[D_STEM]),
+                            abuf(s.D0, nullptr, B, 80, T, 128, 1), st), "D stem");
   // downSample1..3: 3x3 stride 2 conv + IN + swish                                 model.py:345-347
   const TapList k33 = taps_s2_fwd(3, 1);
   run_conv_in(r, parity_op(s.D0.hi, s.D0.lo, B, 80, T, 128), W.fwd(cv[D_DS1]), k33, B, 40, d.W1,
@@ -1066,8 +1063,7 @@ long long discriminator_bwd_ws_bytes(int B, int T) {
   add(parity_elems(B, 40, d.W1, 256) * 4);                     // dD1
   add(M1 * 256 * 2); add(M1 * 256 * 2);                        // dz1
   add(parity_elems(B, 80, d.T, 128) * 4);                      // dD0
-  add(M0 * 128 * 2); add(M0 * 128 * 2);                        // dz0
-  add(M0 * 64 * 4);                                            // dXd
+  add(M0 * 12 * 4);                                            // q (stem input-gradient taps)
   return align_up(b, 256) + 4096;
 }
 
@@ -1135,19 +1131,13 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
     dAct = dIn;
     dActParity = 1;
   }
-  // stem
-  BfPair dz0 = take_pair(a, M0 * 128, nullptr);
-  run_bwd(r, mk_bwd(kSwishNoNorm, s.z0, 128, 80, d.T, Stat{nullptr, nullptr}, 0, nullptr, nullptr, 1,
-                    gbuf(dAct, B, 80, d.T, 128, 1), t1, t2, nullptr, nullptr, dz0, gB(D_STEM)),
-          "D stem bwd");
-  if (needWgrad)
-    run_wgrad(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 128), plain_op(s.Xd.hi, s.Xd.lo, B, 80, d.T, 64), one, nullptr,
-              B, 80, d.T, gW(D_STEM), "D stem wgrad", 9.0 / 64.0);
-  if (dx) {
-    float* dXd = a.takeT<float>(M0 * 64);
-    run_conv(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 128), W.bwd(cv[D_STEM]), one, B, 80, d.T,
-             plain_out(dXd, 80, d.T, 64), nullptr, nullptr, "D stem dgrad", 9.0 / 64.0);
-    if (r.ok) r.check(launch_col2im_d(dXd, B, d.T, dx, st), "D col2im");
+  // stem: direct kernel (recomputes z from x), weight/bias grads straight into the gradient blob
+  {
+    float* q = dx ? a.takeT<float>(M0 * 12) : nullptr;
+    if (r.ok) r.check(launch_d_stem_bwd(s.xin, B, d.T, W.bf + cv[D_STEM].fHi, W.bf + cv[D_STEM].fLo,
+                                        W.bias(cv[D_STEM]), gbuf(dAct, B, 80, d.T, 128, 1),
+                                        needWgrad ? gW(D_STEM) : nullptr, gB(D_STEM), q, st), "D stem bwd");
+    if (dx && r.ok) r.check(launch_col2im_d(q, B, d.T, dx, st), "D col2im");
   }
   (void)M1; (void)M2;
   r.join();
