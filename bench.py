@@ -277,26 +277,40 @@ def main():
 
     # roofline: per-launch CUDA-event timing of the tensor-core kernels over extra steps
     peaks = load_peaks()
+    eng.set_overlap(False)      # kernels timed one at a time on their stream (no concurrent wgrad stream)
+    step_resident()
+    torch.cuda.synchronize()
     eng.profile_enable(True)
     for _ in range(max(args.profile_steps, 1)):
         step_resident()
     torch.cuda.synchronize()
     prof = eng.profile_collect()
     eng.profile_enable(False)
+    eng.set_overlap(True)
     conv, wg = prof["conv"], prof["wgrad"]
     peak = peaks["bf16_tflops_sustained"]
     conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
     wg_tf = wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0
     psteps = max(args.profile_steps, 1)
     step_flops = (ts.STEP_FLOPS_LEAN_T64 if args.lean else ts.STEP_FLOPS_STRICT_T64) * B
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        key = "parity_pair_kernels" if args.precision != "fast" else "fast"
+        if key in tj:
+            traffic = tj[key]["conv_dram_bytes_per_launch_mean_over_G_forward"]
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (implicit-GEMM fprop+dgrad, tcgen05)",
                 "achieved": conv_tf, "peak": peak, "unit": "TFLOP/s", "frac": conv_tf / peak,
                 "peak_source": "bf16_tflops_sustained, " + peaks["source"] + " (kernel timed inside a long step)",
-                "traffic": None,
+                "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write per launch, mean over the 20 conv launches of one Generator forward at batch 64 (ncu --set full, profiles/r01_ncu_full_summary.md)",
                 "algorithmic_flops_per_launch": conv["flops"] / max(conv["launches"], 1),
                 "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
                 "launches_per_step": conv["launches"] / psteps,
                 "share_of_step": (conv["ms"] / psteps) / (ms / K),
+                "traffic_note": "dram__bytes_read+write per launch, mean over the 20 conv launches of one Generator forward at batch 64 (ncu --set full, profiles/r01_ncu_full_summary.md)",
                 "wgrad_kernel": {"achieved": wg_tf, "frac": wg_tf / peak, "launches_per_step": wg["launches"] / psteps,
                                  "share_of_step": (wg["ms"] / psteps) / (ms / K)},
                 "whole_step": {"algorithmic_tflops": step_flops / (ms / K * 1e-3) / 1e12,
@@ -317,6 +331,17 @@ def main():
             other.append({"precision": other_mode, "value": frames * args.fast_steps / (ms_o * 1e-3), "unit": UNIT,
                           "ms_per_step": ms_o / args.fast_steps, "note": mode_note[other_mode] + " -- reported for context only"})
         eng.set_precision(modes[args.precision])
+        if not args.lean:
+            # same precision, but eval-mode modules treated as frozen: skips exactly the gradients
+            # train.py discards (504 instead of 670 GFLOP per sample pair); same optimisation trajectory
+            pkg.set_lean(True)
+            for _ in range(2):
+                step_resident()
+            ms_o = timed_steps(step_resident, args.fast_steps, world)
+            other.append({"precision": args.precision, "lean": True, "value": frames * args.fast_steps / (ms_o * 1e-3),
+                          "unit": UNIT, "ms_per_step": ms_o / args.fast_steps,
+                          "note": "MCGVC_LEAN=1: gradients the reference loop computes and then discards are not computed -- reported for context only"})
+            pkg.set_lean(False)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

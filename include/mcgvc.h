@@ -30,6 +30,9 @@ int mcgvc_set_device(int device);
 int mcgvc_set_backend(int backend);
 int mcgvc_set_precision(int mode);
 int mcgvc_get_precision(void);
+/* 1 (default): backward passes use the engine's two priority streams (weight-gradient GEMMs overlap the
+ * critical path); 0: everything on the caller's stream (used while timing individual kernels). */
+int mcgvc_set_overlap(int on);
 
 /* Model geometry.  Replaces Generator.__init__ / Discriminator.__init__ bookkeeping
  * (model.py:110-211, :287-327): number of floats in the reference-order flat parameter buffer

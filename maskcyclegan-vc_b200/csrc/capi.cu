@@ -21,11 +21,11 @@ struct DevStreams {
   cudaStream_t main = nullptr, side = nullptr;
   cudaEvent_t in = nullptr, out = nullptr;
 };
+static int g_overlap = -1;   // -1: take MCGVC_OVERLAP (default on)
 static DevStreams* dev_streams() {
   static DevStreams ds[64];
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("MCGVC_OVERLAP"); enabled = e ? atoi(e) : 1; }
-  if (!enabled) return nullptr;
+  if (g_overlap < 0) { const char* e = getenv("MCGVC_OVERLAP"); g_overlap = e ? atoi(e) : 1; }
+  if (!g_overlap) return nullptr;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   DevStreams& d = ds[dev];
@@ -91,6 +91,7 @@ int mcgvc_set_precision(int mode) {
   return 0;
 }
 int mcgvc_get_precision(void) { return g_precision; }
+int mcgvc_set_overlap(int on) { g_overlap = on ? 1 : 0; return 0; }
 
 long long mcgvc_param_count(int model) { const ModelDesc* d = desc(model); return d ? d->paramCount : -1; }
 long long mcgvc_packed_bytes(int model) { const ModelDesc* d = desc(model); return d ? d->packed_bytes() : -1; }

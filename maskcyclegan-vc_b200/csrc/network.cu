@@ -386,7 +386,7 @@ void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList&
   const long long units = (long long)xtaps.n * (g.N / 128) * (g.C / g.cTile);
   const long long posTiles = (long long)g.tilesX * g.tilesY * g.tilesB;
   long long maxSplit = posTiles / 8;
-  if (maxSplit > 32) maxSplit = 32;
+  if (maxSplit > 148) maxSplit = 148;
   if (maxSplit < 1) maxSplit = 1;
   int bestSk = 1;
   double bestCost = 1e30;

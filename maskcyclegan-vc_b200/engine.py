@@ -87,6 +87,10 @@ def set_precision(mode):
     _check(lib().mcgvc_set_precision(mode), "set_precision")
 
 
+def set_overlap(on):
+    lib().mcgvc_set_overlap(1 if on else 0)
+
+
 def get_precision():
     return lib().mcgvc_get_precision()
 
