@@ -75,6 +75,10 @@ int mcgvc_discriminator_backward(const void* packed, const void* saved, const fl
  * and fills out6 = {conv ms, conv algorithmic FLOPs, conv launches, wgrad ms, wgrad FLOPs, wgrad
  * launches} accumulated since the previous collect. */
 long long mcgvc_launch_count(void);
+/* CUDA-graph replay of repeated identical forward/backward calls (opt-in: MCGVC_GRAPHS=1 or
+ * mcgvc_set_graphs(1); helps batch-1 latency, neutral at batch 64).  mcgvc_graph_stats reports graphs captured / replays so far. */
+int mcgvc_set_graphs(int on);
+int mcgvc_graph_stats(long long* captures, long long* replays);
 int mcgvc_profile_enable(int on);
 int mcgvc_profile_collect(double* out6);
 

@@ -4,6 +4,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 using namespace mcgvc;
 
@@ -19,7 +21,7 @@ static int g_precision = MCGVC_PRECISION_PARITY;
 // MCGVC_OVERLAP=0 runs everything on the caller's stream.
 struct DevStreams {
   cudaStream_t main = nullptr, side = nullptr;
-  cudaEvent_t in = nullptr, out = nullptr;
+  cudaEvent_t in = nullptr, out = nullptr, fork = nullptr;
 };
 static int g_overlap = -1;   // -1: take MCGVC_OVERLAP (default on)
 static DevStreams* dev_streams() {
@@ -36,12 +38,13 @@ static DevStreams* dev_streams() {
     if (cudaStreamCreateWithPriority(&d.side, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
     cudaEventCreateWithFlags(&d.in, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&d.out, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming);
   }
   return &d;
 }
 static RunCfg cfg(void* stream, bool backward = false) {
   int np = g_precision == MCGVC_PRECISION_PARITY ? 3 : (g_precision == MCGVC_PRECISION_FAST ? 1 : (backward ? 1 : 3));
-  return RunCfg{(cudaStream_t)stream, g_backend, np, nullptr};
+  return RunCfg{(cudaStream_t)stream, g_backend, np, nullptr, nullptr};
 }
 // run a backward body on the engine streams, bracketed by event hand-offs with the caller's stream
 template <class F>
@@ -54,6 +57,7 @@ static int run_backward(void* stream, F body) {
   cudaStreamWaitEvent(d->main, d->in, 0);
   rc.stream = d->main;
   rc.side = d->side;
+  rc.forkEvent = d->fork;
   const int rv = body(rc);               // joins the side stream into d->main before returning
   cudaEventRecord(d->out, d->main);
   cudaStreamWaitEvent(caller, d->out, 0);
@@ -68,6 +72,107 @@ static const ModelDesc* desc(int model) {
 static bool shape_ok(int B, int T) {
   if (B < 1 || T < 1) { set_error("batch and frames must be >= 1 (got %d, %d)", B, T); return false; }
   return true;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-graph replay of whole forward / backward calls.  A call is identified by its model, shape,
+// precision and EVERY device pointer it touches; PyTorch's caching allocator hands out the same
+// addresses step after step, so from the second identical call on the ~80-200 launches of a pass
+// (with their baked TMA descriptors and cross-stream fork/join) are replayed with one
+// cudaGraphLaunch instead of being enqueued one by one.  First sight of a key runs eagerly (also
+// keeps one-off shapes such as validation utterances out of the cache).  Opt-in: MCGVC_GRAPHS=1 or
+// mcgvc_set_graphs(1).
+struct GraphKey {
+  long long kind, B, T, precision, needW;   // 8-byte fields only: no padding, memcmp-safe
+  const void* p[9];
+  GraphKey() { memset(this, 0, sizeof(*this)); }
+  bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+};
+struct GraphEntry {
+  int seen = 0;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+static std::map<GraphKey, GraphEntry> g_graphs;
+static std::mutex g_graph_mu;
+static int g_graphs_on = -1;
+static long long g_graph_replays = 0, g_graph_captures = 0;
+namespace mcgvc { void add_launches(long long n); }
+
+static bool graphs_enabled() {
+  // opt-in: replay trims ~10 % off batch-1 latency but does nothing for the batch-64 step (GPU-bound)
+  if (g_graphs_on < 0) { const char* e = getenv("MCGVC_GRAPHS"); g_graphs_on = e ? atoi(e) : 0; }
+  return g_graphs_on && g_backend == MCGVC_BACKEND_TCGEN05 && !profile_enabled();
+}
+static void drop_graphs() {
+  for (auto& kv : g_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  g_graphs.clear();
+}
+
+// Capture needs a non-legacy stream (PyTorch's default stream is the legacy NULL stream, which
+// cannot be captured): the body is recorded on an engine-owned stream and the instantiated graph
+// is then launched on the caller's stream.
+static cudaStream_t capture_stream(int dev) {
+  static cudaStream_t cs[64] = {};
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!cs[dev] && cudaStreamCreateWithFlags(&cs[dev], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  return cs[dev];
+}
+
+template <class F>
+static int run_graphed(GraphKey key, void* stream, F body) {
+  if (!graphs_enabled()) return body(stream);
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  key.precision = g_precision * 64 + dev;
+  if (g_graphs.size() > 1024) drop_graphs();
+  GraphEntry& e = g_graphs[key];
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e.exec) {
+    if (cudaGraphLaunch(e.exec, s) == cudaSuccess) {
+      add_launches(e.launches);
+      ++g_graph_replays;
+      return 0;
+    }
+    cudaGetLastError();
+    cudaGraphExecDestroy(e.exec);
+    e.exec = nullptr;
+    return body(stream);
+  }
+  if (++e.seen < 2) return body(stream);
+  // second identical call: record it
+  cudaStream_t cs = capture_stream(dev);
+  const long long l0 = launch_count();
+  if (!cs || cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    g_graphs_on = 0;
+    return body(stream);
+  }
+  const int rv = body((void*)cs);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+  if (rv != 0 || ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g_graphs_on = 0;            // capture is not usable in this process: stay eager from now on
+    if (rv != 0) return rv;
+    return body(stream);
+  }
+  e.launches = launch_count() - l0;
+  ce = cudaGraphInstantiate(&e.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess || cudaGraphLaunch(e.exec, s) != cudaSuccess) {
+    cudaGetLastError();
+    if (e.exec) cudaGraphExecDestroy(e.exec);
+    e.exec = nullptr;
+    g_graphs_on = 0;
+    return body(stream);
+  }
+  ++g_graph_captures;
+  return 0;
 }
 
 extern "C" {
@@ -128,30 +233,57 @@ int mcgvc_generator_forward(const void* packed, const float* x, const float* mas
                             float* out, void* saved, void* ws, void* stream) {
   if (!shape_ok(B, T)) return 1;
   if (!packed || !x || !mask || !out || !saved || !ws) { set_error("generator_forward: null pointer"); return 1; }
-  return generator_forward(packed, x, mask, B, T, out, saved, ws, cfg(stream));
+  GraphKey k;
+  k.kind = 0; k.B = B; k.T = T;
+  k.p[0] = packed; k.p[1] = x; k.p[2] = mask; k.p[3] = out; k.p[4] = saved; k.p[5] = ws;
+  return run_graphed(k, stream, [&](void* s) { return generator_forward(packed, x, mask, B, T, out, saved, ws, cfg(s)); });
 }
 int mcgvc_generator_backward(const void* packed, const void* saved, const float* mask,
                              const float* dout, int B, int T, float* dx, float* gblob,
                              int need_wgrad, void* ws, void* stream) {
   if (!shape_ok(B, T)) return 1;
   if (!packed || !saved || !mask || !dout || !ws || (need_wgrad && !gblob)) { set_error("generator_backward: null pointer"); return 1; }
-  return run_backward(stream, [&](const RunCfg& rc) { return generator_backward(packed, saved, mask, dout, B, T, dx, gblob, need_wgrad, ws, rc); });
+  GraphKey k;
+  k.kind = 1; k.B = B; k.T = T; k.needW = need_wgrad;
+  k.p[0] = packed; k.p[1] = saved; k.p[2] = mask; k.p[3] = dout; k.p[4] = dx; k.p[5] = gblob; k.p[6] = ws;
+  return run_graphed(k, stream, [&](void* s) {
+    return run_backward(s, [&](const RunCfg& rc) { return generator_backward(packed, saved, mask, dout, B, T, dx, gblob, need_wgrad, ws, rc); });
+  });
 }
 int mcgvc_discriminator_forward(const void* packed, const float* x, int B, int T, float* out,
                                 void* saved, void* ws, void* stream) {
   if (!shape_ok(B, T)) return 1;
   if (!packed || !x || !out || !saved || !ws) { set_error("discriminator_forward: null pointer"); return 1; }
-  return discriminator_forward(packed, x, B, T, out, saved, ws, cfg(stream));
+  GraphKey k;
+  k.kind = 2; k.B = B; k.T = T;
+  k.p[0] = packed; k.p[1] = x; k.p[2] = out; k.p[3] = saved; k.p[4] = ws;
+  return run_graphed(k, stream, [&](void* s) { return discriminator_forward(packed, x, B, T, out, saved, ws, cfg(s)); });
 }
 int mcgvc_discriminator_backward(const void* packed, const void* saved, const float* out,
                                  const float* dout, int B, int T, float* dx, float* gblob,
                                  int need_wgrad, void* ws, void* stream) {
   if (!shape_ok(B, T)) return 1;
   if (!packed || !saved || !out || !dout || !ws || (need_wgrad && !gblob)) { set_error("discriminator_backward: null pointer"); return 1; }
-  return run_backward(stream, [&](const RunCfg& rc) { return discriminator_backward(packed, saved, out, dout, B, T, dx, gblob, need_wgrad, ws, rc); });
+  GraphKey k;
+  k.kind = 3; k.B = B; k.T = T; k.needW = need_wgrad;
+  k.p[0] = packed; k.p[1] = saved; k.p[2] = out; k.p[3] = dout; k.p[4] = dx; k.p[5] = gblob; k.p[6] = ws;
+  return run_graphed(k, stream, [&](void* s) {
+    return run_backward(s, [&](const RunCfg& rc) { return discriminator_backward(packed, saved, out, dout, B, T, dx, gblob, need_wgrad, ws, rc); });
+  });
 }
 
 long long mcgvc_launch_count(void) { return launch_count(); }
+int mcgvc_set_graphs(int on) {
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  g_graphs_on = on ? 1 : 0;
+  if (!on) drop_graphs();
+  return 0;
+}
+int mcgvc_graph_stats(long long* captures, long long* replays) {
+  if (captures) *captures = g_graph_captures;
+  if (replays) *replays = g_graph_replays;
+  return 0;
+}
 int mcgvc_profile_enable(int on) { profile_enable(on != 0); return 0; }
 int mcgvc_profile_collect(double* out6) {
   KernelProfile c, w;

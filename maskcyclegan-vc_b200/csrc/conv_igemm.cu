@@ -48,6 +48,7 @@ cudaError_t launched() {
   return cudaGetLastError();
 }
 long long launch_count() { return g_launches.load(); }
+void add_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 namespace {
 struct ProfRec { cudaEvent_t a, b; int kind; double flops; };

@@ -208,24 +208,21 @@ struct Run {
   RunCfg rc;
   bool ok = true;
   bool forked = false;
-  cudaEvent_t ev = nullptr;
   // weight-gradient GEMMs go to a side stream: they only feed the gradient blob, so they overlap
   // with the bandwidth-bound layer kernels and data-gradient convs of the main chain
   cudaStream_t wgrad_stream() {
-    if (!rc.side) return rc.stream;
-    if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    cudaEventRecord(ev, rc.stream);          // everything the wgrad reads has been enqueued
-    cudaStreamWaitEvent(rc.side, ev, 0);
+    if (!rc.side || !rc.forkEvent) return rc.stream;
+    cudaEventRecord(rc.forkEvent, rc.stream);   // everything the wgrad reads has been enqueued
+    cudaStreamWaitEvent(rc.side, rc.forkEvent, 0);
     forked = true;
     return rc.side;
   }
   void join() {
     if (forked && rc.side) {
-      cudaEventRecord(ev, rc.side);
-      cudaStreamWaitEvent(rc.stream, ev, 0);
+      cudaEventRecord(rc.forkEvent, rc.side);
+      cudaStreamWaitEvent(rc.stream, rc.forkEvent, 0);
       forked = false;
     }
-    if (ev) { cudaEventDestroy(ev); ev = nullptr; }
   }
   void check(cudaError_t e, const char* what) {
     if (e != cudaSuccess && ok) {

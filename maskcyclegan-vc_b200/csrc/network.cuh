@@ -55,6 +55,7 @@ struct RunCfg {
   int backend;   // 0 = tcgen05/TMA kernels, 1 = SIMT checking kernels
   int nPass;     // passes used by the call: 3 = split-bf16, 1 = bf16 (capi picks it per direction)
   cudaStream_t side;  // stream for the weight-gradient GEMMs of a backward pass, or null (same stream)
+  cudaEvent_t forkEvent;  // persistent event used to fork to / join from the side stream
 };
 
 // sizes (bytes) of the per-call buffers the caller provides

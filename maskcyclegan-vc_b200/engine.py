@@ -91,6 +91,16 @@ def set_overlap(on):
     lib().mcgvc_set_overlap(1 if on else 0)
 
 
+def set_graphs(on):
+    lib().mcgvc_set_graphs(1 if on else 0)
+
+
+def graph_stats():
+    c, r = _c_ll(0), _c_ll(0)
+    lib().mcgvc_graph_stats(ctypes.byref(c), ctypes.byref(r))
+    return {"captures": c.value, "replays": r.value}
+
+
 def get_precision():
     return lib().mcgvc_get_precision()
 

@@ -162,6 +162,20 @@ def test_long_utterance_config5(env):
     assert rel(y, ref) < TOL
 
 
+def test_full_utterance_shapes_like_test_py(env):
+    """test.py:92,107 feeds whole utterances (B=1, arbitrary T, grad mode on); T % 4 != 0 allowed."""
+    for T in (1001, 333):
+        x, m, _, _ = O.synthetic_batch(1, T, seed=T)
+        y = env["G"](x.cuda(), torch.ones_like(x).cuda())      # grad mode left on, as in test.py
+        with torch.no_grad():
+            ref = O.generator_forward(env["gs"], x, torch.ones_like(x))
+            d = env["D"](x.cuda())
+            dref = O.discriminator_forward(env["ds"], x)
+        assert y.shape == ref.shape and y.requires_grad
+        assert rel(y, ref) < TOL
+        assert d.shape == dref.shape and rel(d, dref) < TOL
+
+
 def test_grad_accumulation_and_zeroing_semantics(env):
     D = env["D"]
     x = torch.randn(2, 80, 64, device="cuda")
@@ -249,6 +263,35 @@ def test_mixed_precision_mode_keeps_forward_parity(env):
     assert bwd["fake"] < TOL and bwd["loss"] < TOL
     for k in ("dx", "G.grads(packed)", "D.grads(packed)"):
         assert 1e-4 < bwd[k] < 5e-2, (k, bwd[k])
+
+
+def test_cuda_graph_replay_matches_eager(env):
+    """Opt-in graph replay: repeated identical calls are captured on their 2nd sight and replayed."""
+    e = env["pkg"].engine
+    G, D = env["G"], env["D"]
+    x, m, _, _ = O.synthetic_batch(2, 64, seed=21)
+    x, m = x.cuda(), m.cuda()
+    with torch.no_grad():
+        y_ref = G(x, m).clone()
+    before = e.graph_stats()
+    e.set_graphs(True)
+    try:
+        with torch.no_grad():
+            outs = [G(x, m).clone() for _ in range(6)]
+        grads = []
+        for _ in range(4):
+            G.zero_grad(set_to_none=True)
+            D.zero_grad(set_to_none=True)
+            torch.mean((1 - D(G(x, m))) ** 2).backward()
+            grads.append(G.conv1.weight.grad.clone())
+    finally:
+        e.set_graphs(False)
+    after = e.graph_stats()
+    assert after["captures"] > before["captures"] and after["replays"] > before["replays"]
+    for o in outs:
+        assert rel(o, y_ref) < 1e-6
+    for g in grads[1:]:
+        assert rel(g, grads[0]) < 1e-4      # atomics order differs run to run
 
 
 def test_lean_mode_keeps_the_training_trajectory(env):
