@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--impl", default="engine")
     ap.add_argument("--precision", default="parity", choices=["parity", "mixed", "fast"])
     ap.add_argument("--lean", type=int, default=0)
+    ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
+                    help="torch = torch.optim.Adam as in train.py:119-122; fused = one-kernel Adam on the flat buffers")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--fast-steps", type=int, default=3, help="extra steps in the other precision mode (0 = skip)")
     ap.add_argument("--cpu-batch", type=int, default=4)
@@ -244,7 +246,11 @@ def main():
     pkg.set_lean(bool(args.lean))
 
     models = ts.build_models(pkg.Generator, pkg.Discriminator, dev, seed=0)
-    g_opt, d_opt = ts.build_optimizers(models)
+    if args.optimizer == "fused":
+        g_opt = pkg.FusedAdam(models[:2], lr=2e-4, betas=(0.5, 0.999))
+        d_opt = pkg.FusedAdam(models[2:], lr=1e-4, betas=(0.5, 0.999))
+    else:
+        g_opt, d_opt = ts.build_optimizers(models)
     sync = pkg.GradSync([models[:2], models[2:]]) if world > 1 else None
 
     host = [t.pin_memory() for t in synthetic_batch_host(B, T_FRAMES, seed=1234 + rank)]
@@ -356,6 +362,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "full MaskCycleGAN train step (train.py:186-299: 10 G fwd + 12 D fwd, 2 backward, 2 Adam), batch %d per GPU, 80x%d mel (BASELINE configs[3])" % (B, T_FRAMES),
                        "batch_per_gpu": B, "global_batch": B * world, "frames": T_FRAMES,
+                       "optimizer": "torch.optim.Adam" if args.optimizer == "torch" else "engine FusedAdam",
                        "precision_mode": args.precision, "precision_note": mode_note[args.precision], "lean": bool(args.lean),
                        "parallelism": "dp%d" % world,
                        "l2": "inputs larger than L2: ~%.1f GB of activations touched per step vs 126 MB L2" % (24.0 * B / 64.0),

@@ -70,6 +70,12 @@ int mcgvc_discriminator_backward(const void* packed, const void* saved, const fl
                                  const float* dout, int batch, int frames, float* dx,
                                  float* grad_blob, int need_wgrad, void* workspace, void* stream);
 
+/* One Adam update (torch.optim.Adam semantics, no weight decay / amsgrad; replaces the optimizer
+ * steps at train.py:242,299 for a contiguous 16-byte-aligned range of the flat parameter buffer).
+ * step is the 1-based update count used for bias correction. */
+int mcgvc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                    float lr, float beta1, float beta2, float eps, int step, void* stream);
+
 /* Accounting for bench.py: number of kernels this library has launched so far, and optional
  * per-launch CUDA-event timing of the two tensor-core kernels.  mcgvc_profile_collect synchronises
  * and fills out6 = {conv ms, conv algorithmic FLOPs, conv launches, wgrad ms, wgrad FLOPs, wgrad

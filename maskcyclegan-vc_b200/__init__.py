@@ -7,3 +7,4 @@ reference's `mask_cyclegan_vc.model` in place.
 from . import engine  # noqa: F401
 from .model import Discriminator, Generator, is_lean, set_lean  # noqa: F401
 from .parallel import GradSync, shard_batch  # noqa: F401
+from .optim import FusedAdam  # noqa: F401

@@ -272,6 +272,15 @@ int mcgvc_discriminator_backward(const void* packed, const void* saved, const fl
   });
 }
 
+int mcgvc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                    float lr, float beta1, float beta2, float eps, int step, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) { set_error("adam_step: bad arguments"); return 1; }
+  if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) { set_error("adam_step: ranges must be 16-byte aligned"); return 1; }
+  cudaError_t e = launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("adam_step: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
 long long mcgvc_launch_count(void) { return launch_count(); }
 int mcgvc_set_graphs(int on) {
   std::lock_guard<std::mutex> lk(g_graph_mu);

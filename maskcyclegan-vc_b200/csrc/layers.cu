@@ -4,6 +4,8 @@
 #include "layers.cuh"
 #include "gemm_types.cuh"
 
+#include <cmath>
+
 namespace mcgvc {
 
 static int grid_for(long long work, int threads) {
@@ -204,14 +206,11 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const ApplyArgs a) {
         const float4 r = ld4(a.residual + (((long long)img * a.out.Y + y) * a.out.X + x) * C + c);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
-    } else if (MODE == kINSwish || MODE == kINSwishShuffle) {
+    } else {  // kINSwish, kINSwishShuffle
       const Norm4 n = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, c);
       const float4 yv = affine4(xhat4(v, n), n);
       o = make_float4(yv.x * sigmoidf_(yv.x), yv.y * sigmoidf_(yv.y), yv.z * sigmoidf_(yv.z),
                       yv.w * sigmoidf_(yv.w));
-    } else {  // kSwishNoNorm
-      o = make_float4(v.x * sigmoidf_(v.x), v.y * sigmoidf_(v.y), v.z * sigmoidf_(v.z),
-                      v.w * sigmoidf_(v.w));
     }
     const long long off = act_off(a.out, img, y, x) + c;
     if (a.out.hi) split_store4(a.out.hi, a.out.lo, off, o);
@@ -227,7 +226,6 @@ cudaError_t launch_apply_fwd(const ApplyArgs& a, cudaStream_t s) {
     case kGatedIN: apply_fwd_kernel<kGatedIN><<<g, 256, 0, s>>>(a); break;
     case kINOnly: apply_fwd_kernel<kINOnly><<<g, 256, 0, s>>>(a); break;
     case kINSwish: apply_fwd_kernel<kINSwish><<<g, 256, 0, s>>>(a); break;
-    case kSwishNoNorm: apply_fwd_kernel<kSwishNoNorm><<<g, 256, 0, s>>>(a); break;
     case kINSwishShuffle: apply_fwd_kernel<kINSwishShuffle><<<g, 256, 0, s>>>(a); break;
     default: set_error("apply_fwd: bad mode %d", a.mode); return cudaErrorInvalidValue;
   }
@@ -335,7 +333,7 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
 }
 
 cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
-  if (a.mode == kGatedNoNorm || a.mode == kSwishNoNorm) return cudaSuccess;  // nothing to reduce
+  if (a.mode == kGatedNoNorm) return cudaSuccess;  // no normalisation: nothing to reduce
   const int cg = (a.dA.C + 127) / 128;
   const int P = a.dA.Y * a.dA.X;
   int splits = (4 * 148 + cg * a.dA.nImg - 1) / (cg * a.dA.nImg);
@@ -352,8 +350,6 @@ cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
     case kINOnly: apply_bwd_reduce_kernel<kINOnly><<<grid, 256, 0, s>>>(a); break;
     case kINSwish: apply_bwd_reduce_kernel<kINSwish><<<grid, 256, 0, s>>>(a); break;
     case kINSwishShuffle: apply_bwd_reduce_kernel<kINSwishShuffle><<<grid, 256, 0, s>>>(a); break;
-    case kGatedNoNorm:
-    case kSwishNoNorm: return cudaSuccess;  // nothing to reduce
     default: set_error("apply_bwd_reduce: bad mode %d", a.mode); return cudaErrorInvalidValue;
   }
   return launched();
@@ -403,10 +399,6 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
       if (!gate) dz = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
       else dz = make_float4(d.x * va.x * sg.x * (1.f - sg.x), d.y * va.y * sg.y * (1.f - sg.y),
                             d.z * va.z * sg.z * (1.f - sg.z), d.w * va.w * sg.w * (1.f - sg.w));
-    } else if (MODE == kSwishNoNorm) {
-      const float4 v = ld4(zr + c);
-      dz = make_float4(d.x * swish_grad(v.x), d.y * swish_grad(v.y), d.z * swish_grad(v.z),
-                       d.w * swish_grad(v.w));
     } else {
       const int s = (MODE == kINSwishShuffle) ? c : col;  // stat channel of this column
       const Norm4 n = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, s);
@@ -475,7 +467,6 @@ cudaError_t launch_apply_bwd(const ApplyBwdArgs& a, cudaStream_t s) {
     case kGatedIN: apply_bwd_kernel<kGatedIN><<<g, 256, 0, s>>>(a); break;
     case kINOnly: apply_bwd_kernel<kINOnly><<<g, 256, 0, s>>>(a); break;
     case kINSwish: apply_bwd_kernel<kINSwish><<<g, 256, 0, s>>>(a); break;
-    case kSwishNoNorm: apply_bwd_kernel<kSwishNoNorm><<<g, 256, 0, s>>>(a); break;
     case kINSwishShuffle: apply_bwd_kernel<kINSwishShuffle><<<g, 256, 0, s>>>(a); break;
     default: set_error("apply_bwd: bad mode %d", a.mode); return cudaErrorInvalidValue;
   }
@@ -849,82 +840,11 @@ __device__ __forceinline__ void pack_map(const PackArgs& a, int n, int c, int t,
   }
 }
 
-__global__ void pack_weight_kernel(const PackArgs a) {
-  const long long total = (long long)a.N * a.C * a.T;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(idx % a.T);
-    const int c = (int)((idx / a.T) % a.C);
-    const int n = (int)(idx / ((long long)a.T * a.C));
-    int tp, np, cp;
-    pack_map(a, n, c, t, &tp, &np, &cp);
-    const float v = a.ref[idx];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-    const long long fo = ((long long)tp * a.Np + np) * a.Cp + cp;
-    a.f_hi[fo] = h;
-    a.f_lo[fo] = l;
-    if (a.d_hi) {
-      // data-gradient layout [Tp][Cd][Np]; the 1D->2D layer keeps its 20 frequency rows as taps
-      // ([20][Cd][256]) because its gradient is read back through the (c, w, h) activation view
-      const long long dO = (a.kind == kPack1dTo2d)
-                               ? ((long long)(np / 256) * a.Cd + cp) * 256 + (np % 256)
-                               : ((long long)tp * a.Cd + cp) * a.Np + np;
-      a.d_hi[dO] = h;
-      a.d_lo[dO] = l;
-    }
-  }
-}
-cudaError_t launch_pack_weight(const PackArgs& a, cudaStream_t s) {
-  const long long total = (long long)a.N * a.C * a.T;
-  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(a);
-  return launched();
-}
-
-__global__ void unpack_wgrad_kernel(const PackArgs a, const float* __restrict__ dw,
-                                    float* __restrict__ dref) {
-  const long long total = (long long)a.N * a.C * a.T;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(idx % a.T);
-    const int c = (int)((idx / a.T) % a.C);
-    const int n = (int)(idx / ((long long)a.T * a.C));
-    int tp, np, cp;
-    pack_map(a, n, c, t, &tp, &np, &cp);
-    dref[idx] += dw[((long long)tp * a.Np + np) * a.Cp + cp];
-  }
-}
-cudaError_t launch_unpack_wgrad(const PackArgs& a, const float* dw_engine, float* dref,
-                                cudaStream_t s) {
-  const long long total = (long long)a.N * a.C * a.T;
-  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, dw_engine, dref);
-  return launched();
-}
-
 __device__ __forceinline__ int vec_map(int kind, int i, int n) {
   if (kind == kVecShuffle) return (i & 3) * (n >> 2) + (i >> 2);
   if (kind == kVecHC20) return (i % 20) * 256 + i / 20;
   return i;
 }
-__global__ void pack_vec_kernel(int kind, const float* __restrict__ ref, int n,
-                                float* __restrict__ eng) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) eng[vec_map(kind, i, n)] = ref[i];
-}
-__global__ void unpack_vec_kernel(int kind, const float* __restrict__ eng, int n,
-                                  float* __restrict__ dref) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dref[i] += eng[vec_map(kind, i, n)];
-}
-cudaError_t launch_pack_vec(int kind, const float* ref, int n, float* eng, cudaStream_t s) {
-  pack_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(kind, ref, n, eng);
-  return launched();
-}
-cudaError_t launch_unpack_vec(int kind, const float* eng, int n, float* dref, cudaStream_t s) {
-  unpack_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(kind, eng, n, dref);
-  return launched();
-}
-
 
 // ---- table-driven packing: one launch per model ------------------------------------------------
 __device__ __forceinline__ PackArgs entry_args(const PackEntry& e) {
@@ -1013,6 +933,51 @@ cudaError_t launch_unpack_vecs_table(const VecTable& t, const float* eng, float*
                                      cudaStream_t s) {
   dim3 grid(4, t.count);
   unpack_vecs_table_kernel<<<grid, 256, 0, s>>>(t, eng, gradFlat);
+  return launched();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Adam on a flat parameter range (torch.optim.Adam semantics without weight
+// decay / amsgrad, train.py:119-122): one bandwidth-bound pass over {param, grad, exp_avg,
+// exp_avg_sq} instead of a multi-tensor launch sequence over 100+ tensors.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v,
+                                                   long long n, float b1, float b2, float eps,
+                                                   float stepSize, float invBc2Sqrt) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define MCGVC_ADAM1(c)                                              \
+    mv.c = b1 * mv.c + (1.f - b1) * gv.c;                           \
+    vv.c = b2 * vv.c + (1.f - b2) * gv.c * gv.c;                    \
+    pv.c -= stepSize * mv.c / (sqrtf(vv.c) * invBc2Sqrt + eps);
+    MCGVC_ADAM1(x) MCGVC_ADAM1(y) MCGVC_ADAM1(z) MCGVC_ADAM1(w)
+#undef MCGVC_ADAM1
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail (n not a multiple of 4)
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= stepSize * mi / (sqrtf(vi) * invBc2Sqrt + eps);
+  }
+}
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,
+                        float b2, float eps, int step, cudaStream_t s) {
+  const double bc1 = 1.0 - pow((double)b1, (double)step);
+  const double bc2 = 1.0 - pow((double)b2, (double)step);
+  adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(p, g, m, v, n, b1, b2, eps, (float)(lr / bc1),
+                                                      (float)(1.0 / sqrt(bc2)));
   return launched();
 }
 

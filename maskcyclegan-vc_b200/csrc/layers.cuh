@@ -24,7 +24,6 @@ enum ApplyMode {
   kGatedIN = 1,         // a = IN(z[c]) * sigmoid(IN(z[C+c]))              (model.py:101-103, :71-74)
   kINOnly = 2,          // a = IN(z[c]) (+ residual)                       (model.py:255, :75-76, :267)
   kINSwish = 3,         // y = IN(z[c]); a = y*sigmoid(y)                  (D blocks, model.py:330-337)
-  kSwishNoNorm = 4,     // a = z*sigmoid(z)                                (D stem, model.py:290-295)
   kINSwishShuffle = 5,  // PixelShuffle(2) then IN then swish              (model.py:226-237)
 };
 
@@ -117,15 +116,9 @@ struct PackArgs {
   __nv_bfloat16* d_lo;
   int Cd;
 };
-cudaError_t launch_pack_weight(const PackArgs& a, cudaStream_t s);
-// dref[n][c][t] += dW_engine[t'][n'][c']  (same mapping)
-cudaError_t launch_unpack_wgrad(const PackArgs& a, const float* dw_engine, float* dref,
-                                cudaStream_t s);
 
 // Small per-channel vectors (bias / gamma / beta): engine[i'] <-> ref[i] permutations.
 enum VecKind { kVecIdent = 0, kVecShuffle = 1, kVecHC20 = 2 };
-cudaError_t launch_pack_vec(int kind, const float* ref, int n, float* eng, cudaStream_t s);
-cudaError_t launch_unpack_vec(int kind, const float* eng, int n, float* dref, cudaStream_t s);
 
 // Table-driven variants: one launch packs / unpacks every tensor of a model (blockIdx.y = entry).
 struct PackEntry {
@@ -153,6 +146,8 @@ cudaError_t launch_pack_vecs_table(const VecTable& t, const float* params, float
 cudaError_t launch_unpack_vecs_table(const VecTable& t, const float* eng, float* gradFlat,
                                      cudaStream_t s);
 
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,
+                        float b2, float eps, int step, cudaStream_t s);
 cudaError_t launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
 
 }  // namespace mcgvc

@@ -53,6 +53,8 @@ def lib():
     l.mcgvc_discriminator_forward.argtypes = [_c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]
     l.mcgvc_discriminator_backward.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp,
                                                _c_int, _c_vp, _c_vp]
+    l.mcgvc_adam_step.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_ll, ctypes.c_float, ctypes.c_float,
+                                  ctypes.c_float, ctypes.c_float, _c_int, _c_vp]
     l.mcgvc_saved_layout.argtypes = [_c_int, _c_int, _c_int, _c_int, ctypes.c_char_p, _c_int,
                                      ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]
     _lib = l

@@ -68,6 +68,7 @@ class _EngineModule(nn.Module):
         self._touched = False
         self._live = None          # parameters that receive gradients (excludes dead tensors)
         self._grad_sync = None     # set by parallel.GradSync
+        self._weights_epoch = 0    # bumped by optim.FusedAdam (in-place update of the flat buffer)
 
     # ------------------------------------------------------------------ parameter storage
     def _unique_params(self):
@@ -120,7 +121,7 @@ class _EngineModule(nn.Module):
             self._anchor = torch.zeros(1, device=dev, requires_grad=True)
 
     def _version(self):
-        return sum(p._version for p in self._unique_params())
+        return self._weights_epoch * 1000003 + sum(p._version for p in self._unique_params())
 
     def _packed_weights(self):
         self._ensure_device_state()

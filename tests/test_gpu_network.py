@@ -145,8 +145,8 @@ def test_samples_are_independent_at_full_batch(env):
         y = G(x, m)
         d = D(x)
         for i in (0, 17, 63):
-            assert rel(y[i:i + 1], G(x[i:i + 1], m[i:i + 1])) < 2e-5
-            assert rel(d[i:i + 1], D(x[i:i + 1])) < 2e-5
+            assert rel(y[i:i + 1], G(x[i:i + 1], m[i:i + 1])) < 1e-4   # atomics-order noise only
+            assert rel(d[i:i + 1], D(x[i:i + 1])) < 1e-4
         # and the batch result still matches the oracle on a few rows
         ref = O.generator_forward(env["gs"], x[:2].cpu(), m[:2].cpu())
     assert rel(y[:2], ref) < TOL
@@ -265,6 +265,33 @@ def test_mixed_precision_mode_keeps_forward_parity(env):
         assert 1e-4 < bwd[k] < 5e-2, (k, bwd[k])
 
 
+def test_fused_adam_matches_torch_adam(env):
+    """one-kernel Adam on the flat buffers == torch.optim.Adam (train.py:119-122)."""
+    pkg = env["pkg"]
+    x, m, _, _ = O.synthetic_batch(2, 64, seed=31)
+    x, m = x.cuda(), m.cuda()
+    results = []
+    for fused in (False, True):
+        torch.manual_seed(5)
+        G, D = pkg.Generator().cuda(), pkg.Discriminator().cuda()
+        if fused:
+            opt = pkg.FusedAdam([G, D], lr=2e-4, betas=(0.5, 0.999))
+        else:
+            opt = torch.optim.Adam(list(G.parameters()) + list(D.parameters()), lr=2e-4, betas=(0.5, 0.999))
+        for _ in range(3):
+            opt.zero_grad()
+            torch.mean((1 - D(G(x, m))) ** 2).backward()
+            opt.step()
+        with torch.no_grad():
+            results.append((G._flat.clone(), D._flat.clone(), G(x, m).clone()))
+    # same gradients up to atomics order; Adam normalises, so compare with an lr-sized absolute floor
+    for a, b in ((results[0][0], results[1][0]), (results[0][1], results[1][1])):
+        assert (a - b).abs().max().item() < 3 * 2e-4 * 1.01
+        assert rel(a, b) < 1e-4
+    assert rel(results[0][2], results[1][2]) < 5e-3
+    assert torch.equal(results[1][1][6199808:6199808 + 16], results[0][1][6199808:6199808 + 16])  # dead params untouched
+
+
 def test_cuda_graph_replay_matches_eager(env):
     """Opt-in graph replay: repeated identical calls are captured on their 2nd sight and replayed."""
     e = env["pkg"].engine
@@ -289,7 +316,7 @@ def test_cuda_graph_replay_matches_eager(env):
     after = e.graph_stats()
     assert after["captures"] > before["captures"] and after["replays"] > before["replays"]
     for o in outs:
-        assert rel(o, y_ref) < 1e-6
+        assert rel(o, y_ref) < 1e-4         # statistics are reduced with atomics: order noise ~1e-5
     for g in grads[1:]:
         assert rel(g, grads[0]) < 1e-4      # atomics order differs run to run
 
