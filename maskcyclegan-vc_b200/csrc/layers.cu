@@ -165,52 +165,70 @@ __device__ __forceinline__ float4 affine4(float4 xh, const Norm4& n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Forward normalise + activation pass.  One block row per image (blockIdx.y); a thread owns one
+// 4-channel group for the whole kernel, so its InstanceNorm parameters are folded ONCE into a
+// scale/shift pair kept in registers (y = s*z + t) and the loop over positions is pure streaming:
+// no per-element parameter loads, no 64-bit index arithmetic.
+struct ScaleShift4 {
+  float4 s, t;
+};
+__device__ __forceinline__ ScaleShift4 load_scale_shift(const float* mean, const float* rstd,
+                                                        const float* gamma, const float* beta,
+                                                        int img, int Nstat, int affPeriod, int ch) {
+  const Norm4 n = load_norm(mean, rstd, gamma, beta, img, Nstat, affPeriod, ch);
+  ScaleShift4 r;
+  r.s = make_float4(n.rstd.x * n.gamma.x, n.rstd.y * n.gamma.y, n.rstd.z * n.gamma.z, n.rstd.w * n.gamma.w);
+  r.t = make_float4(n.beta.x - n.mean.x * r.s.x, n.beta.y - n.mean.y * r.s.y, n.beta.z - n.mean.z * r.s.z,
+                    n.beta.w - n.mean.w * r.s.w);
+  return r;
+}
+__device__ __forceinline__ float4 ss_apply(float4 v, const ScaleShift4& k) {
+  return make_float4(fmaf(v.x, k.s.x, k.t.x), fmaf(v.y, k.s.y, k.t.y), fmaf(v.z, k.s.z, k.t.z),
+                     fmaf(v.w, k.s.w, k.t.w));
+}
+__device__ __forceinline__ float4 swish4(float4 y) {
+  return make_float4(y.x * sigmoidf_(y.x), y.y * sigmoidf_(y.y), y.z * sigmoidf_(y.z), y.w * sigmoidf_(y.w));
+}
+__device__ __forceinline__ float4 gate4(float4 a, float4 g) {
+  return make_float4(a.x * sigmoidf_(g.x), a.y * sigmoidf_(g.y), a.z * sigmoidf_(g.z), a.w * sigmoidf_(g.w));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) apply_fwd_kernel(const ApplyArgs a) {
-  const int C = a.out.C, C4 = C >> 2;
-  const long long total = (long long)a.out.nImg * a.out.Y * a.out.X * C4;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C4) << 2;
-    long long pos = idx / C4;
-    const int x = (int)(pos % a.out.X);
-    pos /= a.out.X;
-    const int y = (int)(pos % a.out.Y);
-    const int img = (int)(pos / a.out.Y);
-    long long zrow;
-    int col = c;
-    if (MODE == kINSwishShuffle) {
-      zrow = ((long long)img * a.zY + (y >> 1)) * a.zX + (x >> 1);
-      col = ((((y & 1) << 1) | (x & 1)) * C) + c;
-    } else {
-      zrow = ((long long)img * a.zY + y) * a.zX + x;
-    }
-    const float* zr = a.z + zrow * a.Nz;
-    float4 v = ld4(zr + col);
+  const int C = a.out.C, C4 = C >> 2;           // C4 in {32, 64, 128, 256}
+  const int rows = 256 / C4;                    // positions handled per block iteration
+  const int c = (threadIdx.x % C4) << 2;
+  const int r = threadIdx.x / C4;
+  const int img = blockIdx.y;
+  const int X = a.out.X, P = a.out.Y * X;
+  ScaleShift4 ka{}, kg{};
+  if (MODE != kGatedNoNorm) {
+    ka = load_scale_shift(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, c);
+    if (MODE == kGatedIN) kg = load_scale_shift(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, C + c);
+  }
+  const float* zimg = a.z + (long long)img * a.zY * a.zX * a.Nz;
+  const float* rimg = a.residual ? a.residual + (long long)img * P * C : nullptr;
+  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
+    const int y = p / X, x = p - y * X;
+    const float* zr;
+    if (MODE == kINSwishShuffle)
+      zr = zimg + ((long long)(y >> 1) * a.zX + (x >> 1)) * a.Nz + ((((y & 1) << 1) | (x & 1)) * C) + c;
+    else
+      zr = zimg + (long long)p * a.Nz + c;
+    const float4 v = ld4(zr);
     float4 o;
     if (MODE == kGatedNoNorm) {
-      const float4 g = ld4(zr + C + c);
-      o = make_float4(v.x * sigmoidf_(g.x), v.y * sigmoidf_(g.y), v.z * sigmoidf_(g.z),
-                      v.w * sigmoidf_(g.w));
+      o = gate4(v, ld4(zr + C));
     } else if (MODE == kGatedIN) {
-      const Norm4 na = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, c);
-      const Norm4 ng = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, C + c);
-      const float4 ya = affine4(xhat4(v, na), na);
-      const float4 yg = affine4(xhat4(ld4(zr + C + c), ng), ng);
-      o = make_float4(ya.x * sigmoidf_(yg.x), ya.y * sigmoidf_(yg.y), ya.z * sigmoidf_(yg.z),
-                      ya.w * sigmoidf_(yg.w));
+      o = gate4(ss_apply(v, ka), ss_apply(ld4(zr + C), kg));
     } else if (MODE == kINOnly) {
-      const Norm4 n = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, c);
-      o = affine4(xhat4(v, n), n);
-      if (a.residual) {
-        const float4 r = ld4(a.residual + (((long long)img * a.out.Y + y) * a.out.X + x) * C + c);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      o = ss_apply(v, ka);
+      if (rimg) {
+        const float4 rv = ld4(rimg + (long long)p * C + c);
+        o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
       }
     } else {  // kINSwish, kINSwishShuffle
-      const Norm4 n = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, c);
-      const float4 yv = affine4(xhat4(v, n), n);
-      o = make_float4(yv.x * sigmoidf_(yv.x), yv.y * sigmoidf_(yv.y), yv.z * sigmoidf_(yv.z),
-                      yv.w * sigmoidf_(yv.w));
+      o = swish4(ss_apply(v, ka));
     }
     const long long off = act_off(a.out, img, y, x) + c;
     if (a.out.hi) split_store4(a.out.hi, a.out.lo, off, o);
@@ -218,9 +236,19 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const ApplyArgs a) {
   }
 }
 
+static dim3 rows_grid(int P, int rows, int nImg) {
+  int bx = (P + rows - 1) / rows;
+  int cap = (148 * 8 + nImg - 1) / nImg;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return dim3(bx, nImg);
+}
+
 cudaError_t launch_apply_fwd(const ApplyArgs& a, cudaStream_t s) {
-  const long long total = (long long)a.out.nImg * a.out.Y * a.out.X * (a.out.C >> 2);
-  const int g = grid_for(total, 256);
+  const int C4 = a.out.C >> 2;
+  if (C4 < 1 || C4 > 256 || 256 % C4) { set_error("apply_fwd: C=%d unsupported", a.out.C); return cudaErrorInvalidValue; }
+  const dim3 g = rows_grid(a.out.Y * a.out.X, 256 / C4, a.out.nImg);
   switch (a.mode) {
     case kGatedNoNorm: apply_fwd_kernel<kGatedNoNorm><<<g, 256, 0, s>>>(a); break;
     case kGatedIN: apply_fwd_kernel<kGatedIN><<<g, 256, 0, s>>>(a); break;
@@ -355,113 +383,126 @@ cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
   return launched();
 }
 
-// Backward, pass 2: dz = rstd*gamma*(dy - t1/Np - xhat*t2/Np) split into bf16 hi/lo (operand of the
-// data- and weight-gradient GEMMs); optional conv-bias gradient (column sums of dz).
-// Thread = (z row, 4 consecutive z columns); a thread's column group is fixed across its grid-stride
-// loop (total threads is a multiple of Nz/4), so the bias sums stay in registers until the end.
+// Backward, pass 2: dz = rstd*gamma*(dy - t1/Np - xhat*t2/Np), split into bf16 hi/lo (operand of
+// the data- and weight-gradient GEMMs); optional conv-bias gradient (column sums of dz).
+// Same structure as the forward pass: block row = image, a thread owns one 4-channel group of z
+// columns for the whole kernel (gated modes: the conv AND the gate column of its channels, so z and
+// dA are read once), with mean / rstd / rstd*gamma / t1/Np / t2/Np folded into registers up front.
+struct Bwd4 {
+  float4 mean, rstd, a, k1, k2, gamma, beta;   // a = rstd*gamma, k1 = t1/Np, k2 = t2/Np
+};
+__device__ __forceinline__ Bwd4 load_bwd4(const ApplyBwdArgs& p, int img, int ch, float invNp) {
+  const Norm4 n = load_norm(p.mean, p.rstd, p.gamma, p.beta, img, p.Nstat, p.affPeriod, ch);
+  const long long so = (long long)img * p.Nstat + ch;
+  const float4 t1 = ld4(p.t1 + so), t2 = ld4(p.t2 + so);
+  Bwd4 r;
+  r.mean = n.mean; r.rstd = n.rstd; r.gamma = n.gamma; r.beta = n.beta;
+  r.a = make_float4(n.rstd.x * n.gamma.x, n.rstd.y * n.gamma.y, n.rstd.z * n.gamma.z, n.rstd.w * n.gamma.w);
+  r.k1 = make_float4(t1.x * invNp, t1.y * invNp, t1.z * invNp, t1.w * invNp);
+  r.k2 = make_float4(t2.x * invNp, t2.y * invNp, t2.z * invNp, t2.w * invNp);
+  return r;
+}
+__device__ __forceinline__ float4 in_bwd4(float4 dy, float4 xh, const Bwd4& k) {
+  return make_float4(k.a.x * (dy.x - k.k1.x - xh.x * k.k2.x), k.a.y * (dy.y - k.k1.y - xh.y * k.k2.y),
+                     k.a.z * (dy.z - k.k1.z - xh.z * k.k2.z), k.a.w * (dy.w - k.k1.w - xh.w * k.k2.w));
+}
+__device__ __forceinline__ float4 xhat_b(float4 v, const Bwd4& k) {
+  return make_float4((v.x - k.mean.x) * k.rstd.x, (v.y - k.mean.y) * k.rstd.y, (v.z - k.mean.z) * k.rstd.z,
+                     (v.w - k.mean.w) * k.rstd.w);
+}
+__device__ __forceinline__ float4 affine_b(float4 xh, const Bwd4& k) {
+  return make_float4(fmaf(xh.x, k.gamma.x, k.beta.x), fmaf(xh.y, k.gamma.y, k.beta.y),
+                     fmaf(xh.z, k.gamma.z, k.beta.z), fmaf(xh.w, k.gamma.w, k.beta.w));
+}
+// block-level column sums -> atomicAdd (threads tid, tid+G4, ... share a column group)
+__device__ __forceinline__ void bias_reduce(float4 bsum, int G4, float* dst) {
+  __shared__ float4 sm[256];
+  sm[threadIdx.x] = bsum;
+  __syncthreads();
+  if ((int)threadIdx.x < G4) {
+    float4 t = bsum;
+    for (int k = threadIdx.x + G4; k < 256; k += G4) acc4(t, sm[k]);
+    atomicAdd(dst + 0, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
+  }
+  __syncthreads();
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
+  constexpr bool kGated = (MODE == kGatedIN || MODE == kGatedNoNorm);
   const int C = a.dA.C;
-  const int N4 = a.Nz >> 2;
-  const long long rows = (long long)a.dA.nImg * a.zY * a.zX;
-  const long long total = rows * N4;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int G4 = (kGated ? C : a.Nz) >> 2;       // column groups a block iteration covers
+  const int rows = 256 / G4;
+  const int col = (threadIdx.x % G4) << 2;       // z column (gated: conv column; gate = C + col)
+  const int r = threadIdx.x / G4;
+  const int img = blockIdx.y;
   const float invNp = 1.f / (float)((long long)a.dA.Y * a.dA.X);
-  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int col = (int)(first % N4) << 2;
-  for (long long idx = first; idx < total; idx += stride) {
-    long long row = idx / N4;
-    const int zx = (int)(row % a.zX);
-    long long r2 = row / a.zX;
-    const int zy = (int)(r2 % a.zY);
-    const int img = (int)(r2 / a.zY);
-    // which activation element this z column feeds
-    int c, y = zy, x = zx;
-    bool gate = false;
-    if (MODE == kINSwishShuffle) {
-      const int q = col / C;
-      c = col - q * C;
-      y = (zy << 1) | (q >> 1);
-      x = (zx << 1) | (q & 1);
-    } else if (MODE == kGatedIN || MODE == kGatedNoNorm) {
-      gate = col >= C;
-      c = gate ? col - C : col;
-    } else {
-      c = col;
-    }
-    const float* zr = a.z + row * a.Nz;
+  const int zP = a.zY * a.zX;
+  // which activation channel / sub-position this thread's z columns feed
+  int c = col, q = 0;
+  if (MODE == kINSwishShuffle) { q = col / C; c = col - q * C; }
+  Bwd4 ka{}, kg{};
+  if (MODE != kGatedNoNorm) {
+    ka = load_bwd4(a, img, (MODE == kINSwishShuffle) ? c : col, invNp);
+    if (MODE == kGatedIN) kg = load_bwd4(a, img, C + col, invNp);
+  }
+  const float* zimg = a.z + (long long)img * zP * a.Nz;
+  float4 bsa = make_float4(0.f, 0.f, 0.f, 0.f), bsg = bsa;
+  for (int p = blockIdx.x * rows + r; p < zP; p += gridDim.x * rows) {
+    const int zy = p / a.zX, zx = p - zy * a.zX;
+    int y = zy, x = zx;
+    if (MODE == kINSwishShuffle) { y = (zy << 1) | (q >> 1); x = (zx << 1) | (q & 1); }
+    const float* zr = zimg + (long long)p * a.Nz;
     const float4 d = ld4(a.dA.f32 + act_off(a.dA, img, y, x) + c);
-    float4 dz;
+    const long long orow = ((long long)img * zP + p) * a.Nz;
     if (MODE == kGatedNoNorm) {
-      const float4 va = ld4(zr + c), vg = ld4(zr + C + c);
+      const float4 va = ld4(zr + col), vg = ld4(zr + C + col);
       const float4 sg = make_float4(sigmoidf_(vg.x), sigmoidf_(vg.y), sigmoidf_(vg.z), sigmoidf_(vg.w));
-      if (!gate) dz = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
-      else dz = make_float4(d.x * va.x * sg.x * (1.f - sg.x), d.y * va.y * sg.y * (1.f - sg.y),
-                            d.z * va.z * sg.z * (1.f - sg.z), d.w * va.w * sg.w * (1.f - sg.w));
+      const float4 dza = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
+      const float4 dzg = make_float4(d.x * va.x * sg.x * (1.f - sg.x), d.y * va.y * sg.y * (1.f - sg.y),
+                                     d.z * va.z * sg.z * (1.f - sg.z), d.w * va.w * sg.w * (1.f - sg.w));
+      split_store4(a.dz_hi, a.dz_lo, orow + col, dza);
+      split_store4(a.dz_hi, a.dz_lo, orow + C + col, dzg);
+      acc4(bsa, dza); acc4(bsg, dzg);
+    } else if (MODE == kGatedIN) {
+      const float4 xa = xhat_b(ld4(zr + col), ka), xg = xhat_b(ld4(zr + C + col), kg);
+      const float4 ya = affine_b(xa, ka), yg = affine_b(xg, kg);
+      const float4 sg = make_float4(sigmoidf_(yg.x), sigmoidf_(yg.y), sigmoidf_(yg.z), sigmoidf_(yg.w));
+      const float4 dya = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
+      const float4 dyg = make_float4(d.x * ya.x * sg.x * (1.f - sg.x), d.y * ya.y * sg.y * (1.f - sg.y),
+                                     d.z * ya.z * sg.z * (1.f - sg.z), d.w * ya.w * sg.w * (1.f - sg.w));
+      const float4 dza = in_bwd4(dya, xa, ka), dzg = in_bwd4(dyg, xg, kg);
+      split_store4(a.dz_hi, a.dz_lo, orow + col, dza);
+      split_store4(a.dz_hi, a.dz_lo, orow + C + col, dzg);
+      acc4(bsa, dza); acc4(bsg, dzg);
     } else {
-      const int s = (MODE == kINSwishShuffle) ? c : col;  // stat channel of this column
-      const Norm4 n = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, s);
-      const float4 xh = xhat4(ld4(zr + col), n);
-      float4 dy;
-      if (MODE == kGatedIN) {
-        const Norm4 na = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, c);
-        const Norm4 ng = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, C + c);
-        const float4 ya = affine4(xhat4(ld4(zr + c), na), na);
-        const float4 yg = affine4(xhat4(ld4(zr + C + c), ng), ng);
-        const float4 sg = make_float4(sigmoidf_(yg.x), sigmoidf_(yg.y), sigmoidf_(yg.z), sigmoidf_(yg.w));
-        if (!gate) dy = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
-        else dy = make_float4(d.x * ya.x * sg.x * (1.f - sg.x), d.y * ya.y * sg.y * (1.f - sg.y),
-                              d.z * ya.z * sg.z * (1.f - sg.z), d.w * ya.w * sg.w * (1.f - sg.w));
-      } else if (MODE == kINOnly) {
-        dy = d;
-      } else {
-        const float4 yv = affine4(xh, n);
-        dy = make_float4(d.x * swish_grad(yv.x), d.y * swish_grad(yv.y), d.z * swish_grad(yv.z),
-                         d.w * swish_grad(yv.w));
+      const float4 xh = xhat_b(ld4(zr + col), ka);
+      float4 dy = d;
+      if (MODE != kINOnly) {
+        const float4 g = swish_grad4(affine_b(xh, ka));
+        dy = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
       }
-      const long long so = (long long)img * a.Nstat + s;
-      const float4 t1 = ld4(a.t1 + so), t2 = ld4(a.t2 + so);
-      dz.x = n.rstd.x * n.gamma.x * (dy.x - t1.x * invNp - xh.x * t2.x * invNp);
-      dz.y = n.rstd.y * n.gamma.y * (dy.y - t1.y * invNp - xh.y * t2.y * invNp);
-      dz.z = n.rstd.z * n.gamma.z * (dy.z - t1.z * invNp - xh.z * t2.z * invNp);
-      dz.w = n.rstd.w * n.gamma.w * (dy.w - t1.w * invNp - xh.w * t2.w * invNp);
+      const float4 dz = in_bwd4(dy, xh, ka);
+      split_store4(a.dz_hi, a.dz_lo, orow + col, dz);
+      acc4(bsa, dz);
     }
-    split_store4(a.dz_hi, a.dz_lo, row * a.Nz + col, dz);
-    bsum.x += dz.x; bsum.y += dz.y; bsum.z += dz.z; bsum.w += dz.w;
   }
   if (a.dbias) {
-    // threads of a block that share a column group: tid, tid + N4, ... (N4 divides 256 or is >= 256)
-    __shared__ float4 sm[256];
-    sm[threadIdx.x] = bsum;
-    __syncthreads();
-    if (N4 >= 256 || (int)threadIdx.x < N4) {
-      float4 t = bsum;
-      if (N4 < 256)
-        for (int k = threadIdx.x + N4; k < 256; k += N4) {
-          t.x += sm[k].x; t.y += sm[k].y; t.z += sm[k].z; t.w += sm[k].w;
-        }
-      atomicAdd(a.dbias + col + 0, t.x);
-      atomicAdd(a.dbias + col + 1, t.y);
-      atomicAdd(a.dbias + col + 2, t.z);
-      atomicAdd(a.dbias + col + 3, t.w);
-    }
+    bias_reduce(bsa, G4, a.dbias + col);
+    if (kGated) bias_reduce(bsg, G4, a.dbias + C + col);
   }
 }
 
 cudaError_t launch_apply_bwd(const ApplyBwdArgs& a, cudaStream_t s) {
-  const int N4 = a.Nz >> 2;
-  const long long total = (long long)a.dA.nImg * a.zY * a.zX * N4;
-  if (a.dbias && !(256 % N4 == 0 || N4 % 256 == 0)) {
-    set_error("apply_bwd: Nz=%d unsupported for bias reduction", a.Nz);
+  const bool gated = a.mode == kGatedIN || a.mode == kGatedNoNorm;
+  const int G4 = (gated ? a.dA.C : a.Nz) >> 2;
+  if (G4 < 1 || (G4 <= 256 && 256 % G4)) { set_error("apply_bwd: %d column groups unsupported", G4); return cudaErrorInvalidValue; }
+  if (G4 > 256) {
+    // wide rows (the 1D->2D layer, 5120 columns viewed as [B*20][256]) are passed as narrower images
+    set_error("apply_bwd: Nz=%d too wide; pass it as more images of <= 1024 columns", a.Nz);
     return cudaErrorInvalidValue;
   }
-  int g = grid_for(total, 256);
-  // keep (grid*256) a multiple of N4 so each thread stays on one column group
-  if (N4 > 256) {
-    const int m = N4 / 256;
-    g = ((g + m - 1) / m) * m;
-  }
+  const dim3 g = rows_grid(a.zY * a.zX, 256 / G4, a.dA.nImg);
   switch (a.mode) {
     case kGatedNoNorm: apply_bwd_kernel<kGatedNoNorm><<<g, 256, 0, s>>>(a); break;
     case kGatedIN: apply_bwd_kernel<kGatedIN><<<g, 256, 0, s>>>(a); break;
