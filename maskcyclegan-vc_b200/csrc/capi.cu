@@ -71,6 +71,8 @@ static const ModelDesc* desc(int model) {
 }
 static bool shape_ok(int B, int T) {
   if (B < 1 || T < 1) { set_error("batch and frames must be >= 1 (got %d, %d)", B, T); return false; }
+  // the layer kernels index positions with 32-bit integers
+  if ((long long)B * 80 * T >= (1LL << 31) / 4) { set_error("batch x frames too large (%d x %d)", B, T); return false; }
   return true;
 }
 

@@ -370,8 +370,13 @@ cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
   if (splits > 64) splits = 64;
   dim3 grid(cg, a.dA.nImg, splits);
   const size_t tbytes = (size_t)a.dA.nImg * a.Nstat * sizeof(float);
-  cudaError_t e = cudaMemsetAsync(a.t1, 0, tbytes, s);
-  if (e == cudaSuccess) e = cudaMemsetAsync(a.t2, 0, tbytes, s);
+  cudaError_t e;
+  if (a.t2 == a.t1 + (size_t)a.dA.nImg * a.Nstat) {
+    e = cudaMemsetAsync(a.t1, 0, 2 * tbytes, s);        // adjacent: one memset
+  } else {
+    e = cudaMemsetAsync(a.t1, 0, tbytes, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a.t2, 0, tbytes, s);
+  }
   if (e != cudaSuccess) return e;
   switch (a.mode) {
     case kGatedIN: apply_bwd_reduce_kernel<kGatedIN><<<grid, 256, 0, s>>>(a); break;
@@ -573,14 +578,15 @@ __device__ __forceinline__ StemW load_stem_w(const __nv_bfloat16* __restrict__ w
   }
   return r;
 }
-__device__ __forceinline__ void load_patch(const float* __restrict__ x, long long b, int h, int w,
-                                           int T, float (&xv)[9]) {
+__device__ __forceinline__ void load_patch(const float* __restrict__ x, int b, int h, int w, int T,
+                                           float (&xv)[9]) {
+  const float* xc = x + ((long long)b * 80 + h) * T + w;   // centre tap
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
       const int hs = h + kh - 1, ws = w + kw - 1;
-      xv[kh * 3 + kw] = (hs >= 0 && hs < 80 && ws >= 0 && ws < T) ? __ldg(x + (b * 80 + hs) * T + ws) : 0.f;
+      xv[kh * 3 + kw] = (hs >= 0 && hs < 80 && ws >= 0 && ws < T) ? __ldg(xc + (kh - 1) * T + (kw - 1)) : 0.f;
     }
 }
 
@@ -592,11 +598,12 @@ __global__ void __launch_bounds__(256) d_stem_fwd_kernel(const float* __restrict
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const StemW sw = load_stem_w(wh, wl, bias, lane);
-  const long long total = (long long)B * 80 * T;
-  for (long long pos = warp; pos < total; pos += nwarps) {
-    const int w = (int)(pos % T);
-    const int h = (int)((pos / T) % 80);
-    const long long b = pos / ((long long)T * 80);
+  const int total = B * 80 * T;              // launcher guarantees < 2^31
+  for (int pos = (int)warp; pos < total; pos += (int)nwarps) {
+    const int w = pos % T;
+    const int bh = pos / T;
+    const int h = bh % 80;
+    const int b = bh / 80;
     float xv[9];
     load_patch(x, b, h, w, T, xv);
     float z[4];
@@ -607,7 +614,7 @@ __global__ void __launch_bounds__(256) d_stem_fwd_kernel(const float* __restrict
       for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], xv[t], acc);
       z[c] = acc * sigmoidf_(acc);
     }
-    split_store4(out.hi, out.lo, act_off(out, (int)b, h, w) + lane * 4, make_float4(z[0], z[1], z[2], z[3]));
+    split_store4(out.hi, out.lo, act_off(out, b, h, w) + lane * 4, make_float4(z[0], z[1], z[2], z[3]));
   }
 }
 cudaError_t launch_d_stem_fwd(const float* x, int B, int T, const __nv_bfloat16* wh,
@@ -640,14 +647,15 @@ __global__ void __launch_bounds__(256) d_stem_bwd_kernel(const float* __restrict
 #pragma unroll
     for (int t = 0; t < 9; ++t) gw[c][t] = 0.f;
   }
-  const long long total = (long long)B * 80 * T;
-  for (long long pos = warp; pos < total; pos += nwarps) {
-    const int w = (int)(pos % T);
-    const int h = (int)((pos / T) % 80);
-    const long long b = pos / ((long long)T * 80);
+  const int total = B * 80 * T;              // launcher guarantees < 2^31
+  for (int pos = (int)warp; pos < total; pos += (int)nwarps) {
+    const int w = pos % T;
+    const int bh = pos / T;
+    const int h = bh % 80;
+    const int b = bh / 80;
     float xv[9];
     load_patch(x, b, h, w, T, xv);
-    const float4 d4 = ld4(dA.f32 + act_off(dA, (int)b, h, w) + lane * 4);
+    const float4 d4 = ld4(dA.f32 + act_off(dA, b, h, w) + lane * 4);
     const float d[4] = {d4.x, d4.y, d4.z, d4.w};
     float dz[4];
 #pragma unroll
@@ -666,7 +674,7 @@ __global__ void __launch_bounds__(256) d_stem_bwd_kernel(const float* __restrict
         float p = dz[0] * sw.w[0][t] + dz[1] * sw.w[1][t] + dz[2] * sw.w[2][t] + dz[3] * sw.w[3][t];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        if (lane == t) q[pos * 12 + t] = p;
+        if (lane == t) q[(long long)pos * 12 + t] = p;
       }
     }
   }
@@ -699,12 +707,12 @@ cudaError_t launch_d_stem_bwd(const float* x, int B, int T, const __nv_bfloat16*
 //   out[b,h,w] = bias + sum_{kh,kw} P[(b, h+kh-2, w+kw-7), kh*15+kw]
 __global__ void head_g_fwd_kernel(const float* __restrict__ P, const float* __restrict__ bias,
                                   int B, int Y, int X, float* __restrict__ out) {
-  const long long total = (long long)B * Y * X;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % X);
-    const int y = (int)((idx / X) % Y);
-    const long long b = idx / ((long long)X * Y);
+  const int total = B * Y * X;               // launcher guarantees < 2^31
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int x = idx % X;
+    const int by = idx / X;
+    const int y = by % Y;
+    const long long b = by / Y;
     float acc = bias[0];
     for (int kh = 0; kh < 5; ++kh) {
       const int ys = y + kh - 2;
@@ -733,10 +741,11 @@ __global__ void head_g_bwd_kernel(const float* __restrict__ dout, int B, int Y, 
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int t4 = (int)(idx & 31) << 2;
-    const long long pos = idx >> 5;
-    const int x = (int)(pos % X);
-    const int y = (int)((pos / X) % Y);
-    const long long b = pos / ((long long)X * Y);
+    const int pos = (int)(idx >> 5);           // launcher guarantees B*Y*X < 2^31
+    const int x = pos % X;
+    const int by = pos / X;
+    const int y = by % Y;
+    const long long b = by / Y;
     float v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -745,7 +754,7 @@ __global__ void head_g_bwd_kernel(const float* __restrict__ dout, int B, int Y, 
       const int ys = y - kh + 2, xs = x - kw + 7;
       v[i] = (t < 75 && ys >= 0 && ys < Y && xs >= 0 && xs < X) ? dout[(b * Y + ys) * X + xs] : 0.f;
     }
-    split_store4(hi, lo, pos * 128 + t4, make_float4(v[0], v[1], v[2], v[3]));
+    split_store4(hi, lo, (long long)pos * 128 + t4, make_float4(v[0], v[1], v[2], v[3]));
     if (t4 == 0) bacc += dout[pos];
   }
   if (dbias) {

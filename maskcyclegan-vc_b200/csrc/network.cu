@@ -441,14 +441,14 @@ bool fused_stats_enabled() {
   return v != 0;
 }
 void run_conv_in(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& taps, int oB, int oY,
-                 int oX, const OutAddr& o, const float* bias, const char* what, float* ssum, float* ssq,
+                 int oX, const OutAddr& o, const float* bias, const char* what, float* ssum, float* /*unused*/,
                  int statImgs, int statNz, int groups, int planePositions, const Stat& st, const float* z) {
   if (!r.ok) return;
+  float* ssq = ssum + (size_t)statImgs * statNz;   // sums of squares right behind the sums
   const bool fused = r.rc.backend == 0 && fused_stats_enabled();
   if (fused) {
     const size_t bytes = (size_t)statImgs * statNz * sizeof(float);
-    r.check(cudaMemsetAsync(ssum, 0, bytes, r.rc.stream), what);
-    r.check(cudaMemsetAsync(ssq, 0, bytes, r.rc.stream), what);
+    r.check(cudaMemsetAsync(ssum, 0, 2 * bytes, r.rc.stream), what);   // sums and squares in one memset
     run_conv(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0, ssum, ssq);
     if (r.ok) r.check(launch_stats_finalize(ssum, ssq, statImgs, statNz, groups, planePositions, st.mean, st.rstd, r.rc.stream), what);
   } else {
@@ -474,7 +474,9 @@ ApplyBwdArgs mk_bwd(int mode, const float* z, int Nz, int zY, int zX, const Stat
   a.mode = mode; a.z = z; a.Nz = Nz; a.zY = zY; a.zX = zX;
   a.mean = st.mean; a.rstd = st.rstd; a.Nstat = Nstat;
   a.gamma = gamma; a.beta = beta; a.affPeriod = affPeriod;
-  a.dA = dA; a.t1 = t1; a.t2 = t2; a.dgamma = dgamma; a.dbeta = dbeta;
+  (void)t2;
+  a.dA = dA; a.t1 = t1; a.t2 = t1 + (size_t)dA.nImg * Nstat;   // adjacent: zeroed with one memset
+  a.dgamma = dgamma; a.dbeta = dbeta;
   a.dz_hi = dz.hi; a.dz_lo = dz.lo; a.dbias = dbias;
   return a;
 }
@@ -642,8 +644,8 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   const auto& cv = md.convs;
   const auto& nm = md.norms;
   Arena wa(ws);
-  float* ssum = wa.takeT<float>((long long)B * 5120);   // conv-epilogue statistics accumulators
-  float* ssq = wa.takeT<float>((long long)B * 5120);
+  float* ssum = wa.takeT<float>((long long)2 * B * 5120);   // conv-epilogue statistics: sums, then sums of squares
+  float* ssq = nullptr;
 
   // parity-split buffers have a padding column/row when the extent is odd: keep it zero
   if (d.T & 1) {
@@ -1001,8 +1003,8 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
   const auto& cv = md.convs;
   const auto& nm = md.norms;
   Arena wa(ws);
-  float* ssum = wa.takeT<float>((long long)B * 1024);
-  float* ssq = wa.takeT<float>((long long)B * 1024);
+  float* ssum = wa.takeT<float>((long long)2 * B * 1024);
+  float* ssq = nullptr;
   if (d.T & 1) {
     r.check(launch_fill_zero(s.D0.hi, parity_elems(B, 80, d.T, 128) * 2, st), "zero D0");
     r.check(launch_fill_zero(s.D0.lo, parity_elems(B, 80, d.T, 128) * 2, st), "zero D0");
