@@ -304,7 +304,7 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        key = "parity_pair_kernels" if args.precision != "fast" else "fast"
+        key = "parity_final" if args.precision != "fast" else "fast"
         if key in tj:
             traffic = tj[key]["conv_dram_bytes_per_launch_mean_over_G_forward"]
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (implicit-GEMM fprop+dgrad, tcgen05)",

@@ -332,22 +332,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
   const int nTiles = g.w.N / BLOCK_N;
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
-  const int totalTiles = nTiles * mTiles;
-  const int numK = g.nTaps * g.cBlocks;
+  const int tilesPerGroup = nTiles * mTiles;
+  const int totalTiles = tilesPerGroup * g.nGroups;   // groups: same operands, own tap list + output base
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
-      const int nt = tile % nTiles;
-      int mt = tile / nTiles;
+      const int grp = tile / tilesPerGroup;
+      const int tl = tile - grp * tilesPerGroup;
+      const int nt = tl % nTiles;
+      int mt = tl / nTiles;
       const int tx = mt % g.tilesX;
       mt /= g.tilesX;
       const int ty = mt % g.tilesY;
       const int tb = mt / g.tilesY;
       const int x0 = tx * g.BX, y0 = ty * g.BY, b0 = tb * g.BB, n0 = nt * BLOCK_N;
-      for (int t = 0; t < g.nTaps; ++t) {
+      const int tapEnd = g.grpTapStart[grp] + g.grpTapCount[grp];
+      for (int t = g.grpTapStart[grp]; t < tapEnd; ++t) {
         const Tap tap = g.taps[t];
         for (int cb = 0; cb < g.cBlocks; ++cb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -378,6 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       ptx::mbar_wait(&tempty[acc], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const int numK = g.grpTapCount[tile / tilesPerGroup] * g.cBlocks;
       for (int kb = 0; kb < numK; ++kb) {
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
@@ -410,8 +414,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int nt = tile % nTiles;
-      int mt = tile / nTiles;
+      const int grp = tile / tilesPerGroup;
+      const int tl = tile - grp * tilesPerGroup;
+      const int nt = tl % nTiles;
+      int mt = tl / nTiles;
       const int tx = mt % g.tilesX;
       mt /= g.tilesX;
       const int ty = mt % g.tilesY;
@@ -422,8 +428,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const int bb = row / (g.BX * g.BY);
       const int x = tx * g.BX + bx, y = ty * g.BY + by, b = tb * g.BB + bb;
       const bool valid = (x < g.oX) && (y < g.oY) && (b < g.oB);
-      const long long off = (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
-                            (long long)(n0 / g.nSplit) * g.sNhi + (n0 % g.nSplit);
+      const long long off = g.grpOutOff[grp] + (long long)b * g.sB + (long long)y * g.sY +
+                            (long long)x * g.sX + (long long)(n0 / g.nSplit) * g.sNhi + (n0 % g.nSplit);
       float* orow = g.out + off;
       const float* arow = g.addsrc ? g.addsrc + off : nullptr;
 
@@ -470,6 +476,9 @@ static bool check_conv_geom(const ConvGeom& g, int blockN) {
   if (g.nTaps < 1 || g.nTaps > kMaxTaps) { set_error("conv: nTaps=%d", g.nTaps); return false; }
   if (g.cBlocks != g.a.C / kBlockK) { set_error("conv: cBlocks"); return false; }
   if (g.nPass != 1 && g.nPass != 3) { set_error("conv: nPass=%d", g.nPass); return false; }
+  if (g.nGroups < 1 || g.nGroups > 4) { set_error("conv: nGroups=%d", g.nGroups); return false; }
+  for (int i = 0; i < g.nGroups; ++i)
+    if (g.grpTapCount[i] < 1 || g.grpTapStart[i] + g.grpTapCount[i] > g.nTaps) { set_error("conv: group %d taps", i); return false; }
   return true;
 }
 
@@ -498,7 +507,7 @@ static cudaError_t launch_conv_tc_t(const ConvGeom& g, cudaStream_t stream) {
     if (e != cudaSuccess) { set_error("conv: smem attr: %s", cudaGetErrorString(e)); return e; }
     attr_set = true;
   }
-  const int total = (g.w.N / BLOCK_N) * g.tilesX * g.tilesY * g.tilesB;
+  const int total = (g.w.N / BLOCK_N) * g.tilesX * g.tilesY * g.tilesB * g.nGroups;
   const int grid = total < num_sms() ? total : num_sms();
   profile_begin(0, g.algoFlops, stream);
   conv_tc_kernel<BLOCK_N, NPASS><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
@@ -580,8 +589,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const int nTiles = g.w.N / BLOCK_N;
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
   const int pairM = (mTiles + 1) / 2;
-  const int totalTiles = nTiles * pairM;
-  const int numK = g.nTaps * g.cBlocks;
+  const int tilesPerGroup = nTiles * pairM;
+  const int totalTiles = tilesPerGroup * g.nGroups;
   const int pairIdx = blockIdx.x >> 1;
   const int numPairs = gridDim.x >> 1;
 
@@ -590,8 +599,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pairIdx; tile < totalTiles; tile += numPairs) {
-      const int nt = tile % nTiles;
-      int mt = (tile / nTiles) * 2 + (int)rank;
+      const int grp = tile / tilesPerGroup;
+      const int tl = tile - grp * tilesPerGroup;
+      const int nt = tl % nTiles;
+      int mt = (tl / nTiles) * 2 + (int)rank;
       int x0, y0, b0;
       if (mt < mTiles) {
         const int tx = mt % g.tilesX;
@@ -601,7 +612,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         x0 = 0; y0 = 0; b0 = g.tilesB * g.BB;
       }
       const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
-      for (int t = 0; t < g.nTaps; ++t) {
+      const int tapEnd = g.grpTapStart[grp] + g.grpTapCount[grp];
+      for (int t = g.grpTapStart[grp]; t < tapEnd; ++t) {
         const Tap tap = g.taps[t];
         for (int cb = 0; cb < g.cBlocks; ++cb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -633,6 +645,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       ptx::mbar_wait(&tempty[acc], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const int numK = g.grpTapCount[tile / tilesPerGroup] * g.cBlocks;
       for (int kb = 0; kb < numK; ++kb) {
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
@@ -665,8 +678,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     for (int tile = pairIdx; tile < totalTiles; tile += numPairs, ++it) {
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int nt = tile % nTiles;
-      int mt = (tile / nTiles) * 2 + (int)rank;
+      const int grp = tile / tilesPerGroup;
+      const int tl = tile - grp * tilesPerGroup;
+      const int nt = tl % nTiles;
+      int mt = (tl / nTiles) * 2 + (int)rank;
       const bool real = mt < mTiles;
       const int tx = mt % g.tilesX;
       mt /= g.tilesX;
@@ -680,8 +695,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       int b = tb * g.BB + bb;
       const bool valid = real && (x < g.oX) && (y < g.oY) && (b < g.oB);
       if (!real) b = g.oB;
-      const long long off = (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
-                            (long long)(n0 / g.nSplit) * g.sNhi + (n0 % g.nSplit);
+      const long long off = g.grpOutOff[grp] + (long long)b * g.sB + (long long)y * g.sY +
+                            (long long)x * g.sX + (long long)(n0 / g.nSplit) * g.sNhi + (n0 % g.nSplit);
       float* orow = g.out + off;
       const float* arow = g.addsrc ? g.addsrc + off : nullptr;
 
@@ -735,7 +750,7 @@ static cudaError_t launch_conv_tc2_t(const ConvGeom& g, cudaStream_t stream) {
     attr_set = true;
   }
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
-  const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2);
+  const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups;
   const int maxPairs = num_sms() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
   profile_begin(0, g.algoFlops, stream);
@@ -764,7 +779,7 @@ static bool try_launch_conv_tc2(const ConvGeom& g, cudaStream_t stream, cudaErro
   int bn = (g.w.N % 256 == 0 && g.nSplit % 256 == 0) ? 256 : 128;
   if (g_force_block_n == 128) bn = 128;
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
-  const long long pairTiles = (long long)(g.w.N / bn) * ((mTiles + 1) / 2);
+  const long long pairTiles = (long long)(g.w.N / bn) * ((mTiles + 1) / 2) * g.nGroups;
   if (g_force_cta2 < 0 && pairTiles < num_sms() / 2) return false;   // small layers: 1-CTA kernel
   if (g.nPass == 3) *err = bn == 256 ? launch_conv_tc2_t<256, 3>(g, stream) : launch_conv_tc2_t<128, 3>(g, stream);
   else *err = bn == 256 ? launch_conv_tc2_t<256, 1>(g, stream) : launch_conv_tc2_t<128, 1>(g, stream);
@@ -792,7 +807,7 @@ cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream) {
   int bn = 64;
   if (g.w.N % 128 == 0 && g.nSplit % 128 == 0) bn = 128;
   // small position grids (the 1-D trunk): narrower tiles so that more SMs get a tile
-  if (bn == 128 && (long long)g.tilesX * g.tilesY * g.tilesB * (g.w.N / 128) < num_sms()) bn = 64;
+  if (bn == 128 && (long long)g.tilesX * g.tilesY * g.tilesB * (g.w.N / 128) * g.nGroups < num_sms()) bn = 64;
   if (g_force_block_n == 256 && g.w.N % 256 == 0 && g.nSplit % 256 == 0) bn = 256;
   if (g_force_block_n == 64) bn = 64;
   if (g.nPass == 3) {
@@ -814,9 +829,11 @@ __device__ __forceinline__ float bf16_bits_to_f(uint16_t v) {
 }
 
 __global__ void conv_simt_kernel(const __grid_constant__ ConvGeom g) {
-  const long long total = (long long)g.tilesX * g.tilesY * g.tilesB * kTileM * g.w.N;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  const long long perGroup = (long long)g.tilesX * g.tilesY * g.tilesB * kTileM * g.w.N;
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= perGroup * g.nGroups) return;
+  const int grp = (int)(gidx / perGroup);
+  const long long idx = gidx - grp * perGroup;
   const int n = (int)(idx % g.w.N);
   long long r = idx / g.w.N;
   const int row = (int)(r % kTileM);
@@ -833,7 +850,7 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvGeom g) {
   const uint16_t* Wh = reinterpret_cast<const uint16_t*>(g.w.hi);
   const uint16_t* Wl = reinterpret_cast<const uint16_t*>(g.w.lo);
   float acc = 0.f;
-  for (int t = 0; t < g.nTaps; ++t) {
+  for (int t = g.grpTapStart[grp]; t < g.grpTapStart[grp] + g.grpTapCount[grp]; ++t) {
     const Tap tap = g.taps[t];
     const int xx = x + tap.dx, yy = y + tap.dy;
     if (xx < 0 || xx >= g.a.X || yy < 0 || yy >= g.a.Y) continue;
@@ -851,7 +868,7 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvGeom g) {
       }
     }
   }
-  const long long off = (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
+  const long long off = g.grpOutOff[grp] + (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
                         (long long)(n / g.nSplit) * g.sNhi + (n % g.nSplit);
   if (g.bias) acc += g.bias[n];
   if (g.addsrc) acc += g.addsrc[off];
@@ -860,7 +877,7 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvGeom g) {
 
 cudaError_t launch_conv_simt(const ConvGeom& g, cudaStream_t stream) {
   if (!check_conv_geom(g, 64)) return cudaErrorInvalidValue;
-  const long long total = (long long)g.tilesX * g.tilesY * g.tilesB * kTileM * g.w.N;
+  const long long total = (long long)g.tilesX * g.tilesY * g.tilesB * kTileM * g.w.N * g.nGroups;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   conv_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>(g);

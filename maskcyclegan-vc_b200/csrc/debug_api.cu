@@ -31,6 +31,7 @@ int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY,
     g.taps[t].plane = (uint8_t)taps4[4 * t + 2];
     g.taps[t].w = (uint8_t)taps4[4 * t + 3];
   }
+  g.nGroups = 1; g.grpTapStart[0] = 0; g.grpTapCount[0] = nTaps; g.grpOutOff[0] = 0;
   g.sB = sB; g.sY = sY; g.sX = sX; g.nSplit = nSplit; g.sNhi = sNhi;
   g.out = out; g.bias = bias; g.addsrc = addsrc; g.nPass = nPass;
   // backend: 0 = tcgen05 single-CTA, 1 = SIMT checker, 2 = tcgen05 CTA-pair (cta_group::2)

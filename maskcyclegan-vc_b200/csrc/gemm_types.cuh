@@ -41,6 +41,12 @@ struct ConvGeom {
   int tilesX, tilesY, tilesB;
   int nTaps, cBlocks;
   Tap taps[kMaxTaps];
+  // tile groups: up to 4 convolutions over the same operands and position grid that differ only in
+  // their tap sub-list and output base (the four parity planes of a stride-2 data gradient) run as
+  // ONE launch so that their tiles fill the SMs together; nGroups = 1 for ordinary convolutions
+  int nGroups;
+  int grpTapStart[4], grpTapCount[4];
+  long long grpOutOff[4];
   // output addressing, in floats
   long long sB, sY, sX;
   int nSplit;          // column n lives at (n / nSplit) * sNhi + (n % nSplit)

@@ -340,6 +340,7 @@ void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& t
   g.nTaps = taps.n;
   g.cBlocks = a.C / kBlockK;
   for (int i = 0; i < taps.n; ++i) g.taps[i] = taps.t[i];
+  g.nGroups = 1; g.grpTapStart[0] = 0; g.grpTapCount[0] = taps.n; g.grpOutOff[0] = 0;
   g.sB = o.sB; g.sY = o.sY; g.sX = o.sX; g.nSplit = o.nSplit; g.sNhi = o.sNhi;
   g.out = o.out; g.bias = bias; g.addsrc = addsrc;
   g.nPass = r.rc.nPass;
@@ -430,6 +431,42 @@ Stat take_stat(Arena& a, long long n) {
   s.mean = a.takeT<float>(n);
   s.rstd = a.takeT<float>(n);
   return s;
+}
+
+// Data gradient of a stride-2 KxK convolution: the four input-parity planes are four stride-1
+// convolutions over dz with disjoint tap subsets; they run as ONE launch (tile groups) so that
+// their tiles fill the SMs together.  dIn is the parity-split fp32 gradient [B][4][Yp][Xp][Cin].
+void run_dgrad_s2(Run& r, const ActOperand& dz, const WgtOperand& w, int K, int pad, int B, int Yp, int Xp,
+                  int Cin, float* dIn, const char* what) {
+  if (!r.ok) return;
+  ConvGeom g{};
+  g.a = dz;
+  g.w = w;
+  g.oX = Xp; g.oY = Yp; g.oB = B;
+  if (!choose_box(B, Yp, Xp, kTileM, &g.BX, &g.BY, &g.BB)) { r.ok = false; set_error("%s: box", what); return; }
+  g.tilesX = (Xp + g.BX - 1) / g.BX;
+  g.tilesY = (Yp + g.BY - 1) / g.BY;
+  g.tilesB = (B + g.BB - 1) / g.BB;
+  g.cBlocks = dz.C / kBlockK;
+  g.nGroups = 4;
+  int nt = 0;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      const int p = ph * 2 + pw;
+      const TapList tl = taps_s2_bwd(K, pad, ph, pw);
+      g.grpTapStart[p] = nt;
+      g.grpTapCount[p] = tl.n;
+      g.grpOutOff[p] = (long long)p * Yp * Xp * Cin;
+      for (int i = 0; i < tl.n; ++i) g.taps[nt++] = tl.t[i];
+    }
+  g.nTaps = nt;
+  g.sB = (long long)4 * Yp * Xp * Cin; g.sY = (long long)Xp * Cin; g.sX = Cin;
+  g.nSplit = Cin; g.sNhi = 0;
+  g.out = dIn; g.bias = nullptr; g.addsrc = nullptr;
+  g.nPass = r.rc.nPass;
+  g.algoFlops = 2.0 * B * Yp * Xp * (double)w.N * nt * dz.C;
+  g.statSum = nullptr; g.statSq = nullptr; g.statSeg = 32;
+  r.check(r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream), what);
 }
 
 // Convolution whose output feeds an InstanceNorm: the statistics come out of the conv epilogue
@@ -890,16 +927,8 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   run_bwd(r, mk_bwd(kGatedIN, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[GN_DS2]), W.beta(nm[GN_DS2]), 1,
                     gbuf(dA2, B, 20, d.W2, 256, 0), t1, t2, gGa(GN_DS2), gBe(GN_DS2), dz2, nullptr), "G ds2 bwd");
   float* dA1 = a.takeT<float>(parity_elems(B, 40, d.W1, 256));
-  {
-    const int Yp = 20, Xp = (d.W1 + 1) / 2;  // == output grid of ds2 (20 x W2)
-    for (int ph = 0; ph < 2; ++ph)
-      for (int pw = 0; pw < 2; ++pw) {
-        const int p = ph * 2 + pw;
-        OutAddr o{dA1 + (long long)p * Yp * Xp * 256, (long long)4 * Yp * Xp * 256, (long long)Xp * 256, 256, 256, 0};
-        run_conv(r, plain_op(dz2.hi, dz2.lo, B, 20, d.W2, 512), W.bwd(cv[G_DS2]), taps_s2_bwd(5, 2, ph, pw),
-                 B, Yp, Xp, o, nullptr, nullptr, "G ds2 dgrad");
-      }
-  }
+  run_dgrad_s2(r, plain_op(dz2.hi, dz2.lo, B, 20, d.W2, 512), W.bwd(cv[G_DS2]), 5, 2, B, 20, (d.W1 + 1) / 2, 256,
+               dA1, "G ds2 dgrad");
   if (needWgrad)
     run_wgrad(r, plain_op(dz2.hi, dz2.lo, B, 20, d.W2, 512), parity_op(s.A1.hi, s.A1.lo, B, 40, d.W1, 256),
               taps_s2_fwd(5, 2), nullptr, B, 20, d.W2, gW(G_DS2), "G ds2 wgrad");
@@ -908,16 +937,8 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   run_bwd(r, mk_bwd(kGatedIN, s.z1, 512, 40, d.W1, s.st1, 512, W.gamma(nm[GN_DS1]), W.beta(nm[GN_DS1]), 1,
                     gbuf(dA1, B, 40, d.W1, 256, 1), t1, t2, gGa(GN_DS1), gBe(GN_DS1), dz1, nullptr), "G ds1 bwd");
   float* dA0 = a.takeT<float>(parity_elems(B, 80, d.T, 128));
-  {
-    const int Yp = 40, Xp = (d.T + 1) / 2;
-    for (int ph = 0; ph < 2; ++ph)
-      for (int pw = 0; pw < 2; ++pw) {
-        const int p = ph * 2 + pw;
-        OutAddr o{dA0 + (long long)p * Yp * Xp * 128, (long long)4 * Yp * Xp * 128, (long long)Xp * 128, 128, 128, 0};
-        run_conv(r, plain_op(dz1.hi, dz1.lo, B, 40, d.W1, 512), W.bwd(cv[G_DS1]), taps_s2_bwd(5, 2, ph, pw),
-                 B, Yp, Xp, o, nullptr, nullptr, "G ds1 dgrad");
-      }
-  }
+  run_dgrad_s2(r, plain_op(dz1.hi, dz1.lo, B, 40, d.W1, 512), W.bwd(cv[G_DS1]), 5, 2, B, 40, (d.T + 1) / 2, 128,
+               dA0, "G ds1 dgrad");
   if (needWgrad)
     run_wgrad(r, plain_op(dz1.hi, dz1.lo, B, 40, d.W1, 512), parity_op(s.A0.hi, s.A0.lo, B, 80, d.T, 128),
               taps_s2_fwd(5, 2), nullptr, B, 40, d.W1, gW(G_DS1), "G ds1 wgrad");
@@ -1115,15 +1136,8 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
                       gbuf(dAct, B, v.Yo, v.Xo, v.Nz, dActParity), t1, t2, gGa(v.ni), gBe(v.ni), dz, nullptr),
             "D ds bwd");
     float* dIn = a.takeT<float>(parity_elems(B, v.Yi, v.Xi, v.Cin));
-    const int Yp = (v.Yi + 1) / 2, Xp = (v.Xi + 1) / 2;
-    for (int ph = 0; ph < 2; ++ph)
-      for (int pw = 0; pw < 2; ++pw) {
-        const int p = ph * 2 + pw;
-        OutAddr o{dIn + (long long)p * Yp * Xp * v.Cin, (long long)4 * Yp * Xp * v.Cin, (long long)Xp * v.Cin,
-                  v.Cin, v.Cin, 0};
-        run_conv(r, plain_op(dz.hi, dz.lo, B, v.Yo, v.Xo, v.Nz), W.bwd(cv[v.ci]), taps_s2_bwd(3, 1, ph, pw), B,
-                 Yp, Xp, o, nullptr, nullptr, "D ds dgrad");
-      }
+    run_dgrad_s2(r, plain_op(dz.hi, dz.lo, B, v.Yo, v.Xo, v.Nz), W.bwd(cv[v.ci]), 3, 1, B, (v.Yi + 1) / 2,
+                 (v.Xi + 1) / 2, v.Cin, dIn, "D ds dgrad");
     if (needWgrad)
       run_wgrad(r, plain_op(dz.hi, dz.lo, B, v.Yo, v.Xo, v.Nz), parity_op(v.xin.hi, v.xin.lo, B, v.Yi, v.Xi, v.Cin),
                 k33, nullptr, B, v.Yo, v.Xo, gW(v.ci), "D ds wgrad");
