@@ -230,8 +230,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line)
+        # NCCL prints its version banner (and warnings) to stdout; rank 0's stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
