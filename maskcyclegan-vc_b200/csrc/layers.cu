@@ -16,7 +16,9 @@ static int grid_for(long long work, int threads) {
   return (int)blocks;
 }
 
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+// fast sigmoid: ex2.approx + rcp.approx (~1e-7 relative error); an IEEE division here costs more
+// instructions than the rest of an activation and made several layer kernels issue-bound
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
 __device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off,
                                              float4 v) {
@@ -578,16 +580,36 @@ __device__ __forceinline__ StemW load_stem_w(const __nv_bfloat16* __restrict__ w
   }
   return r;
 }
-__device__ __forceinline__ void load_patch(const float* __restrict__ x, int b, int h, int w, int T,
-                                           float (&xv)[9]) {
-  const float* xc = x + ((long long)b * 80 + h) * T + w;   // centre tap
+// One warp walks one (b, h) row left to right with a sliding 3x3 window (3 new loads per step, no
+// per-position index divisions); the parity-split store alternates between the row's two planes.
+struct RowWindow {
+  const float* r[3];   // rows h-1, h, h+1 of the input (null when outside the 80 mel bins)
+  float v[9];
+  int T;
+  __device__ __forceinline__ void init(const float* x, int b, int h, int T_) {
+    T = T_;
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int hs = h + kh - 1, ws = w + kw - 1;
-      xv[kh * 3 + kw] = (hs >= 0 && hs < 80 && ws >= 0 && ws < T) ? __ldg(xc + (kh - 1) * T + (kw - 1)) : 0.f;
+    for (int k = 0; k < 3; ++k) {
+      const int hs = h + k - 1;
+      r[k] = (hs >= 0 && hs < 80) ? x + ((long long)b * 80 + hs) * T : nullptr;
+      v[k * 3 + 0] = 0.f;                                   // column w-1 = -1
+      v[k * 3 + 1] = 0.f;                                   // filled by the first advance()
+      v[k * 3 + 2] = r[k] ? __ldg(r[k]) : 0.f;              // column 0
     }
+  }
+  // move the window so that its centre column is w (call with w = 0, 1, 2, ...)
+  __device__ __forceinline__ void advance(int w) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      v[k * 3 + 0] = v[k * 3 + 1];
+      v[k * 3 + 1] = v[k * 3 + 2];
+      v[k * 3 + 2] = (r[k] && w + 1 < T) ? __ldg(r[k] + w + 1) : 0.f;
+    }
+  }
+};
+__device__ __forceinline__ long long row_plane_base(const ActBuf& a, int b, int h, int pw) {
+  // offset of element (b, h, x = pw, c = 0); consecutive same-parity x are a.C apart
+  return act_off(a, b, h, pw);
 }
 
 __global__ void __launch_bounds__(256) d_stem_fwd_kernel(const float* __restrict__ x, int B, int T,
@@ -595,31 +617,38 @@ __global__ void __launch_bounds__(256) d_stem_fwd_kernel(const float* __restrict
                                                          const __nv_bfloat16* __restrict__ wl,
                                                          const float* __restrict__ bias, ActBuf out) {
   const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const StemW sw = load_stem_w(wh, wl, bias, lane);
-  const int total = B * 80 * T;              // launcher guarantees < 2^31
-  for (int pos = (int)warp; pos < total; pos += (int)nwarps) {
-    const int w = pos % T;
-    const int bh = pos / T;
-    const int h = bh % 80;
-    const int b = bh / 80;
-    float xv[9];
-    load_patch(x, b, h, w, T, xv);
-    float z[4];
+  const int rows = B * 80;
+  for (int row = warp; row < rows; row += nwarps) {
+    const int b = row / 80, h = row - b * 80;
+    RowWindow win;
+    win.init(x, b, h, T);
+    const long long base0 = row_plane_base(out, b, h, 0) + lane * 4;
+    const long long base1 = T > 1 ? row_plane_base(out, b, h, 1) + lane * 4 : base0;
+    for (int w = 0; w < T; ++w) {
+      win.advance(w);
+      float z[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float acc = sw.b[c];
+      for (int c = 0; c < 4; ++c) {
+        float acc = sw.b[c];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], xv[t], acc);
-      z[c] = acc * sigmoidf_(acc);
+        for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], win.v[t], acc);
+        z[c] = acc * sigmoidf_(acc);
+      }
+      const long long off = ((w & 1) ? base1 : base0) + (long long)(w >> 1) * out.C;
+      split_store4(out.hi, out.lo, off, make_float4(z[0], z[1], z[2], z[3]));
     }
-    split_store4(out.hi, out.lo, act_off(out, b, h, w) + lane * 4, make_float4(z[0], z[1], z[2], z[3]));
   }
 }
 cudaError_t launch_d_stem_fwd(const float* x, int B, int T, const __nv_bfloat16* wh,
                               const __nv_bfloat16* wl, const float* bias, ActBuf out, cudaStream_t s) {
-  d_stem_fwd_kernel<<<148 * 8, 256, 0, s>>>(x, B, T, wh, wl, bias, out);
+  if (!out.parity) { set_error("d_stem_fwd: expects a parity-split output"); return cudaErrorInvalidValue; }
+  const int rows = B * 80;
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  d_stem_fwd_kernel<<<blocks, 256, 0, s>>>(x, B, T, wh, wl, bias, out);
   return launched();
 }
 
@@ -633,12 +662,12 @@ __global__ void __launch_bounds__(256) d_stem_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ bias, ActBuf dA,
                                                          float* __restrict__ dW, float* __restrict__ dB,
                                                          float* __restrict__ q) {
-  __shared__ float sacc[40 * 128];
+  __shared__ float sacc[10 * 128];
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 40 * 128; i += blockDim.x) sacc[i] = 0.f;
+  for (int i = threadIdx.x; i < 10 * 128; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const StemW sw = load_stem_w(wh, wl, bias, lane);
   float gw[4][9], gb[4];
 #pragma unroll
@@ -647,34 +676,37 @@ __global__ void __launch_bounds__(256) d_stem_bwd_kernel(const float* __restrict
 #pragma unroll
     for (int t = 0; t < 9; ++t) gw[c][t] = 0.f;
   }
-  const int total = B * 80 * T;              // launcher guarantees < 2^31
-  for (int pos = (int)warp; pos < total; pos += (int)nwarps) {
-    const int w = pos % T;
-    const int bh = pos / T;
-    const int h = bh % 80;
-    const int b = bh / 80;
-    float xv[9];
-    load_patch(x, b, h, w, T, xv);
-    const float4 d4 = ld4(dA.f32 + act_off(dA, b, h, w) + lane * 4);
-    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-    float dz[4];
+  const int rows = B * 80;
+  for (int row = warp; row < rows; row += nwarps) {
+    const int b = row / 80, h = row - b * 80;
+    RowWindow win;
+    win.init(x, b, h, T);
+    const long long base0 = row_plane_base(dA, b, h, 0) + lane * 4;
+    const long long base1 = T > 1 ? row_plane_base(dA, b, h, 1) + lane * 4 : base0;
+    for (int w = 0; w < T; ++w) {
+      win.advance(w);
+      const float4 d4 = ld4(dA.f32 + ((w & 1) ? base1 : base0) + (long long)(w >> 1) * dA.C);
+      const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+      float dz[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float acc = sw.b[c];
+      for (int c = 0; c < 4; ++c) {
+        float acc = sw.b[c];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], xv[t], acc);
-      dz[c] = d[c] * swish_grad(acc);
-      gb[c] += dz[c];
+        for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], win.v[t], acc);
+        dz[c] = d[c] * swish_grad(acc);
+        gb[c] += dz[c];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) gw[c][t] = fmaf(dz[c], xv[t], gw[c][t]);
-    }
-    if (q) {
+        for (int t = 0; t < 9; ++t) gw[c][t] = fmaf(dz[c], win.v[t], gw[c][t]);
+      }
+      if (q) {
+        const long long pos = (long long)row * T + w;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        float p = dz[0] * sw.w[0][t] + dz[1] * sw.w[1][t] + dz[2] * sw.w[2][t] + dz[3] * sw.w[3][t];
+        for (int t = 0; t < 9; ++t) {
+          float p = dz[0] * sw.w[0][t] + dz[1] * sw.w[1][t] + dz[2] * sw.w[2][t] + dz[3] * sw.w[3][t];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        if (lane == t) q[(long long)pos * 12 + t] = p;
+          for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+          if (lane == t) q[pos * 12 + t] = p;
+        }
       }
     }
   }
@@ -697,7 +729,11 @@ __global__ void __launch_bounds__(256) d_stem_bwd_kernel(const float* __restrict
 cudaError_t launch_d_stem_bwd(const float* x, int B, int T, const __nv_bfloat16* wh,
                               const __nv_bfloat16* wl, const float* bias, ActBuf dA, float* dW,
                               float* dB, float* q, cudaStream_t s) {
-  d_stem_bwd_kernel<<<148 * 4, 256, 0, s>>>(x, B, T, wh, wl, bias, dA, dW, dB, q);
+  if (!dA.parity) { set_error("d_stem_bwd: expects a parity-split gradient"); return cudaErrorInvalidValue; }
+  const int rows = B * 80;
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  d_stem_bwd_kernel<<<blocks, 256, 0, s>>>(x, B, T, wh, wl, bias, dA, dW, dB, q);
   return launched();
 }
 
