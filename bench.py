@@ -281,8 +281,30 @@ def main():
     value = frames * K / (ms * 1e-3)
     e2e_value = frames * K / (ms_e2e * 1e-3)
 
-    # roofline: per-launch CUDA-event timing of the tensor-core kernels over extra steps
+    # north_star's own target line: Generator forward + backward (parameter gradients, input not
+    # requiring grad) at this batch, 58.636 algorithmic GFLOP per 80x64 sample
     peaks = load_peaks()
+    G0 = models[0]
+    gx, gm = resident[0], resident[1]
+
+    def g_fwd_bwd():
+        G0.zero_grad(set_to_none=True)
+        G0(gx, gm).sum().backward()
+
+    gfb = {}
+    G0.train()
+    for gmode in ("parity", "mixed", "fast"):
+        eng.set_precision(modes[gmode])
+        for _ in range(3):
+            g_fwd_bwd()
+        ms_g = timed_steps(g_fwd_bwd, 10, world) / 10
+        tf = 58.636e9 * B / (ms_g * 1e-3) / 1e12
+        gfb[gmode] = {"ms": ms_g, "algorithmic_tflops": tf, "frac_of_sustained_peak": tf / peaks["bf16_tflops_sustained"],
+                      "frac_of_burst_peak": tf / peaks["bf16_tflops"]}
+    eng.set_precision(modes[args.precision])
+    G0.zero_grad(set_to_none=True)
+
+    # roofline: per-launch CUDA-event timing of the tensor-core kernels over extra steps
     eng.set_overlap(False)      # kernels timed one at a time on their stream (no concurrent wgrad stream)
     step_resident()
     torch.cuda.synchronize()
@@ -373,6 +395,9 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "other_precision": other,
+            "generator_fwd_bwd": {"note": "north_star target line: Generator forward+backward at batch %d, 80x64 "
+                                          "(58.636 algorithmic GFLOP per sample; parity mode issues 3 MMAs per MAC, "
+                                          "mixed = forward x3 / backward x1)" % B, **gfb},
             "losses_last_step": {"g": float(losses["gh"]), "d": float(losses["dh"])},
         }
         if sync is not None:

@@ -100,6 +100,9 @@ int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY,
                      int oB, int nTaps, const int8_t* taps4, float* out, long long sB,
                      long long sY, long long sX, int nSplit, long long sNhi, const float* bias,
                      const float* addsrc, int nPass, int backend, int blockN, void* stream);
+/* split-K factor used by the following mcgvc_debug_conv calls on the tensor-core backends: every tile's
+ * k-blocks run as `k` work items that are added into `out` (which the caller zero-fills); 1 = off. */
+int mcgvc_debug_set_conv_ksplit(int k);
 int mcgvc_debug_wgrad(const void* z_hi, const void* z_lo, int zC, int zX, int zY, int zB,
                       const void* x_hi, const void* x_lo, int xC, int xX, int xY, int xP, int xB,
                       int pX, int pY, int pB, int nTaps, const int8_t* taps4,

@@ -221,9 +221,17 @@ __device__ __forceinline__ void warp_colsum_add(float (&a)[32], float (&b)[32], 
 }
 
 // one 32-column chunk of this thread's output row: +bias, +residual, store, optional statistics
+__device__ __forceinline__ void red_add_f32x4(float* addr, float4 t) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(t.x), "f"(t.y), "f"(t.z),
+               "f"(t.w)
+               : "memory");
+}
+
+// `partial`: this work item holds one K-slice of the tile (split-K): its accumulator is ADDED to the
+// zero-initialised output with red.global.add; bias and residual ride on the first slice only.
 __device__ __forceinline__ void epilogue_chunk(const ConvGeom& g, const uint32_t (&v)[32], bool valid,
                                                float* orow, const float* arow, int ncol0, int lane,
-                                               int b) {
+                                               int b, bool partial, bool first) {
   float o[32];
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
@@ -232,16 +240,17 @@ __device__ __forceinline__ void epilogue_chunk(const ConvGeom& g, const uint32_t
     t.y = __uint_as_float(v[i + 1]);
     t.z = __uint_as_float(v[i + 2]);
     t.w = __uint_as_float(v[i + 3]);
-    if (g.bias) {
+    if (g.bias && first) {
       const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + ncol0 + i));
       t.x += bv.x; t.y += bv.y; t.z += bv.z; t.w += bv.w;
     }
     if (valid) {
-      if (arow) {
+      if (arow && first) {
         const float4 av = *reinterpret_cast<const float4*>(arow + i);
         t.x += av.x; t.y += av.y; t.z += av.z; t.w += av.w;
       }
-      *reinterpret_cast<float4*>(orow + i) = t;
+      if (partial) red_add_f32x4(orow + i, t);
+      else *reinterpret_cast<float4*>(orow + i) = t;
     }
     o[i] = t.x; o[i + 1] = t.y; o[i + 2] = t.z; o[i + 3] = t.w;
   }
@@ -334,12 +343,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
   const int tilesPerGroup = nTiles * mTiles;
   const int totalTiles = tilesPerGroup * g.nGroups;   // groups: same operands, own tap list + output base
+  // split-K: a work item is (tile, K-slice); the slices of one tile are neighbouring items, so they
+  // run at the same time on neighbouring SMs (shared activation rows and output lines stay in L2)
+  const int kSplit = g.kSplit > 1 ? g.kSplit : 1;
+  const int totalItems = totalTiles * kSplit;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < totalItems; item += gridDim.x) {
+      const int tile = item / kSplit;
+      const int ks = item - tile * kSplit;
       const int grp = tile / tilesPerGroup;
       const int tl = tile - grp * tilesPerGroup;
       const int nt = tl % nTiles;
@@ -349,24 +364,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const int ty = mt % g.tilesY;
       const int tb = mt / g.tilesY;
       const int x0 = tx * g.BX, y0 = ty * g.BY, b0 = tb * g.BB, n0 = nt * BLOCK_N;
-      const int tapEnd = g.grpTapStart[grp] + g.grpTapCount[grp];
-      for (int t = g.grpTapStart[grp]; t < tapEnd; ++t) {
+      const int numK = g.grpTapCount[grp] * g.cBlocks;
+      const int kBeg = ks * numK / kSplit, kEnd = (ks + 1) * numK / kSplit;
+      int t = g.grpTapStart[grp] + kBeg / g.cBlocks;
+      int cb = kBeg % g.cBlocks;
+      for (int kb = kBeg; kb < kEnd; ++kb) {
         const Tap tap = g.taps[t];
-        for (int cb = 0; cb < g.cBlocks; ++cb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* st = smem + stage * Cfg::kStageBytes;
-          ptx::mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-          ptx::tma_load_5d(st, &tmAh, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        ptx::mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+        ptx::tma_load_5d(st, &tmAh, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
+                         tap.plane, b0);
+        ptx::tma_load_3d(st + Cfg::kABytes, &tmWh, &full[stage], cb * kBlockK, n0, tap.w);
+        if (NPASS == 3) {
+          uint8_t* lo = st + Cfg::kABytes + Cfg::kBBytes;
+          ptx::tma_load_5d(lo, &tmAl, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
                            tap.plane, b0);
-          ptx::tma_load_3d(st + Cfg::kABytes, &tmWh, &full[stage], cb * kBlockK, n0, tap.w);
-          if (NPASS == 3) {
-            uint8_t* lo = st + Cfg::kABytes + Cfg::kBBytes;
-            ptx::tma_load_5d(lo, &tmAl, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
-                             tap.plane, b0);
-            ptx::tma_load_3d(lo + Cfg::kABytes, &tmWl, &full[stage], cb * kBlockK, n0, tap.w);
-          }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          ptx::tma_load_3d(lo + Cfg::kABytes, &tmWl, &full[stage], cb * kBlockK, n0, tap.w);
         }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++cb == g.cBlocks) { cb = 0; ++t; }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -375,13 +392,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < totalItems; item += gridDim.x, ++it) {
+      const int tile = item / kSplit;
+      const int ks = item - tile * kSplit;
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       ptx::mbar_wait(&tempty[acc], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      const int numK = g.grpTapCount[tile / tilesPerGroup] * g.cBlocks;
+      const int numKg = g.grpTapCount[tile / tilesPerGroup] * g.cBlocks;
+      const int numK = (ks + 1) * numKg / kSplit - ks * numKg / kSplit;
       for (int kb = 0; kb < numK; ++kb) {
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
@@ -411,7 +431,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < totalItems; item += gridDim.x, ++it) {
+      const int tile = item / kSplit;
+      const int ks = item - tile * kSplit;
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int grp = tile / tilesPerGroup;
@@ -441,7 +463,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         uint32_t v[32];
         ptx::tmem_ld32(taddr + j * 32, v);
         ptx::tmem_ld_wait();
-        epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b);
+        epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b,
+                       kSplit > 1, ks == 0);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -479,6 +502,11 @@ static bool check_conv_geom(const ConvGeom& g, int blockN) {
   if (g.nGroups < 1 || g.nGroups > 4) { set_error("conv: nGroups=%d", g.nGroups); return false; }
   for (int i = 0; i < g.nGroups; ++i)
     if (g.grpTapCount[i] < 1 || g.grpTapStart[i] + g.grpTapCount[i] > g.nTaps) { set_error("conv: group %d taps", i); return false; }
+  if (g.kSplit > 1) {
+    if (g.statSum) { set_error("conv: split-K cannot feed the fused statistics"); return false; }
+    for (int i = 0; i < g.nGroups; ++i)
+      if (g.kSplit > g.grpTapCount[i] * g.cBlocks) { set_error("conv: kSplit=%d exceeds the %d k-blocks of group %d", g.kSplit, g.grpTapCount[i] * g.cBlocks, i); return false; }
+  }
   return true;
 }
 
@@ -507,7 +535,7 @@ static cudaError_t launch_conv_tc_t(const ConvGeom& g, cudaStream_t stream) {
     if (e != cudaSuccess) { set_error("conv: smem attr: %s", cudaGetErrorString(e)); return e; }
     attr_set = true;
   }
-  const int total = (g.w.N / BLOCK_N) * g.tilesX * g.tilesY * g.tilesB * g.nGroups;
+  const int total = (g.w.N / BLOCK_N) * g.tilesX * g.tilesY * g.tilesB * g.nGroups * (g.kSplit > 1 ? g.kSplit : 1);
   const int grid = total < num_sms() ? total : num_sms();
   profile_begin(0, g.algoFlops, stream);
   conv_tc_kernel<BLOCK_N, NPASS><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
@@ -591,6 +619,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const int pairM = (mTiles + 1) / 2;
   const int tilesPerGroup = nTiles * pairM;
   const int totalTiles = tilesPerGroup * g.nGroups;
+  const int kSplit = g.kSplit > 1 ? g.kSplit : 1;   // split-K work items, see conv_tc_kernel
+  const int totalItems = totalTiles * kSplit;
   const int pairIdx = blockIdx.x >> 1;
   const int numPairs = gridDim.x >> 1;
 
@@ -598,7 +628,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = pairIdx; tile < totalTiles; tile += numPairs) {
+    for (int item = pairIdx; item < totalItems; item += numPairs) {
+      const int tile = item / kSplit;
+      const int ks = item - tile * kSplit;
       const int grp = tile / tilesPerGroup;
       const int tl = tile - grp * tilesPerGroup;
       const int nt = tl % nTiles;
@@ -612,25 +644,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         x0 = 0; y0 = 0; b0 = g.tilesB * g.BB;
       }
       const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
-      const int tapEnd = g.grpTapStart[grp] + g.grpTapCount[grp];
-      for (int t = g.grpTapStart[grp]; t < tapEnd; ++t) {
+      const int numK = g.grpTapCount[grp] * g.cBlocks;
+      const int kBeg = ks * numK / kSplit, kEnd = (ks + 1) * numK / kSplit;
+      int t = g.grpTapStart[grp] + kBeg / g.cBlocks;
+      int cb = kBeg % g.cBlocks;
+      for (int kb = kBeg; kb < kEnd; ++kb) {
         const Tap tap = g.taps[t];
-        for (int cb = 0; cb < g.cBlocks; ++cb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* st = smem + stage * Cfg::kStageBytes;
-          if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
-          ptx::tma_load_5d_2sm(st, &tmAh, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+        ptx::tma_load_5d_2sm(st, &tmAh, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
+                             tap.plane, b0);
+        ptx::tma_load_3d_2sm(st + Cfg::kABytes, &tmWh, &full[stage], cb * kBlockK, n0, tap.w);
+        if (NPASS == 3) {
+          uint8_t* lo = st + Cfg::kABytes + Cfg::kBBytes;
+          ptx::tma_load_5d_2sm(lo, &tmAl, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
                                tap.plane, b0);
-          ptx::tma_load_3d_2sm(st + Cfg::kABytes, &tmWh, &full[stage], cb * kBlockK, n0, tap.w);
-          if (NPASS == 3) {
-            uint8_t* lo = st + Cfg::kABytes + Cfg::kBBytes;
-            ptx::tma_load_5d_2sm(lo, &tmAl, &full[stage], cb * kBlockK, x0 + tap.dx, y0 + tap.dy,
-                                 tap.plane, b0);
-            ptx::tma_load_3d_2sm(lo + Cfg::kABytes, &tmWl, &full[stage], cb * kBlockK, n0, tap.w);
-          }
-          if (!leader) ptx::mbar_arrive_remote(&full[stage], 0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          ptx::tma_load_3d_2sm(lo + Cfg::kABytes, &tmWl, &full[stage], cb * kBlockK, n0, tap.w);
         }
+        if (!leader) ptx::mbar_arrive_remote(&full[stage], 0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++cb == g.cBlocks) { cb = 0; ++t; }
       }
     }
   } else if (warp == 1 && lane == 0 && leader) {
@@ -639,13 +673,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = pairIdx; tile < totalTiles; tile += numPairs, ++it) {
+    for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
+      const int tile = item / kSplit;
+      const int ks = item - tile * kSplit;
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       ptx::mbar_wait(&tempty[acc], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      const int numK = g.grpTapCount[tile / tilesPerGroup] * g.cBlocks;
+      const int numKg = g.grpTapCount[tile / tilesPerGroup] * g.cBlocks;
+      const int numK = (ks + 1) * numKg / kSplit - ks * numKg / kSplit;
       for (int kb = 0; kb < numK; ++kb) {
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
@@ -675,7 +712,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     int it = 0;
-    for (int tile = pairIdx; tile < totalTiles; tile += numPairs, ++it) {
+    for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
+      const int tile = item / kSplit;
+      const int ks = item - tile * kSplit;
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int grp = tile / tilesPerGroup;
@@ -708,7 +747,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         uint32_t v[32];
         ptx::tmem_ld32(taddr + j * 32, v);
         ptx::tmem_ld_wait();
-        epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b);
+        epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b,
+                       kSplit > 1, ks == 0);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -750,7 +790,7 @@ static cudaError_t launch_conv_tc2_t(const ConvGeom& g, cudaStream_t stream) {
     attr_set = true;
   }
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
-  const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups;
+  const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups * (g.kSplit > 1 ? g.kSplit : 1);
   const int maxPairs = num_sms() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
   profile_begin(0, g.algoFlops, stream);
@@ -772,20 +812,6 @@ static int env_cta2() {
 static int g_force_cta2 = -1;
 void set_force_cta2(int v) { g_force_cta2 = v; }
 
-static bool try_launch_conv_tc2(const ConvGeom& g, cudaStream_t stream, cudaError_t* err) {
-  const int want = g_force_cta2 >= 0 ? g_force_cta2 : env_cta2();
-  if (!want) return false;
-  if (g.w.N % 128 || g.nSplit % 128) return false;
-  int bn = (g.w.N % 256 == 0 && g.nSplit % 256 == 0) ? 256 : 128;
-  if (g_force_block_n == 128) bn = 128;
-  const int mTiles = g.tilesX * g.tilesY * g.tilesB;
-  const long long pairTiles = (long long)(g.w.N / bn) * ((mTiles + 1) / 2) * g.nGroups;
-  if (g_force_cta2 < 0 && pairTiles < num_sms() / 2) return false;   // small layers: 1-CTA kernel
-  if (g.nPass == 3) *err = bn == 256 ? launch_conv_tc2_t<256, 3>(g, stream) : launch_conv_tc2_t<128, 3>(g, stream);
-  else *err = bn == 256 ? launch_conv_tc2_t<256, 1>(g, stream) : launch_conv_tc2_t<128, 1>(g, stream);
-  return true;
-}
-
 // BLOCK_N selection: widest tile that divides N and nSplit (256 halves B-operand smem traffic per
 // MMA; 64 exists for the narrow data-gradient outputs of the two stem layers).
 
@@ -798,25 +824,86 @@ static int env_block_n() {
   return v;
 }
 
-cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream) {
-  if (g_force_block_n == 0 && env_block_n() != 0) g_force_block_n = env_block_n();
-  {
-    cudaError_t e2 = cudaSuccess;
-    if (try_launch_conv_tc2(g, stream, &e2)) return e2;
+// Which kernel a geometry runs on: CTA pair (M = 256) or single CTA (M = 128), and its BLOCK_N.
+struct ConvVariant {
+  bool pair;
+  int bn;
+  long long tiles;   // work items before split-K
+  int slots;         // concurrent work items on the chip
+};
+static ConvVariant conv_variant(const ConvGeom& g) {
+  ConvVariant v{};
+  const int mTiles = g.tilesX * g.tilesY * g.tilesB;
+  const int want = g_force_cta2 >= 0 ? g_force_cta2 : env_cta2();
+  if (want && g.w.N % 128 == 0 && g.nSplit % 128 == 0) {
+    int bn = (g.w.N % 256 == 0 && g.nSplit % 256 == 0) ? 256 : 128;
+    if (g_force_block_n == 128) bn = 128;
+    const long long pairTiles = (long long)(g.w.N / bn) * ((mTiles + 1) / 2) * g.nGroups;
+    if (g_force_cta2 >= 0 || pairTiles >= num_sms() / 2) {   // small layers: 1-CTA kernel
+      v.pair = true; v.bn = bn; v.tiles = pairTiles; v.slots = num_sms() / 2;
+      return v;
+    }
   }
   int bn = 64;
   if (g.w.N % 128 == 0 && g.nSplit % 128 == 0) bn = 128;
   // small position grids (the 1-D trunk): narrower tiles so that more SMs get a tile
-  if (bn == 128 && (long long)g.tilesX * g.tilesY * g.tilesB * (g.w.N / 128) * g.nGroups < num_sms()) bn = 64;
+  if (bn == 128 && (long long)mTiles * (g.w.N / 128) * g.nGroups < num_sms()) bn = 64;
   if (g_force_block_n == 256 && g.w.N % 256 == 0 && g.nSplit % 256 == 0) bn = 256;
   if (g_force_block_n == 64) bn = 64;
+  v.pair = false; v.bn = bn; v.tiles = (long long)mTiles * (g.w.N / bn) * g.nGroups; v.slots = num_sms();
+  return v;
+}
+
+static int env_ksplit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCGVC_KSPLIT");   // 0 disables split-K (A/B measurements)
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+int conv_plan_ksplit(const ConvGeom& g, double minGain) {
+  if (!env_ksplit() || g.statSum) return 1;
+  if (g_force_block_n == 0 && env_block_n() != 0) g_force_block_n = env_block_n();
+  const ConvVariant v = conv_variant(g);
+  if (v.tiles < v.slots) return 1;             // sub-wave layers are latency-bound, not wave-bound
+  int minK = 1 << 30;
+  for (int i = 0; i < g.nGroups; ++i) {
+    const int k = g.grpTapCount[i] * g.cBlocks;
+    if (k < minK) minK = k;
+  }
+  int maxS = minK / 4;                          // at least 4 k-blocks per slice
+  if (maxS > 8) maxS = 8;
+  auto cost = [&](int s) {
+    const double waves = (double)(v.tiles * s) / v.slots;
+    const double rounds = (double)((v.tiles * s + v.slots - 1) / v.slots);
+    return rounds / waves + 0.01 * (s - 1);
+  };
+  int best = 1;
+  double bestCost = cost(1);
+  for (int s = 2; s <= maxS; ++s) {
+    const double c = cost(s);
+    if (c < bestCost - 1e-9) { bestCost = c; best = s; }
+  }
+  if (best > 1 && cost(1) - bestCost < minGain * cost(1)) best = 1;
+  return best;
+}
+
+cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream) {
+  if (g_force_block_n == 0 && env_block_n() != 0) g_force_block_n = env_block_n();
+  const ConvVariant v = conv_variant(g);
+  if (v.pair) {
+    if (g.nPass == 3) return v.bn == 256 ? launch_conv_tc2_t<256, 3>(g, stream) : launch_conv_tc2_t<128, 3>(g, stream);
+    return v.bn == 256 ? launch_conv_tc2_t<256, 1>(g, stream) : launch_conv_tc2_t<128, 1>(g, stream);
+  }
   if (g.nPass == 3) {
-    if (bn == 256) return launch_conv_tc_t<256, 3>(g, stream);
-    if (bn == 128) return launch_conv_tc_t<128, 3>(g, stream);
+    if (v.bn == 256) return launch_conv_tc_t<256, 3>(g, stream);
+    if (v.bn == 128) return launch_conv_tc_t<128, 3>(g, stream);
     return launch_conv_tc_t<64, 3>(g, stream);
   }
-  if (bn == 256) return launch_conv_tc_t<256, 1>(g, stream);
-  if (bn == 128) return launch_conv_tc_t<128, 1>(g, stream);
+  if (v.bn == 256) return launch_conv_tc_t<256, 1>(g, stream);
+  if (v.bn == 128) return launch_conv_tc_t<128, 1>(g, stream);
   return launch_conv_tc_t<64, 1>(g, stream);
 }
 

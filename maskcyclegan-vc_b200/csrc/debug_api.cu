@@ -7,7 +7,16 @@ using namespace mcgvc;
 
 namespace mcgvc { void set_force_block_n(int n); void set_force_cta2(int v); void set_force_wgrad_cta2(int v); }
 
+static int g_debug_ksplit = 1;
+
 extern "C" {
+
+/* split-K factor the next mcgvc_debug_conv calls use on the tensor-core backends (the caller
+ * zero-fills `out`; bias / addsrc ride on the first slice); 1 = off. */
+int mcgvc_debug_set_conv_ksplit(int k) {
+  g_debug_ksplit = k < 1 ? 1 : k;
+  return 0;
+}
 
 int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY, int aP, int aB,
                      const void* w_hi, const void* w_lo, int wK, int wN, int wT, int oX, int oY,
@@ -34,6 +43,7 @@ int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY,
   g.nGroups = 1; g.grpTapStart[0] = 0; g.grpTapCount[0] = nTaps; g.grpOutOff[0] = 0;
   g.sB = sB; g.sY = sY; g.sX = sX; g.nSplit = nSplit; g.sNhi = sNhi;
   g.out = out; g.bias = bias; g.addsrc = addsrc; g.nPass = nPass;
+  g.kSplit = backend == 1 ? 1 : g_debug_ksplit;
   // backend: 0 = tcgen05 single-CTA, 1 = SIMT checker, 2 = tcgen05 CTA-pair (cta_group::2)
   set_force_block_n(blockN);
   set_force_cta2(backend == 2 ? 1 : 0);

@@ -60,6 +60,10 @@ struct ConvGeom {
   float* statSum;
   float* statSq;
   int statSeg;          // lanes of an epilogue warp that share an image: min(32, BX*BY)
+  // split-K: every tile's k-blocks (taps x channel blocks) are cut into kSplit slices that run as
+  // separate work items and are ADDED into `out` (red.global.add) -- the caller zero-fills `out`
+  // first; incompatible with the fused statistics.  0 / 1 = off.  See conv_plan_ksplit().
+  int kSplit;
 };
 
 // Weight-gradient GEMM:  dW[w_t][n][c] += sum over positions (b,y,x) in this CTA's K-slice of
@@ -83,6 +87,11 @@ struct WgradGeom {
 };
 
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);
+// Split-K factor that fills whole waves of SMs best for this geometry (1 = leave it alone).  Layers
+// whose tile count is a little over one wave (80 CTA-pair tiles on 74 pairs) otherwise pay two full
+// rounds for 1.08 rounds of work.  `minGain` = required relative time saving (the zero-fill and the
+// atomic merge are not free).
+int conv_plan_ksplit(const ConvGeom& g, double minGain);
 cudaError_t launch_conv_simt(const ConvGeom& g, cudaStream_t stream);
 cudaError_t launch_wgrad_tc(const WgradGeom& g, cudaStream_t stream);
 cudaError_t launch_wgrad_simt(const WgradGeom& g, cudaStream_t stream);

@@ -325,15 +325,14 @@ OutAddr plain_out(float* out, int Y, int X, int N) {
   return OutAddr{out, (long long)Y * X * N, (long long)X * N, (long long)N, N, 0};
 }
 
-void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& taps, int oB, int oY,
-              int oX, const OutAddr& o, const float* bias, const float* addsrc, const char* what,
-              double algoFrac = 1.0, float* statSum = nullptr, float* statSq = nullptr) {
-  if (!r.ok) return;
+ConvGeom conv_geom(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& taps, int oB, int oY,
+                   int oX, const OutAddr& o, const float* bias, const float* addsrc, const char* what,
+                   double algoFrac) {
   ConvGeom g{};
   g.a = a;
   g.w = w;
   g.oX = oX; g.oY = oY; g.oB = oB;
-  if (!choose_box(oB, oY, oX, kTileM, &g.BX, &g.BY, &g.BB)) { r.ok = false; set_error("%s: box", what); return; }
+  if (!choose_box(oB, oY, oX, kTileM, &g.BX, &g.BY, &g.BB)) { r.ok = false; set_error("%s: box", what); return g; }
   g.tilesX = (oX + g.BX - 1) / g.BX;
   g.tilesY = (oY + g.BY - 1) / g.BY;
   g.tilesB = (oB + g.BB - 1) / g.BB;
@@ -345,9 +344,34 @@ void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& t
   g.out = o.out; g.bias = bias; g.addsrc = addsrc;
   g.nPass = r.rc.nPass;
   g.algoFlops = 2.0 * oB * oY * oX * (double)w.N * taps.n * a.C * algoFrac;
+  g.statSum = nullptr; g.statSq = nullptr;
+  g.statSeg = g.BX * g.BY >= 32 ? 32 : g.BX * g.BY;
+  g.kSplit = 1;
+  return g;
+}
+
+// Split-K (tensor-core backend only): when the planner finds that K-slices fill the SM waves
+// better, zero-fill the `splitFloats` floats at g.out and let the slices add into it.
+void plan_split(Run& r, ConvGeom& g, long long splitFloats, double minGain, const char* what) {
+  if (!r.ok || splitFloats <= 0 || r.rc.backend != 0) return;
+  const int s = conv_plan_ksplit(g, minGain);
+  if (s <= 1) return;
+  r.check(cudaMemsetAsync(g.out, 0, (size_t)splitFloats * sizeof(float), r.rc.stream), what);
+  g.kSplit = s;
+}
+
+// `splitFloats` > 0: the output is a dense region of that many floats starting at o.out and the
+// convolution may run split-K (data gradients: no statistics to fuse).
+void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& taps, int oB, int oY,
+              int oX, const OutAddr& o, const float* bias, const float* addsrc, const char* what,
+              double algoFrac = 1.0, float* statSum = nullptr, float* statSq = nullptr,
+              long long splitFloats = 0) {
+  if (!r.ok) return;
+  ConvGeom g = conv_geom(r, a, w, taps, oB, oY, oX, o, bias, addsrc, what, algoFrac);
+  if (!r.ok) return;
   g.statSum = r.rc.backend == 0 ? statSum : nullptr;
   g.statSq = statSq;
-  g.statSeg = g.BX * g.BY >= 32 ? 32 : g.BX * g.BY;
+  if (!g.statSum) plan_split(r, g, splitFloats, 0.08, what);
   r.check(r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream), what);
 }
 
@@ -466,6 +490,8 @@ void run_dgrad_s2(Run& r, const ActOperand& dz, const WgtOperand& w, int K, int 
   g.nPass = r.rc.nPass;
   g.algoFlops = 2.0 * B * Yp * Xp * (double)w.N * nt * dz.C;
   g.statSum = nullptr; g.statSq = nullptr; g.statSeg = 32;
+  g.kSplit = 1;
+  plan_split(r, g, (long long)B * 4 * Yp * Xp * Cin, 0.08, what);
   r.check(r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream), what);
 }
 
@@ -479,10 +505,22 @@ bool fused_stats_enabled() {
 }
 void run_conv_in(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& taps, int oB, int oY,
                  int oX, const OutAddr& o, const float* bias, const char* what, float* ssum, float* /*unused*/,
-                 int statImgs, int statNz, int groups, int planePositions, const Stat& st, const float* z) {
+                 int statImgs, int statNz, int groups, int planePositions, const Stat& st, const float* z,
+                 long long splitFloats = 0) {
   if (!r.ok) return;
   float* ssq = ssum + (size_t)statImgs * statNz;   // sums of squares right behind the sums
-  const bool fused = r.rc.backend == 0 && fused_stats_enabled();
+  bool fused = r.rc.backend == 0 && fused_stats_enabled();
+  if (fused && splitFloats > 0) {
+    // layers a little over one SM wave (Discriminator ds3: 80 pair tiles on 74 pairs): split-K plus
+    // one stand-alone statistics pass over z beats paying a second, nearly empty round
+    ConvGeom g = conv_geom(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0);
+    if (r.ok && conv_plan_ksplit(g, 0.2) > 1) fused = false;
+  }
+  if (!fused && r.rc.backend == 0 && splitFloats > 0) {
+    run_conv(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0, nullptr, nullptr, splitFloats);
+    if (r.ok) r.check(launch_stats(z, statNz, planePositions, statImgs, groups, st.mean, st.rstd, r.rc.stream), what);
+    return;
+  }
   if (fused) {
     const size_t bytes = (size_t)statImgs * statNz * sizeof(float);
     r.check(cudaMemsetAsync(ssum, 0, 2 * bytes, r.rc.stream), what);   // sums and squares in one memset
@@ -704,13 +742,13 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   // downSample1 / downSample2: 5x5 stride 2 conv || gates, IN, gated GLU         model.py:245-246
   run_conv_in(r, parity_op(s.A0.hi, s.A0.lo, B, 80, T, 128), W.fwd(cv[G_DS1]), taps_s2_fwd(5, 2), B, 40,
               d.W1, plain_out(s.z1, 40, d.W1, 512), W.bias(cv[G_DS1]), "G ds1 conv", ssum, ssq, B, 512, 1,
-              40 * d.W1, s.st1, s.z1);
+              40 * d.W1, s.st1, s.z1, (long long)B * 40 * d.W1 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z1, 512, 40, d.W1, s.st1, 512, W.gamma(nm[GN_DS1]),
                                               W.beta(nm[GN_DS1]), 1, nullptr,
                                               abuf(s.A1, nullptr, B, 40, d.W1, 256, 1)), st), "G ds1 glu");
   run_conv_in(r, parity_op(s.A1.hi, s.A1.lo, B, 40, d.W1, 256), W.fwd(cv[G_DS2]), taps_s2_fwd(5, 2), B,
               20, d.W2, plain_out(s.z2, 20, d.W2, 512), W.bias(cv[G_DS2]), "G ds2 conv", ssum, ssq, B, 512, 1,
-              20 * d.W2, s.st2, s.z2);
+              20 * d.W2, s.st2, s.z2, (long long)B * 20 * d.W2 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[GN_DS2]),
                                               W.beta(nm[GN_DS2]), 1, nullptr,
                                               abuf(s.A2, nullptr, B, 20, d.W2, 256, 0)), st), "G ds2 glu");
@@ -754,13 +792,13 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   const TapList k55 = taps_s1(5, 5, 2, 2, 1);
   run_conv_in(r, plain_op(s.U0.hi, s.U0.lo, B, 20, d.W2, 256), W.fwd(cv[G_UP1]), k55, B, 20, d.W2,
               plain_out(s.z7, 20, d.W2, 1024), W.bias(cv[G_UP1]), "G up1 conv", ssum, ssq, B, 1024, 4,
-              20 * d.W2, s.st7, s.z7);
+              20 * d.W2, s.st7, s.z7, (long long)B * 20 * d.W2 * 1024);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z7, 1024, 20, d.W2, s.st7, 256, W.gamma(nm[GN_UP1]),
                                               W.beta(nm[GN_UP1]), 1, nullptr,
                                               abuf(s.U1, nullptr, B, 40, d.X1, 256, 0)), st), "G up1 act");
   run_conv_in(r, plain_op(s.U1.hi, s.U1.lo, B, 40, d.X1, 256), W.fwd(cv[G_UP2]), k55, B, 40, d.X1,
               plain_out(s.z8, 40, d.X1, 512), W.bias(cv[G_UP2]), "G up2 conv", ssum, ssq, B, 512, 4,
-              40 * d.X1, s.st8, s.z8);
+              40 * d.X1, s.st8, s.z8, (long long)B * 40 * d.X1 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z8, 512, 40, d.X1, s.st8, 128, W.gamma(nm[GN_UP2]),
                                               W.beta(nm[GN_UP2]), 1, nullptr,
                                               abuf(s.U2, nullptr, B, 80, d.X2, 128, 0)), st), "G up2 act");
@@ -830,7 +868,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   r.check(launch_head_g_bwd(dout, B, 80, d.X2, dP.hi, dP.lo, gB(G_HEAD), st), "G head bwd");
   float* dU2 = a.takeT<float>(M8 * 128);
   run_conv(r, plain_op(dP.hi, dP.lo, B, 80, d.X2, 128), W.bwd(cv[G_HEAD]), one, B, 80, d.X2,
-           plain_out(dU2, 80, d.X2, 128), nullptr, nullptr, "G head dgrad", 75.0 / 128.0);
+           plain_out(dU2, 80, d.X2, 128), nullptr, nullptr, "G head dgrad", 75.0 / 128.0, nullptr, nullptr, M8 * 128);
   if (needWgrad)
     run_wgrad(r, plain_op(dP.hi, dP.lo, B, 80, d.X2, 128), plain_op(s.U2.hi, s.U2.lo, B, 80, d.X2, 128),
               one, nullptr, B, 80, d.X2, gW(G_HEAD), "G head wgrad", 75.0 / 128.0);
@@ -842,7 +880,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
           "G up2 bwd");
   float* dU1 = a.takeT<float>(M7 * 256);
   run_conv(r, plain_op(dz8.hi, dz8.lo, B, 40, d.X1, 512), W.bwd(cv[G_UP2]), k55b, B, 40, d.X1,
-           plain_out(dU1, 40, d.X1, 256), nullptr, nullptr, "G up2 dgrad");
+           plain_out(dU1, 40, d.X1, 256), nullptr, nullptr, "G up2 dgrad", 1.0, nullptr, nullptr, M7 * 256);
   if (needWgrad)
     run_wgrad(r, plain_op(dz8.hi, dz8.lo, B, 40, d.X1, 512), plain_op(s.U1.hi, s.U1.lo, B, 40, d.X1, 256),
               k55f, nullptr, B, 40, d.X1, gW(G_UP2), "G up2 wgrad");
@@ -853,7 +891,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
           "G up1 bwd");
   float* dU0 = a.takeT<float>(M2 * 256);
   run_conv(r, plain_op(dz7.hi, dz7.lo, B, 20, d.W2, 1024), W.bwd(cv[G_UP1]), k55b, B, 20, d.W2,
-           plain_out(dU0, 20, d.W2, 256), nullptr, nullptr, "G up1 dgrad");
+           plain_out(dU0, 20, d.W2, 256), nullptr, nullptr, "G up1 dgrad", 1.0, nullptr, nullptr, M2 * 256);
   if (needWgrad)
     run_wgrad(r, plain_op(dz7.hi, dz7.lo, B, 20, d.W2, 1024), plain_op(s.U0.hi, s.U0.lo, B, 20, d.W2, 256),
               k55f, nullptr, B, 20, d.W2, gW(G_UP1), "G up1 wgrad");
@@ -1046,17 +1084,17 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
   const TapList k33 = taps_s2_fwd(3, 1);
   run_conv_in(r, parity_op(s.D0.hi, s.D0.lo, B, 80, T, 128), W.fwd(cv[D_DS1]), k33, B, 40, d.W1,
               plain_out(s.z1, 40, d.W1, 256), W.bias(cv[D_DS1]), "D ds1 conv", ssum, ssq, B, 256, 1, 40 * d.W1,
-              s.st1, s.z1);
+              s.st1, s.z1, (long long)B * 40 * d.W1 * 256);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z1, 256, 40, d.W1, s.st1, 256, W.gamma(nm[DN_DS1]),
                                               W.beta(nm[DN_DS1]), 1, nullptr, abuf(s.D1, nullptr, B, 40, d.W1, 256, 1)), st), "D ds1 act");
   run_conv_in(r, parity_op(s.D1.hi, s.D1.lo, B, 40, d.W1, 256), W.fwd(cv[D_DS2]), k33, B, 20, d.W2,
               plain_out(s.z2, 20, d.W2, 512), W.bias(cv[D_DS2]), "D ds2 conv", ssum, ssq, B, 512, 1, 20 * d.W2,
-              s.st2, s.z2);
+              s.st2, s.z2, (long long)B * 20 * d.W2 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[DN_DS2]),
                                               W.beta(nm[DN_DS2]), 1, nullptr, abuf(s.D2, nullptr, B, 20, d.W2, 512, 1)), st), "D ds2 act");
   run_conv_in(r, parity_op(s.D2.hi, s.D2.lo, B, 20, d.W2, 512), W.fwd(cv[D_DS3]), k33, B, 10, d.W3,
               plain_out(s.z3, 10, d.W3, 1024), W.bias(cv[D_DS3]), "D ds3 conv", ssum, ssq, B, 1024, 1, 10 * d.W3,
-              s.st3, s.z3);
+              s.st3, s.z3, (long long)B * 10 * d.W3 * 1024);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z3, 1024, 10, d.W3, s.st3, 1024, W.gamma(nm[DN_DS3]),
                                               W.beta(nm[DN_DS3]), 1, nullptr, abuf(s.D3, nullptr, B, 10, d.W3, 1024, 0)), st), "D ds3 act");
   // outputConvLayer 1x3 1024->1 + sigmoid                                          model.py:323-327,348
@@ -1115,7 +1153,7 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
   r.check(launch_head_d_bwd(dout, out, B, 10, d.W3, dP.hi, dP.lo, gB(D_HEAD), st), "D head bwd");
   float* dD3 = a.takeT<float>(M3 * 1024);
   run_conv(r, plain_op(dP.hi, dP.lo, B, 10, d.W3, 128), W.bwd(cv[D_HEAD]), one, B, 10, d.W3,
-           plain_out(dD3, 10, d.W3, 1024), nullptr, nullptr, "D head dgrad", 3.0 / 128.0);
+           plain_out(dD3, 10, d.W3, 1024), nullptr, nullptr, "D head dgrad", 3.0 / 128.0, nullptr, nullptr, M3 * 1024);
   if (needWgrad)
     run_wgrad(r, plain_op(dP.hi, dP.lo, B, 10, d.W3, 128), plain_op(s.D3.hi, s.D3.lo, B, 10, d.W3, 1024), one,
               nullptr, B, 10, d.W3, gW(D_HEAD), "D head wgrad", 3.0 / 128.0);

@@ -51,12 +51,15 @@ def ref_conv(A, W, taps, oB, oY, oX):
 
 
 def run_conv(lib, Ah, Al, Wh, Wl, taps, oB, oY, oX, nPass, backend, blockN, bias=None,
-             addsrc=None, nSplit=None, out_shape=None, strides=None):
+             addsrc=None, nSplit=None, out_shape=None, strides=None, ksplit=1):
     B, P, Y, X, C = Ah.shape
     T, N, K = Wh.shape
+    lib.mcgvc_debug_set_conv_ksplit(ksplit)
     if nSplit is None:
         nSplit = N
-        out = torch.full((oB, oY, oX, N), float("nan"), device="cuda")
+        # split-K slices are ADDED into a zero-filled output (SIMT checker: plain store)
+        fill = 0.0 if (ksplit > 1 and backend != 1) else float("nan")
+        out = torch.full((oB, oY, oX, N), fill, device="cuda")
         sB, sY, sX, sNhi = oY * oX * N, oX * N, N, 0
     else:
         out = torch.full(out_shape, float("nan"), device="cuda")
@@ -66,6 +69,7 @@ def run_conv(lib, Ah, Al, Wh, Wl, taps, oB, oY, oX, nPass, backend, blockN, bias
                               ctypes.c_longlong(sB), ctypes.c_longlong(sY), ctypes.c_longlong(sX),
                               nSplit, ctypes.c_longlong(sNhi), ptr(bias), ptr(addsrc), nPass,
                               backend, blockN, ctypes.c_void_p(0))
+    lib.mcgvc_debug_set_conv_ksplit(1)
     if rc != 0:
         raise RuntimeError("mcgvc_debug_conv: " + lib.mcgvc_last_error().decode())
     torch.cuda.synchronize()
@@ -77,7 +81,7 @@ def relerr(a, b):
 
 
 def conv_case(lib, name, B, P, Y, X, C, N, taps, oB, oY, oX, nPass, blockN, with_bias=True,
-              with_add=False, seed=0):
+              with_add=False, seed=0, ksplit=1):
     g = torch.Generator(device="cuda").manual_seed(seed)
     A = torch.randn(B, P, Y, X, C, device="cuda", generator=g)
     T = max(t[3] for t in taps) + 1
@@ -101,11 +105,13 @@ def conv_case(lib, name, B, P, Y, X, C, N, taps, oB, oY, oX, nPass, blockN, with
     if N % 128 == 0:
         backends.append((2, "tc2"))   # CTA-pair kernel (cta_group::2)
     for backend, bname in backends:
-        out = run_conv(lib, Ah, Al, Wh, Wl, taps, oB, oY, oX, nPass, backend, blockN, bias, addsrc)
+        out = run_conv(lib, Ah, Al, Wh, Wl, taps, oB, oY, oX, nPass, backend, blockN, bias, addsrc, ksplit=ksplit)
         nan = torch.isnan(out).sum().item()
         res[bname] = (relerr(torch.nan_to_num(out), ref), nan)
     ok = all(e < 2e-5 and n == 0 for e, n in res.values())
     tc2 = f"| tc2 err={res['tc2'][0]:.2e} nan={res['tc2'][1]} " if "tc2" in res else ""
+    if ksplit > 1:
+        name = f"{name} kSplit={ksplit}"
     print(f"[conv ] {name:34s} nPass={nPass} blockN={blockN:3d} simt err={res['simt'][0]:.2e} nan={res['simt'][1]} "
           f"| tc err={res['tc'][0]:.2e} nan={res['tc'][1]} {tc2}{'OK' if ok else 'FAIL'}", flush=True)
     return ok
@@ -199,6 +205,12 @@ def all_cases(lib):
     ok &= conv_case(lib, "2dto1d 20 taps oY=1", 4, 1, 20, 16, 256, 256, [(0, h, 0, h) for h in range(20)], 4, 1, 16, 3, 128)
     # --- conv: 1D k=3
     ok &= conv_case(lib, "1D k3 B8 L16 C256 N1024", 8, 1, 1, 16, 256, 1024, [(-1, 0, 0, 0), (0, 0, 0, 1), (1, 0, 0, 2)], 8, 1, 16, 3, 128)
+    # --- conv: split-K work items (K slices added into a zero-filled output with red.global.add)
+    ok &= conv_case(lib, "5x5 s1 B2 Y20 X16 C128 N256", 2, 1, 20, 16, 128, 256, taps_5x5_s1(), 2, 20, 16, 3, 128, with_add=True, ksplit=3)
+    ok &= conv_case(lib, "5x5 s1 B2 Y20 X16 C128 N256", 2, 1, 20, 16, 128, 256, taps_5x5_s1(), 2, 20, 16, 3, 256, ksplit=7)
+    ok &= conv_case(lib, "5x5 s1 bf16 odd B3 Y5 X17 C64", 3, 1, 5, 17, 64, 128, taps_5x5_s1(), 3, 5, 17, 1, 128, ksplit=5)
+    ok &= conv_case(lib, "3x3 s2 parity C256 (4 kblocks/tap)", 2, 4, 10, 9, 256, 128, taps_kxk_s2(3, 1), 2, 10, 9, 3, 64, ksplit=8)
+    ok &= conv_case(lib, "1D k3 B8 L16 C256 N1024", 8, 1, 1, 16, 256, 1024, [(-1, 0, 0, 0), (0, 0, 0, 1), (1, 0, 0, 2)], 8, 1, 16, 3, 128, ksplit=2)
     # --- wgrad
     for nPass in (1, 3):
         for ct in (64, 128, 256):

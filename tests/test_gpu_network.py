@@ -257,6 +257,35 @@ def test_simt_backend_agrees_with_tcgen05(env):
     assert rel(y_tc, y_simt) < 1e-4
 
 
+def test_split_k_layers_agree_with_simt_backend_at_batch16(env):
+    """At batch 16 the up-block data gradients (80 CTA-pair tiles / 160 single-CTA tiles) and the
+    Discriminator's ds2/ds3 convolutions take the split-K path (K slices added with red.global.add,
+    stand-alone statistics).  The SIMT checking backend never splits: outputs, input gradients and the
+    packed parameter gradients of a G -> D adversarial pass must agree."""
+    e = env["pkg"].engine
+    G, D = env["G"], env["D"]
+    x, m, _, _ = O.synthetic_batch(16, 64, seed=77)
+    res = {}
+    for name, backend in (("tc", e.BACKEND_TCGEN05), ("simt", e.BACKEND_SIMT)):
+        e.set_backend(backend)
+        try:
+            G.zero_grad(set_to_none=True)
+            D.zero_grad(set_to_none=True)
+            xin = x.cuda().requires_grad_(True)
+            y = G(xin, m.cuda())
+            d = D(y)
+            ((1 - d) ** 2).mean().backward()
+            torch.cuda.synchronize()
+            res[name] = (y.detach().clone(), d.detach().clone(), xin.grad.clone(),
+                         G._flat_grad.clone(), D._flat_grad.clone())
+        finally:
+            e.set_backend(e.BACKEND_TCGEN05)
+    G.zero_grad(set_to_none=True)
+    D.zero_grad(set_to_none=True)
+    for got, want, key in zip(res["tc"], res["simt"], ("G.out", "D.out", "dx", "G.grads", "D.grads")):
+        assert rel(got, want) < 2e-4, key
+
+
 def test_fast_precision_mode_is_labelled_and_bounded(env):
     """bf16 single pass: faster, ~1e-2 relative error -- NOT within the 1e-3 gate."""
     e = env["pkg"].engine
