@@ -64,6 +64,7 @@ struct ConvGeom {
   // separate work items and are ADDED into `out` (red.global.add) -- the caller zero-fills `out`
   // first; incompatible with the fused statistics.  0 / 1 = off.  See conv_plan_ksplit().
   int kSplit;
+  int timingProbe;      // set from MCGVC_F8_TIMING_PROBE by the CTA-pair launcher (measurement hack, see there)
 };
 
 // Weight-gradient GEMM:  dW[w_t][n][c] += sum over positions (b,y,x) in this CTA's K-slice of

@@ -223,6 +223,19 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, 8-bit float operands (kind::f8f6f4, K = 32 per instruction, twice the bf16 MAC rate).
+__device__ __forceinline__ void umma_f8_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at this smem offset in every CTA of `mask` once prior MMAs have completed
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
   asm volatile(
@@ -254,6 +267,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
                                                        uint32_t b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
          ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::f8f6f4 with e4m3 A/B (format code 0) and fp32 D, K-major operands.
+__host__ __device__ constexpr uint32_t umma_idesc_e4m3(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 }  // namespace ptx

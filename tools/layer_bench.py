@@ -86,6 +86,8 @@ if __name__ == "__main__":
     s2 = kc.taps_kxk_s2(5, 2)
     conv_layer("up2", 1, 40, 32, 256, 512, s1, 40, 32)
     conv_layer("up1", 1, 20, 16, 256, 1024, s1, 20, 16)
+    if len(sys.argv) > 2 and sys.argv[2] == "conv":
+        sys.exit(0)
     conv_layer("ds1", 4, 40, 32, 128, 512, s2, 40, 32)
     conv_layer("ds2", 4, 20, 16, 256, 512, s2, 20, 16)
     conv_layer("D.ds2", 4, 20, 16, 256, 512, kc.taps_kxk_s2(3, 1), 20, 16)
