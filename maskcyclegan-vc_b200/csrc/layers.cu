@@ -372,8 +372,10 @@ cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
   if (splits > 64) splits = 64;
   dim3 grid(cg, a.dA.nImg, splits);
   const size_t tbytes = (size_t)a.dA.nImg * a.Nstat * sizeof(float);
-  cudaError_t e;
-  if (a.t2 == a.t1 + (size_t)a.dA.nImg * a.Nstat) {
+  cudaError_t e = cudaSuccess;
+  if (a.prezeroed) {
+    // nothing to do
+  } else if (a.t2 == a.t1 + (size_t)a.dA.nImg * a.Nstat) {
     e = cudaMemsetAsync(a.t1, 0, 2 * tbytes, s);        // adjacent: one memset
   } else {
     e = cudaMemsetAsync(a.t1, 0, tbytes, s);

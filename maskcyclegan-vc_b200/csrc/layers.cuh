@@ -54,6 +54,7 @@ struct ApplyBwdArgs {
   ActBuf dA;            // gradient w.r.t. the layer's activation (fp32 in .f32, same layout as fwd out)
   float* t1;            // [nImg][Nstat] sum dy        (written by reduce, read by apply)
   float* t2;            // [nImg][Nstat] sum dy*xhat
+  int prezeroed;        // t1/t2 were zero-filled by the caller (one memset per backward call)
   float* dgamma;        // engine order, accumulated (+=) over images
   float* dbeta;
   __nv_bfloat16* dz_hi; // [rows][Nz]

@@ -251,6 +251,21 @@ struct Arena {
   }
 };
 
+// Conv-epilogue statistics accumulators: every normalised layer of a forward call gets its own
+// slice (sums, then sums of squares) of one pool that is zero-filled with a single memset.
+struct StatPool {
+  float* base;
+  long long off = 0;
+  explicit StatPool(float* b) : base(b) {}
+  float* take(long long imgs, long long nz) {
+    float* p = base + off;
+    off += 2 * imgs * nz;
+    return p;
+  }
+};
+long long gen_stat_pool_floats(int B) { return 2LL * B * (512 + 512 + 256 + 6 * (1024 + 256) + 5120 + 1024 + 512); }
+long long dis_stat_pool_floats(int B) { return 2LL * B * (256 + 512 + 1024); }
+
 struct Weights {   // views into the packed blob
   const __nv_bfloat16* bf;
   const float* f32;
@@ -522,8 +537,7 @@ void run_conv_in(Run& r, const ActOperand& a, const WgtOperand& w, const TapList
     return;
   }
   if (fused) {
-    const size_t bytes = (size_t)statImgs * statNz * sizeof(float);
-    r.check(cudaMemsetAsync(ssum, 0, 2 * bytes, r.rc.stream), what);   // sums and squares in one memset
+    // ssum / ssq: this layer's own slice of the accumulator pool the caller zero-filled up front
     run_conv(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0, ssum, ssq);
     if (r.ok) r.check(launch_stats_finalize(ssum, ssq, statImgs, statNz, groups, planePositions, st.mean, st.rstd, r.rc.stream), what);
   } else {
@@ -543,14 +557,15 @@ ApplyArgs mk_apply(int mode, const float* z, int Nz, int zY, int zX, const Stat&
   return a;
 }
 ApplyBwdArgs mk_bwd(int mode, const float* z, int Nz, int zY, int zX, const Stat& st, int Nstat,
-                    const float* gamma, const float* beta, int affPeriod, ActBuf dA, float* t1,
-                    float* t2, float* dgamma, float* dbeta, BfPair dz, float* dbias) {
+                    const float* gamma, const float* beta, int affPeriod, ActBuf dA, StatPool& tp,
+                    float* dgamma, float* dbeta, BfPair dz, float* dbias) {
   ApplyBwdArgs a{};
   a.mode = mode; a.z = z; a.Nz = Nz; a.zY = zY; a.zX = zX;
   a.mean = st.mean; a.rstd = st.rstd; a.Nstat = Nstat;
   a.gamma = gamma; a.beta = beta; a.affPeriod = affPeriod;
-  (void)t2;
-  a.dA = dA; a.t1 = t1; a.t2 = t1 + (size_t)dA.nImg * Nstat;   // adjacent: zeroed with one memset
+  // this layer's slice of the reduction pool (sum dy, then sum dy*xhat), zero-filled once per call
+  a.dA = dA; a.t1 = tp.take(dA.nImg, Nstat); a.t2 = a.t1 + (size_t)dA.nImg * Nstat;
+  a.prezeroed = 1;
   a.dgamma = dgamma; a.dbeta = dbeta;
   a.dz_hi = dz.hi; a.dz_lo = dz.lo; a.dbias = dbias;
   return a;
@@ -705,7 +720,7 @@ std::vector<SavedEntry> generator_saved_layout(int B, int T) {
 }
 long long generator_fwd_ws_bytes(int B, int T) {
   GenDims d(B, T);
-  return align_up((long long)B * 80 * d.X2 * 128 * 4, 256) + 2 * align_up((long long)B * 5120 * 4, 256) + 1024;
+  return align_up((long long)B * 80 * d.X2 * 128 * 4, 256) + align_up(gen_stat_pool_floats(B) * 4, 256) + 1024;
 }
 
 int generator_forward(const void* packed, const float* x, const float* mask, int B, int T,
@@ -719,7 +734,8 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   const auto& cv = md.convs;
   const auto& nm = md.norms;
   Arena wa(ws);
-  float* ssum = wa.takeT<float>((long long)2 * B * 5120);   // conv-epilogue statistics: sums, then sums of squares
+  StatPool sp(wa.takeT<float>(gen_stat_pool_floats(B)));   // conv-epilogue statistics, one memset for all layers
+  r.check(cudaMemsetAsync(sp.base, 0, (size_t)gen_stat_pool_floats(B) * sizeof(float), st), "G zero stats");
   float* ssq = nullptr;
 
   // parity-split buffers have a padding column/row when the extent is odd: keep it zero
@@ -741,20 +757,20 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
                                               abuf(s.A0, nullptr, B, 80, T, 128, 1)), st), "G stem glu");
   // downSample1 / downSample2: 5x5 stride 2 conv || gates, IN, gated GLU         model.py:245-246
   run_conv_in(r, parity_op(s.A0.hi, s.A0.lo, B, 80, T, 128), W.fwd(cv[G_DS1]), taps_s2_fwd(5, 2), B, 40,
-              d.W1, plain_out(s.z1, 40, d.W1, 512), W.bias(cv[G_DS1]), "G ds1 conv", ssum, ssq, B, 512, 1,
+              d.W1, plain_out(s.z1, 40, d.W1, 512), W.bias(cv[G_DS1]), "G ds1 conv", sp.take(B, 512), ssq, B, 512, 1,
               40 * d.W1, s.st1, s.z1, (long long)B * 40 * d.W1 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z1, 512, 40, d.W1, s.st1, 512, W.gamma(nm[GN_DS1]),
                                               W.beta(nm[GN_DS1]), 1, nullptr,
                                               abuf(s.A1, nullptr, B, 40, d.W1, 256, 1)), st), "G ds1 glu");
   run_conv_in(r, parity_op(s.A1.hi, s.A1.lo, B, 40, d.W1, 256), W.fwd(cv[G_DS2]), taps_s2_fwd(5, 2), B,
-              20, d.W2, plain_out(s.z2, 20, d.W2, 512), W.bias(cv[G_DS2]), "G ds2 conv", ssum, ssq, B, 512, 1,
+              20, d.W2, plain_out(s.z2, 20, d.W2, 512), W.bias(cv[G_DS2]), "G ds2 conv", sp.take(B, 512), ssq, B, 512, 1,
               20 * d.W2, s.st2, s.z2, (long long)B * 20 * d.W2 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[GN_DS2]),
                                               W.beta(nm[GN_DS2]), 1, nullptr,
                                               abuf(s.A2, nullptr, B, 20, d.W2, 256, 0)), st), "G ds2 glu");
   // 2D -> 1D: view (c*20+h), Conv1d k1 5120->256, IN1d                           model.py:249-255
   run_conv_in(r, plain_op(s.A2.hi, s.A2.lo, B, 20, d.W2, 256), W.fwd(cv[G_2DTO1D]), taps_rows(20, 1), B,
-              1, d.W2, plain_out(s.z3, 1, d.W2, 256), W.bias(cv[G_2DTO1D]), "G 2dto1d conv", ssum, ssq, B, 256,
+              1, d.W2, plain_out(s.z3, 1, d.W2, 256), W.bias(cv[G_2DTO1D]), "G 2dto1d conv", sp.take(B, 256), ssq, B, 256,
               1, d.W2, s.st3, s.z3);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z3, 256, 1, d.W2, s.st3, 256, W.gamma(nm[GN_2DTO1D]),
                                               W.beta(nm[GN_2DTO1D]), 1, nullptr,
@@ -767,13 +783,13 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
     const NormDesc& na = nm[GN_RES0 + 2 * i];
     const NormDesc& nb = nm[GN_RES0 + 2 * i + 1];
     run_conv_in(r, plain_op(s.R[i].hi, s.R[i].lo, B, 1, d.W2, 256), W.fwd(ca), k3, B, 1, d.W2,
-                plain_out(s.z4[i], 1, d.W2, 1024), W.bias(ca), "G res conv a", ssum, ssq, B, 1024, 1, d.W2,
+                plain_out(s.z4[i], 1, d.W2, 1024), W.bias(ca), "G res conv a", sp.take(B, 1024), ssq, B, 1024, 1, d.W2,
                 s.st4[i], s.z4[i]);
     if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z4[i], 1024, 1, d.W2, s.st4[i], 1024, W.gamma(na),
                                                 W.beta(na), 1, nullptr,
                                                 abuf(s.H[i], nullptr, B, 1, d.W2, 512, 0)), st), "G res glu");
     run_conv_in(r, plain_op(s.H[i].hi, s.H[i].lo, B, 1, d.W2, 512), W.fwd(cb), k3, B, 1, d.W2,
-                plain_out(s.z5[i], 1, d.W2, 256), W.bias(cb), "G res conv b", ssum, ssq, B, 256, 1, d.W2,
+                plain_out(s.z5[i], 1, d.W2, 256), W.bias(cb), "G res conv b", sp.take(B, 256), ssq, B, 256, 1, d.W2,
                 s.st5[i], s.z5[i]);
     if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z5[i], 256, 1, d.W2, s.st5[i], 256, W.gamma(nb),
                                                 W.beta(nb), 1, s.Rf[i],
@@ -783,7 +799,7 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   {
     OutAddr o{s.z6, (long long)20 * d.W2 * 256, 0, 256, 256, (long long)d.W2 * 256};
     run_conv_in(r, plain_op(s.R[6].hi, s.R[6].lo, B, 1, d.W2, 256), W.fwd(cv[G_1DTO2D]), taps_one(), B, 1,
-                d.W2, o, W.bias(cv[G_1DTO2D]), "G 1dto2d conv", ssum, ssq, B * 20, 256, 1, d.W2, s.st6, s.z6);
+                d.W2, o, W.bias(cv[G_1DTO2D]), "G 1dto2d conv", sp.take(B * 20, 256), ssq, B * 20, 256, 1, d.W2, s.st6, s.z6);
   }
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z6, 256, 1, d.W2, s.st6, 256, W.gamma(nm[GN_1DTO2D]),
                                               W.beta(nm[GN_1DTO2D]), 20, nullptr,
@@ -791,13 +807,13 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   // upSample1 / upSample2: 5x5 conv, PixelShuffle(2), IN, swish                  model.py:274-275
   const TapList k55 = taps_s1(5, 5, 2, 2, 1);
   run_conv_in(r, plain_op(s.U0.hi, s.U0.lo, B, 20, d.W2, 256), W.fwd(cv[G_UP1]), k55, B, 20, d.W2,
-              plain_out(s.z7, 20, d.W2, 1024), W.bias(cv[G_UP1]), "G up1 conv", ssum, ssq, B, 1024, 4,
+              plain_out(s.z7, 20, d.W2, 1024), W.bias(cv[G_UP1]), "G up1 conv", sp.take(B, 1024), ssq, B, 1024, 4,
               20 * d.W2, s.st7, s.z7, (long long)B * 20 * d.W2 * 1024);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z7, 1024, 20, d.W2, s.st7, 256, W.gamma(nm[GN_UP1]),
                                               W.beta(nm[GN_UP1]), 1, nullptr,
                                               abuf(s.U1, nullptr, B, 40, d.X1, 256, 0)), st), "G up1 act");
   run_conv_in(r, plain_op(s.U1.hi, s.U1.lo, B, 40, d.X1, 256), W.fwd(cv[G_UP2]), k55, B, 40, d.X1,
-              plain_out(s.z8, 40, d.X1, 512), W.bias(cv[G_UP2]), "G up2 conv", ssum, ssq, B, 512, 4,
+              plain_out(s.z8, 40, d.X1, 512), W.bias(cv[G_UP2]), "G up2 conv", sp.take(B, 512), ssq, B, 512, 4,
               40 * d.X1, s.st8, s.z8, (long long)B * 40 * d.X1 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z8, 512, 40, d.X1, s.st8, 128, W.gamma(nm[GN_UP2]),
                                               W.beta(nm[GN_UP2]), 1, nullptr,
@@ -834,7 +850,7 @@ long long generator_bwd_ws_bytes(int B, int T) {
   add(parity_elems(B, 80, d.T, 128) * 4);        // dA0
   add(M0 * 256 * 2); add(M0 * 256 * 2);          // dz0
   add(M0 * 64 * 4);                              // dX15
-  add((long long)B * 20 * 1024 * 4); add((long long)B * 20 * 1024 * 4);  // t1, t2
+  add(gen_stat_pool_floats(B) * 4);              // t1 / t2 reduction pool
   add(2 * 5120 * 4);                             // affine-grad sink
   return align_up(b, 256) + 4096;
 }
@@ -854,8 +870,8 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   const long long M0 = (long long)B * 80 * d.T, M2 = (long long)B * 20 * d.W2, L = (long long)B * d.W2,
                   M7 = (long long)B * 40 * d.X1, M8 = (long long)B * 80 * d.X2;
   const long long M1 = (long long)B * 40 * d.W1;
-  float* t1 = a.takeT<float>((long long)B * 20 * 1024);
-  float* t2 = a.takeT<float>((long long)B * 20 * 1024);
+  StatPool tp(a.takeT<float>(gen_stat_pool_floats(B)));   // IN-backward reductions, one memset for all layers
+  r.check(cudaMemsetAsync(tp.base, 0, (size_t)gen_stat_pool_floats(B) * sizeof(float), st), "G zero bwd sums");
   float* junk = a.takeT<float>(2 * 5120);  // sink for affine grads when the caller wants none
   auto gW = [&](int ci) { return gblob + cv[ci].gW; };
   auto gB = [&](int ci) -> float* { return needWgrad ? gblob + cv[ci].gB : nullptr; };
@@ -876,7 +892,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   const TapList k55f = taps_s1(5, 5, 2, 2, 1), k55b = taps_s1(5, 5, 2, 2, -1);
   BfPair dz8 = take_pair(a, M7 * 512, nullptr);
   run_bwd(r, mk_bwd(kINSwishShuffle, s.z8, 512, 40, d.X1, s.st8, 128, W.gamma(nm[GN_UP2]), W.beta(nm[GN_UP2]),
-                    1, gbuf(dU2, B, 80, d.X2, 128, 0), t1, t2, gGa(GN_UP2), gBe(GN_UP2), dz8, gB(G_UP2)),
+                    1, gbuf(dU2, B, 80, d.X2, 128, 0), tp, gGa(GN_UP2), gBe(GN_UP2), dz8, gB(G_UP2)),
           "G up2 bwd");
   float* dU1 = a.takeT<float>(M7 * 256);
   run_conv(r, plain_op(dz8.hi, dz8.lo, B, 40, d.X1, 512), W.bwd(cv[G_UP2]), k55b, B, 40, d.X1,
@@ -887,7 +903,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   // ---- upSample1
   BfPair dz7 = take_pair(a, M2 * 1024, nullptr);
   run_bwd(r, mk_bwd(kINSwishShuffle, s.z7, 1024, 20, d.W2, s.st7, 256, W.gamma(nm[GN_UP1]), W.beta(nm[GN_UP1]),
-                    1, gbuf(dU1, B, 40, d.X1, 256, 0), t1, t2, gGa(GN_UP1), gBe(GN_UP1), dz7, gB(G_UP1)),
+                    1, gbuf(dU1, B, 40, d.X1, 256, 0), tp, gGa(GN_UP1), gBe(GN_UP1), dz7, gB(G_UP1)),
           "G up1 bwd");
   float* dU0 = a.takeT<float>(M2 * 256);
   run_conv(r, plain_op(dz7.hi, dz7.lo, B, 20, d.W2, 1024), W.bwd(cv[G_UP1]), k55b, B, 20, d.W2,
@@ -898,7 +914,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   // ---- 1D -> 2D
   BfPair dz6 = take_pair(a, M2 * 256, nullptr);
   run_bwd(r, mk_bwd(kINOnly, s.z6, 256, 1, d.W2, s.st6, 256, W.gamma(nm[GN_1DTO2D]), W.beta(nm[GN_1DTO2D]), 20,
-                    gbuf(dU0, B * 20, 1, d.W2, 256, 0), t1, t2, gGa(GN_1DTO2D), gBe(GN_1DTO2D), dz6, nullptr),
+                    gbuf(dU0, B * 20, 1, d.W2, 256, 0), tp, gGa(GN_1DTO2D), gBe(GN_1DTO2D), dz6, nullptr),
           "G 1dto2d bwd");
   float* dR[7];
   for (int i = 0; i < 7; ++i) dR[i] = a.takeT<float>(L * 256);
@@ -928,14 +944,14 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
     const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
     const int na = GN_RES0 + 2 * i, nb = GN_RES0 + 2 * i + 1;
     run_bwd(r, mk_bwd(kINOnly, s.z5[i], 256, 1, d.W2, s.st5[i], 256, W.gamma(nm[nb]), W.beta(nm[nb]), 1,
-                      gbuf(dR[i + 1], B, 1, d.W2, 256, 0), t1, t2, gGa(nb), gBe(nb), dz5, nullptr), "G res bwd b");
+                      gbuf(dR[i + 1], B, 1, d.W2, 256, 0), tp, gGa(nb), gBe(nb), dz5, nullptr), "G res bwd b");
     run_conv(r, plain_op(dz5.hi, dz5.lo, B, 1, d.W2, 256), W.bwd(cb), k3b, B, 1, d.W2,
              plain_out(dH, 1, d.W2, 512), nullptr, nullptr, "G res dgrad b");
     if (needWgrad)
       run_wgrad(r, plain_op(dz5.hi, dz5.lo, B, 1, d.W2, 256), plain_op(s.H[i].hi, s.H[i].lo, B, 1, d.W2, 512),
                 k3f, nullptr, B, 1, d.W2, gblob + cb.gW, "G res wgrad b");
     run_bwd(r, mk_bwd(kGatedIN, s.z4[i], 1024, 1, d.W2, s.st4[i], 1024, W.gamma(nm[na]), W.beta(nm[na]), 1,
-                      gbuf(dH, B, 1, d.W2, 512, 0), t1, t2, gGa(na), gBe(na), dz4, nullptr), "G res bwd a");
+                      gbuf(dH, B, 1, d.W2, 512, 0), tp, gGa(na), gBe(na), dz4, nullptr), "G res bwd a");
     // dR[i] = dR[i+1] (skip connection) + dgrad
     run_conv(r, plain_op(dz4.hi, dz4.lo, B, 1, d.W2, 1024), W.bwd(ca), k3b, B, 1, d.W2,
              plain_out(dR[i], 1, d.W2, 256), nullptr, dR[i + 1], "G res dgrad a");
@@ -946,7 +962,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   // ---- 2D -> 1D
   BfPair dz3 = take_pair(a, L * 256, nullptr);
   run_bwd(r, mk_bwd(kINOnly, s.z3, 256, 1, d.W2, s.st3, 256, W.gamma(nm[GN_2DTO1D]), W.beta(nm[GN_2DTO1D]), 1,
-                    gbuf(dR[0], B, 1, d.W2, 256, 0), t1, t2, gGa(GN_2DTO1D), gBe(GN_2DTO1D), dz3, nullptr),
+                    gbuf(dR[0], B, 1, d.W2, 256, 0), tp, gGa(GN_2DTO1D), gBe(GN_2DTO1D), dz3, nullptr),
           "G 2dto1d bwd");
   float* dA2 = a.takeT<float>(M2 * 256);
   {
@@ -963,7 +979,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   // ---- downSample2
   BfPair dz2 = take_pair(a, M2 * 512, nullptr);
   run_bwd(r, mk_bwd(kGatedIN, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[GN_DS2]), W.beta(nm[GN_DS2]), 1,
-                    gbuf(dA2, B, 20, d.W2, 256, 0), t1, t2, gGa(GN_DS2), gBe(GN_DS2), dz2, nullptr), "G ds2 bwd");
+                    gbuf(dA2, B, 20, d.W2, 256, 0), tp, gGa(GN_DS2), gBe(GN_DS2), dz2, nullptr), "G ds2 bwd");
   float* dA1 = a.takeT<float>(parity_elems(B, 40, d.W1, 256));
   run_dgrad_s2(r, plain_op(dz2.hi, dz2.lo, B, 20, d.W2, 512), W.bwd(cv[G_DS2]), 5, 2, B, 20, (d.W1 + 1) / 2, 256,
                dA1, "G ds2 dgrad");
@@ -973,7 +989,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   // ---- downSample1
   BfPair dz1 = take_pair(a, M1 * 512, nullptr);
   run_bwd(r, mk_bwd(kGatedIN, s.z1, 512, 40, d.W1, s.st1, 512, W.gamma(nm[GN_DS1]), W.beta(nm[GN_DS1]), 1,
-                    gbuf(dA1, B, 40, d.W1, 256, 1), t1, t2, gGa(GN_DS1), gBe(GN_DS1), dz1, nullptr), "G ds1 bwd");
+                    gbuf(dA1, B, 40, d.W1, 256, 1), tp, gGa(GN_DS1), gBe(GN_DS1), dz1, nullptr), "G ds1 bwd");
   float* dA0 = a.takeT<float>(parity_elems(B, 80, d.T, 128));
   run_dgrad_s2(r, plain_op(dz1.hi, dz1.lo, B, 40, d.W1, 512), W.bwd(cv[G_DS1]), 5, 2, B, 40, (d.T + 1) / 2, 128,
                dA0, "G ds1 dgrad");
@@ -983,7 +999,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   // ---- stem
   BfPair dz0 = take_pair(a, M0 * 256, nullptr);
   run_bwd(r, mk_bwd(kGatedNoNorm, s.z0, 256, 80, d.T, Stat{nullptr, nullptr}, 0, nullptr, nullptr, 1,
-                    gbuf(dA0, B, 80, d.T, 128, 1), t1, t2, nullptr, nullptr, dz0, gB(G_STEM)),
+                    gbuf(dA0, B, 80, d.T, 128, 1), tp, nullptr, nullptr, dz0, gB(G_STEM)),
           "G stem bwd");
   if (needWgrad)
     run_wgrad(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 256), plain_op(s.X15.hi, s.X15.lo, B, 80, d.T, 64),
@@ -1048,7 +1064,7 @@ std::vector<SavedEntry> discriminator_saved_layout(int B, int T) {
 }
 long long discriminator_fwd_ws_bytes(int B, int T) {
   DisDims d(B, T);
-  return align_up((long long)B * 10 * d.W3 * 128 * 4, 256) + 2 * align_up((long long)B * 1024 * 4, 256) + 1024;
+  return align_up((long long)B * 10 * d.W3 * 128 * 4, 256) + align_up(dis_stat_pool_floats(B) * 4, 256) + 1024;
 }
 
 int discriminator_forward(const void* packed, const float* x, int B, int T, float* out, void* saved,
@@ -1062,7 +1078,8 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
   const auto& cv = md.convs;
   const auto& nm = md.norms;
   Arena wa(ws);
-  float* ssum = wa.takeT<float>((long long)2 * B * 1024);
+  StatPool sp(wa.takeT<float>(dis_stat_pool_floats(B)));
+  r.check(cudaMemsetAsync(sp.base, 0, (size_t)dis_stat_pool_floats(B) * sizeof(float), st), "D zero stats");
   float* ssq = nullptr;
   if (d.T & 1) {
     r.check(launch_fill_zero(s.D0.hi, parity_elems(B, 80, d.T, 128) * 2, st), "zero D0");
@@ -1083,17 +1100,17 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
   // downSample1..3: 3x3 stride 2 conv + IN + swish                                 model.py:345-347
   const TapList k33 = taps_s2_fwd(3, 1);
   run_conv_in(r, parity_op(s.D0.hi, s.D0.lo, B, 80, T, 128), W.fwd(cv[D_DS1]), k33, B, 40, d.W1,
-              plain_out(s.z1, 40, d.W1, 256), W.bias(cv[D_DS1]), "D ds1 conv", ssum, ssq, B, 256, 1, 40 * d.W1,
+              plain_out(s.z1, 40, d.W1, 256), W.bias(cv[D_DS1]), "D ds1 conv", sp.take(B, 256), ssq, B, 256, 1, 40 * d.W1,
               s.st1, s.z1, (long long)B * 40 * d.W1 * 256);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z1, 256, 40, d.W1, s.st1, 256, W.gamma(nm[DN_DS1]),
                                               W.beta(nm[DN_DS1]), 1, nullptr, abuf(s.D1, nullptr, B, 40, d.W1, 256, 1)), st), "D ds1 act");
   run_conv_in(r, parity_op(s.D1.hi, s.D1.lo, B, 40, d.W1, 256), W.fwd(cv[D_DS2]), k33, B, 20, d.W2,
-              plain_out(s.z2, 20, d.W2, 512), W.bias(cv[D_DS2]), "D ds2 conv", ssum, ssq, B, 512, 1, 20 * d.W2,
+              plain_out(s.z2, 20, d.W2, 512), W.bias(cv[D_DS2]), "D ds2 conv", sp.take(B, 512), ssq, B, 512, 1, 20 * d.W2,
               s.st2, s.z2, (long long)B * 20 * d.W2 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[DN_DS2]),
                                               W.beta(nm[DN_DS2]), 1, nullptr, abuf(s.D2, nullptr, B, 20, d.W2, 512, 1)), st), "D ds2 act");
   run_conv_in(r, parity_op(s.D2.hi, s.D2.lo, B, 20, d.W2, 512), W.fwd(cv[D_DS3]), k33, B, 10, d.W3,
-              plain_out(s.z3, 10, d.W3, 1024), W.bias(cv[D_DS3]), "D ds3 conv", ssum, ssq, B, 1024, 1, 10 * d.W3,
+              plain_out(s.z3, 10, d.W3, 1024), W.bias(cv[D_DS3]), "D ds3 conv", sp.take(B, 1024), ssq, B, 1024, 1, 10 * d.W3,
               s.st3, s.z3, (long long)B * 10 * d.W3 * 1024);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z3, 1024, 10, d.W3, s.st3, 1024, W.gamma(nm[DN_DS3]),
                                               W.beta(nm[DN_DS3]), 1, nullptr, abuf(s.D3, nullptr, B, 10, d.W3, 1024, 0)), st), "D ds3 act");
@@ -1111,7 +1128,7 @@ long long discriminator_bwd_ws_bytes(int B, int T) {
                   M3 = (long long)B * 10 * d.W3;
   long long b = 0;
   auto add = [&](long long bytes) { b = align_up(b, 256) + bytes; };
-  add((long long)B * 1024 * 4); add((long long)B * 1024 * 4);  // t1, t2
+  add(dis_stat_pool_floats(B) * 4);                            // t1 / t2 reduction pool
   add(2 * 1024 * 4);                                           // affine-grad sink
   add(M3 * 128 * 2); add(M3 * 128 * 2);                        // dP
   add(M3 * 1024 * 4);                                          // dD3
@@ -1139,8 +1156,8 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
   Arena a(ws);
   const long long M0 = (long long)B * 80 * d.T, M1 = (long long)B * 40 * d.W1, M2 = (long long)B * 20 * d.W2,
                   M3 = (long long)B * 10 * d.W3;
-  float* t1 = a.takeT<float>((long long)B * 1024);
-  float* t2 = a.takeT<float>((long long)B * 1024);
+  StatPool tp(a.takeT<float>(dis_stat_pool_floats(B)));
+  r.check(cudaMemsetAsync(tp.base, 0, (size_t)dis_stat_pool_floats(B) * sizeof(float), st), "D zero bwd sums");
   float* junk = a.takeT<float>(2 * 1024);
   auto gW = [&](int ci) { return gblob + cv[ci].gW; };
   auto gB = [&](int ci) -> float* { return needWgrad ? gblob + cv[ci].gB : nullptr; };
@@ -1171,7 +1188,7 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
     const long long Mo = (long long)B * v.Yo * v.Xo;
     BfPair dz = take_pair(a, Mo * v.Nz, nullptr);
     run_bwd(r, mk_bwd(kINSwish, v.z, v.Nz, v.Yo, v.Xo, v.st, v.Nz, W.gamma(nm[v.ni]), W.beta(nm[v.ni]), 1,
-                      gbuf(dAct, B, v.Yo, v.Xo, v.Nz, dActParity), t1, t2, gGa(v.ni), gBe(v.ni), dz, nullptr),
+                      gbuf(dAct, B, v.Yo, v.Xo, v.Nz, dActParity), tp, gGa(v.ni), gBe(v.ni), dz, nullptr),
             "D ds bwd");
     float* dIn = a.takeT<float>(parity_elems(B, v.Yi, v.Xi, v.Cin));
     run_dgrad_s2(r, plain_op(dz.hi, dz.lo, B, v.Yo, v.Xo, v.Nz), W.bwd(cv[v.ci]), 3, 1, B, (v.Yi + 1) / 2,
