@@ -103,11 +103,28 @@ int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY,
 /* split-K factor used by the following mcgvc_debug_conv calls on the tensor-core backends: every tile's
  * k-blocks run as `k` work items that are added into `out` (which the caller zero-fills); 1 = off. */
 int mcgvc_debug_set_conv_ksplit(int k);
+/* Kernel-level entry of the "16-bit main pass + two e4m3 correction passes" convolution (conv_c8.cu;
+ * not on the network path yet): out = out_scale * (sum a16*w16 + corr_scale * sum (a8h*w8l + a8l*w8h))
+ * + bias + addsrc.  backend 1 = SIMT checker, 2 = tcgen05 CTA-pair kernel (blockN 128 / 256). */
+int mcgvc_debug_conv_c8(const void* a16, const void* a8h, const void* a8l, int aC, int aX, int aY, int aP,
+                        int aB, const void* w16, const void* w8h, const void* w8l, int wK, int wN, int wT,
+                        int oX, int oY, int oB, int nTaps, const int8_t* taps4, float* out,
+                        const float* bias, const float* addsrc, int main_bf16, float out_scale,
+                        float corr_scale, int backend, int blockN, void* stream);
 int mcgvc_debug_wgrad(const void* z_hi, const void* z_lo, int zC, int zX, int zY, int zB,
                       const void* x_hi, const void* x_lo, int xC, int xX, int xY, int xP, int xB,
                       int pX, int pY, int pB, int nTaps, const int8_t* taps4,
                       const int8_t* ztaps4, float* dw, int cTile, int splitK, int nPass,
                       int backend, void* stream);
+
+/* Weight-gradient GEMM in the same scheme (wgrad_c8.cu): dw += out_scale * (sum z16*x16 + corr_scale *
+ * sum (z8h*x8l + z8l*x8h)) over positions.  backend 1 = SIMT checker, 2 = tcgen05 CTA-pair kernel
+ * (zC multiple of 256, cTile 128 or 256). */
+int mcgvc_debug_wgrad_c8(const void* z16, const void* z8h, const void* z8l, int zC, int zX, int zY, int zB,
+                         const void* x16, const void* x8h, const void* x8l, int xC, int xX, int xY, int xP,
+                         int xB, int pX, int pY, int pB, int nTaps, const int8_t* taps4, const int8_t* ztaps4,
+                         float* dw, int cTile, int splitK, int main_bf16, float out_scale, float corr_scale,
+                         int backend, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,12 +22,17 @@ struct ActOperand {
   const void* hi;
   const void* lo;
   int C, X, Y, P, B;
+  // C8 scheme only (conv_c8.cu): e4m3 planes of hi * 2^u and (v - hi) * 2^(u+11), same indexing, 1 B/elem
+  const void* h8;
+  const void* l8;
 };
 // Weight operand: bf16 hi/lo, [T][N][K] (K contiguous, K = channels per tap).
 struct WgtOperand {
   const void* hi;
   const void* lo;
   int K, N, T;
+  const void* h8;   // C8 scheme only, see ActOperand
+  const void* l8;
 };
 
 // Implicit-GEMM convolution:  out[row(b,y,x), n] = bias[n] + addsrc[..] +
@@ -64,6 +69,9 @@ struct ConvGeom {
   // separate work items and are ADDED into `out` (red.global.add) -- the caller zero-fills `out`
   // first; incompatible with the fused statistics.  0 / 1 = off.  See conv_plan_ksplit().
   int kSplit;
+  // C8 scheme (conv_c8.cu): out = c8OutScale * (D1 + c8CorrScale * D2); 16-bit planes are fp16 unless mainBf16
+  int mainBf16;
+  float c8OutScale, c8CorrScale;
   int timingProbe;      // set from MCGVC_F8_TIMING_PROBE by the CTA-pair launcher (measurement hack, see there)
 };
 
@@ -85,6 +93,9 @@ struct WgradGeom {
   float* dw;             // [T][N][C] fp32, accumulated with atomics
   int nPass;
   double algoFlops;
+  // C8 scheme (wgrad_c8.cu): dW += c8OutScale * (D1 + c8CorrScale * D2)
+  int mainBf16;
+  float c8OutScale, c8CorrScale;
 };
 
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);
@@ -94,6 +105,11 @@ cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);
 // atomic merge are not free).
 int conv_plan_ksplit(const ConvGeom& g, double minGain);
 cudaError_t launch_conv_simt(const ConvGeom& g, cudaStream_t stream);
+// 16-bit main pass + two e4m3 correction passes (CTA-pair kernel, blockN 128 or 256) and its SIMT checker
+cudaError_t launch_conv_c8(const ConvGeom& g, int blockN, cudaStream_t stream);
+cudaError_t launch_conv_c8_simt(const ConvGeom& g, cudaStream_t stream);
+cudaError_t launch_wgrad_c8(const WgradGeom& g, cudaStream_t stream);
+cudaError_t launch_wgrad_c8_simt(const WgradGeom& g, cudaStream_t stream);
 cudaError_t launch_wgrad_tc(const WgradGeom& g, cudaStream_t stream);
 cudaError_t launch_wgrad_simt(const WgradGeom& g, cudaStream_t stream);
 

@@ -1,0 +1,346 @@
+// Weight-gradient GEMM, "16-bit main pass + 8-bit correction passes" precision scheme (C8).
+//
+// Same job and decomposition as wgrad_tc2_kernel in wgrad_gemm.cu (CTA pair, 256 gradient rows x
+// CTILE channels per pair, one (tap, n tile, c tile, K split) per pair, red.global.add epilogue),
+// with the operand planes of conv_c8.cu:
+//     dW[tap][n][c] += c1 * ( sum_p dz16[p,n]*x16[p,c]  +  c2 * sum_p (dz8h*x8l + dz8l*x8h) )
+// Both operands stay MN-major (positions are the contraction index and the OUTER shared-memory
+// dimension).  The 16-bit planes arrive as 64-position x 64-channel boxes (128-byte rows), the
+// e4m3 planes as 64-position x 128-channel boxes (again 128-byte rows, 128B swizzle) -- or
+// 64-channel boxes with the 64B swizzle when a CTA's half of the channel tile is only 64 wide
+// (CTILE = 128).  kind::f8f6f4 consumes K = 32 positions per instruction.
+//
+// STATUS (round 1): kernel-level only (mcgvc_debug_wgrad_c8), see conv_c8.cu.
+#include "gemm_types.cuh"
+#include "ptx.cuh"
+
+#include <cuda_fp16.h>
+
+namespace mcgvc {
+
+bool make_act_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int BX, int BY, int BB);
+
+namespace {
+
+constexpr int kPos = 64;                       // positions per k-block
+constexpr int kChunk16 = kPos * kBlockK * 2;   // 64 positions x 64 channels x 2 B = 8 KB
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 8-bit plane [B][P][Y][X][C]: box (boxC bytes, BX, BY, 1, BB); 128B swizzle for 128-channel boxes,
+// 64B swizzle for 64-channel boxes.
+bool make_plane8_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int boxC, int BX, int BY, int BB) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.X, (cuuint64_t)a.Y, (cuuint64_t)a.P, (cuuint64_t)a.B};
+  cuuint64_t strides[4];
+  strides[0] = (cuuint64_t)a.C;
+  strides[1] = strides[0] * a.X;
+  strides[2] = strides[1] * a.Y;
+  strides[3] = strides[2] * a.P;
+  cuuint32_t box[5] = {(cuuint32_t)boxC, (cuuint32_t)BX, (cuuint32_t)BY, 1u, (cuuint32_t)BB};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, boxC == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(plane8 C=%d box %d) failed: %d", a.C, boxC, (int)r); return false; }
+  return true;
+}
+
+// MN-major UMMA descriptor: rows of `rowBytes` (128 -> 128B swizzle, 64 -> 64B swizzle), 8-row groups
+// rowBytes * 8 apart (stride byte offset), next chunk along the MN dimension `lbo` bytes away.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t rowBytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(((rowBytes * 8) >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= (rowBytes == 128 ? 2ull : 4ull) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc16_mn(uint32_t fmt, uint32_t M, uint32_t N) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc8_mn(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int CTILE>
+struct WgC8Cfg {
+  static constexpr int kZ16 = 2 * kChunk16;               // this CTA's 128 gradient rows, 16-bit
+  static constexpr int kX16 = (CTILE / 128) * kChunk16;   // this CTA's CTILE/2 channels, 16-bit
+  static constexpr int kZ8 = kPos * 128;                  // 8 KB per e4m3 plane (128 rows)
+  static constexpr int kX8 = kPos * (CTILE / 2);          // 8 KB (CTILE 256) / 4 KB (CTILE 128)
+  static constexpr int kOffX16 = kZ16;
+  static constexpr int kOffZ8h = kOffX16 + kX16;
+  static constexpr int kOffZ8l = kOffZ8h + kZ8;
+  static constexpr int kOffX8h = kOffZ8l + kZ8;
+  static constexpr int kOffX8l = kOffX8h + kX8;
+  static constexpr int kStageBytes = kOffX8l + kX8;       // 64 KB / 48 KB
+  static constexpr int kStages = (222 * 1024) / kStageBytes > 8 ? 8 : (222 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * CTILE;             // D1 and D2
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kXRow = CTILE / 2;                 // bytes per position row of an x e4m3 box
+  static_assert(CTILE == 128 || CTILE == 256, "pair tile is 128 or 256 channels wide");
+  static_assert(kStageBytes % 1024 == 0 && kOffZ8h % 1024 == 0 && kOffX8h % 1024 == 0 && kOffX8l % 1024 == 0, "tile alignment");
+};
+
+template <int CTILE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+wgrad_c8_kernel(const __grid_constant__ CUtensorMap tmZ16, const __grid_constant__ CUtensorMap tmZ8h,
+                const __grid_constant__ CUtensorMap tmZ8l, const __grid_constant__ CUtensorMap tmX16,
+                const __grid_constant__ CUtensorMap tmX8h, const __grid_constant__ CUtensorMap tmX8l,
+                const __grid_constant__ WgradGeom g) {
+  using Cfg = WgC8Cfg<CTILE>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int cTiles = g.C / CTILE;
+  const int nTiles = g.N / 256;
+  int w = blockIdx.x >> 1;
+  const int split = w % g.splitK;
+  w /= g.splitK;
+  const int ct = w % cTiles;
+  w /= cTiles;
+  const int nt = w % nTiles;
+  const int t = w / nTiles;
+  const Tap tap = g.taps[t];
+  const Tap ztap = g.ztaps[t];
+  const int n0 = nt * 256 + (int)rank * 128;            // this CTA's gradient rows
+  const int c0 = ct * CTILE;                            // pair's channel tile
+  const int cLoad = c0 + (int)rank * (CTILE / 2);       // this CTA's half of the x channels
+
+  const int posTiles = g.tilesX * g.tilesY * g.tilesB;
+  const int per = (posTiles + g.splitK - 1) / g.splitK;
+  const int kBegin = split * per;
+  const int kEnd = (kBegin + per < posTiles) ? kBegin + per : posTiles;
+  const int numK = kEnd - kBegin;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmZ16); ptx::prefetch_tmap(&tmZ8h); ptx::prefetch_tmap(&tmZ8l);
+    ptx::prefetch_tmap(&tmX16); ptx::prefetch_tmap(&tmX8h); ptx::prefetch_tmap(&tmX8l);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 2);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(tfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (numK > 0) {
+    if (warp == 0 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kBegin; kt < kEnd; ++kt) {
+        int m = kt;
+        const int tx = m % g.tilesX;
+        m /= g.tilesX;
+        const int ty = m % g.tilesY;
+        const int tb = m / g.tilesY;
+        const int x0 = tx * g.BX, y0 = ty * g.BY, b0 = tb * g.BB;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+        const int zx = x0 + ztap.dx, zy = y0 + ztap.dy, xx = x0 + tap.dx, xy = y0 + tap.dy;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          ptx::tma_load_5d_2sm(st + j * kChunk16, &tmZ16, &full[stage], n0 + j * 64, zx, zy, 0, b0);
+#pragma unroll
+        for (int j = 0; j < CTILE / 128; ++j)
+          ptx::tma_load_5d_2sm(st + Cfg::kOffX16 + j * kChunk16, &tmX16, &full[stage], cLoad + j * 64, xx, xy, tap.plane, b0);
+        ptx::tma_load_5d_2sm(st + Cfg::kOffZ8h, &tmZ8h, &full[stage], n0, zx, zy, 0, b0);
+        ptx::tma_load_5d_2sm(st + Cfg::kOffZ8l, &tmZ8l, &full[stage], n0, zx, zy, 0, b0);
+        ptx::tma_load_5d_2sm(st + Cfg::kOffX8h, &tmX8h, &full[stage], cLoad, xx, xy, tap.plane, b0);
+        ptx::tma_load_5d_2sm(st + Cfg::kOffX8l, &tmX8l, &full[stage], cLoad, xx, xy, tap.plane, b0);
+        if (!leader) ptx::mbar_arrive_remote(&full[stage], 0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1 && lane == 0 && leader) {
+      const uint32_t idesc16 = idesc16_mn(g.mainBf16 ? 1u : 0u, 256, CTILE);
+      constexpr uint32_t idesc8 = idesc8_mn(256, CTILE);
+      const uint32_t d1 = tmem_base, d2 = tmem_base + CTILE;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < numK; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t s0 = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+#pragma unroll
+        for (int k = 0; k < kPos / 16; ++k)      // 16 positions x 128 B = 2048 B per instruction
+          ptx::umma_bf16_2cta(d1, umma_desc_mn(s0 + k * 2048, kChunk16, 128),
+                              umma_desc_mn(s0 + Cfg::kOffX16 + k * 2048, kChunk16, 128), idesc16, (kb | k) != 0);
+#pragma unroll
+        for (int k = 0; k < kPos / 32; ++k) {    // 32 positions per e4m3 instruction
+          const uint64_t dZ8h = umma_desc_mn(s0 + Cfg::kOffZ8h + k * 32 * 128, 8192, 128);
+          const uint64_t dZ8l = umma_desc_mn(s0 + Cfg::kOffZ8l + k * 32 * 128, 8192, 128);
+          const uint64_t dX8h = umma_desc_mn(s0 + Cfg::kOffX8h + k * 32 * Cfg::kXRow, Cfg::kX8, Cfg::kXRow);
+          const uint64_t dX8l = umma_desc_mn(s0 + Cfg::kOffX8l + k * 32 * Cfg::kXRow, Cfg::kX8, Cfg::kXRow);
+          ptx::umma_f8_2cta(d2, dZ8h, dX8l, idesc8, (kb | k) != 0);
+          ptx::umma_f8_2cta(d2, dZ8l, dX8h, idesc8, 1);
+        }
+        ptx::umma_commit_2cta(&empty[stage], 0x3);
+        if (kb == numK - 1) ptx::umma_commit_2cta(tfull, 0x3);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp >= 4) {
+      const int quad = warp & 3;
+      const int n = n0 + quad * 32 + lane;
+      float* drow = g.dw + ((long long)tap.w * g.N + n) * g.C + c0;
+      const float c1 = g.c8OutScale, c2 = g.c8CorrScale;
+      ptx::mbar_wait(tfull, 0);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+      for (int j = 0; j < CTILE / 32; ++j) {
+        uint32_t v1[32], v2[32];
+        ptx::tmem_ld32(taddr + j * 32, v1);
+        ptx::tmem_ld32(taddr + CTILE + j * 32, v2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          red_add4(drow + j * 32 + i,
+                   c1 * fmaf(c2, __uint_as_float(v2[i + 0]), __uint_as_float(v1[i + 0])),
+                   c1 * fmaf(c2, __uint_as_float(v2[i + 1]), __uint_as_float(v1[i + 1])),
+                   c1 * fmaf(c2, __uint_as_float(v2[i + 2]), __uint_as_float(v1[i + 2])),
+                   c1 * fmaf(c2, __uint_as_float(v2[i + 3]), __uint_as_float(v1[i + 3])));
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 2) ptx::tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+}
+
+template <int CTILE>
+cudaError_t launch_wg_c8_t(const WgradGeom& g, cudaStream_t stream) {
+  using Cfg = WgC8Cfg<CTILE>;
+  CUtensorMap tmZ16, tmZ8h, tmZ8l, tmX16, tmX8h, tmX8l;
+  if (!make_act_tmap(&tmZ16, g.dz.hi, g.dz, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_act_tmap(&tmX16, g.x.hi, g.x, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_plane8_tmap(&tmZ8h, g.dz.h8, g.dz, 128, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_plane8_tmap(&tmZ8l, g.dz.l8, g.dz, 128, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_plane8_tmap(&tmX8h, g.x.h8, g.x, CTILE / 2, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_plane8_tmap(&tmX8l, g.x.l8, g.x, CTILE / 2, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  static bool attr_done[64] = {};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_done[dev_id & 63];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_c8_kernel<CTILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("wgrad_c8: smem attr: %s", cudaGetErrorString(e)); return e; }
+    attr_set = true;
+  }
+  const long long pairs = (long long)g.nTaps * (g.N / 256) * (g.C / CTILE) * g.splitK;
+  profile_begin(1, g.algoFlops, stream);
+  wgrad_c8_kernel<CTILE><<<(unsigned)(2 * pairs), 256, Cfg::kSmemBytes, stream>>>(tmZ16, tmZ8h, tmZ8l, tmX16, tmX8h, tmX8l, g);
+  profile_end(stream);
+  return launched();
+}
+
+}  // namespace
+
+cudaError_t launch_wgrad_c8(const WgradGeom& g, cudaStream_t stream) {
+  if (g.BX * g.BY * g.BB != kPos) { set_error("wgrad_c8: box %dx%dx%d != 64", g.BX, g.BY, g.BB); return cudaErrorInvalidValue; }
+  if (g.N % 256 || g.dz.C != g.N) { set_error("wgrad_c8: N=%d must be a multiple of 256", g.N); return cudaErrorInvalidValue; }
+  if ((g.cTile != 128 && g.cTile != 256) || g.C % g.cTile || g.x.C != g.C) { set_error("wgrad_c8: C=%d cTile=%d", g.C, g.cTile); return cudaErrorInvalidValue; }
+  if (g.nTaps < 1 || g.nTaps > kMaxTaps || g.splitK < 1) { set_error("wgrad_c8: taps/splitK"); return cudaErrorInvalidValue; }
+  if (!g.dz.h8 || !g.dz.l8 || !g.x.h8 || !g.x.l8) { set_error("wgrad_c8: 8-bit planes missing"); return cudaErrorInvalidValue; }
+  return g.cTile == 256 ? launch_wg_c8_t<256>(g, stream) : launch_wg_c8_t<128>(g, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT checker on the same planes.
+namespace {
+__device__ __forceinline__ float e4m3f(uint8_t b) {
+  const int e = (b >> 3) & 0xF, m = b & 7;
+  const float mag = e == 0 ? (float)m * 0.001953125f : ldexpf(1.f + (float)m * 0.125f, e - 7);
+  return (b & 0x80) ? -mag : mag;
+}
+__device__ __forceinline__ float f16f(uint16_t v, int isBf16) {
+  if (isBf16) return __uint_as_float(static_cast<uint32_t>(v) << 16);
+  return __half2float(__ushort_as_half(v));
+}
+__global__ void wgrad_c8_simt_kernel(const __grid_constant__ WgradGeom g) {
+  const long long total = (long long)g.nTaps * g.N * g.C;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % g.C);
+  const int n = (int)((idx / g.C) % g.N);
+  const int t = (int)(idx / ((long long)g.C * g.N));
+  const Tap tap = g.taps[t];
+  const Tap ztap = g.ztaps[t];
+  const uint16_t* Z16 = reinterpret_cast<const uint16_t*>(g.dz.hi);
+  const uint16_t* X16 = reinterpret_cast<const uint16_t*>(g.x.hi);
+  const uint8_t* Z8h = reinterpret_cast<const uint8_t*>(g.dz.h8);
+  const uint8_t* Z8l = reinterpret_cast<const uint8_t*>(g.dz.l8);
+  const uint8_t* X8h = reinterpret_cast<const uint8_t*>(g.x.h8);
+  const uint8_t* X8l = reinterpret_cast<const uint8_t*>(g.x.l8);
+  float d1 = 0.f, d2 = 0.f;
+  for (int b = 0; b < g.pB; ++b) {
+    if (b >= g.dz.B || b >= g.x.B) continue;
+    for (int y = 0; y < g.pY; ++y) {
+      const int zy = y + ztap.dy, xy = y + tap.dy;
+      if (zy < 0 || zy >= g.dz.Y || xy < 0 || xy >= g.x.Y) continue;
+      for (int x = 0; x < g.pX; ++x) {
+        const int zx = x + ztap.dx, xx = x + tap.dx;
+        if (zx < 0 || zx >= g.dz.X || xx < 0 || xx >= g.x.X) continue;
+        const long long zo = ((((long long)b * g.dz.P) * g.dz.Y + zy) * g.dz.X + zx) * g.dz.C + n;
+        const long long xo = ((((long long)b * g.x.P + tap.plane) * g.x.Y + xy) * g.x.X + xx) * g.x.C + c;
+        d1 = fmaf(f16f(Z16[zo], g.mainBf16), f16f(X16[xo], g.mainBf16), d1);
+        d2 = fmaf(e4m3f(Z8h[zo]), e4m3f(X8l[xo]), d2);
+        d2 = fmaf(e4m3f(Z8l[zo]), e4m3f(X8h[xo]), d2);
+      }
+    }
+  }
+  atomicAdd(g.dw + ((long long)tap.w * g.N + n) * g.C + c, g.c8OutScale * fmaf(g.c8CorrScale, d2, d1));
+}
+}  // namespace
+
+cudaError_t launch_wgrad_c8_simt(const WgradGeom& g, cudaStream_t stream) {
+  const long long total = (long long)g.nTaps * g.N * g.C;
+  wgrad_c8_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g);
+  return launched();
+}
+
+}  // namespace mcgvc

@@ -117,6 +117,121 @@ def conv_case(lib, name, B, P, Y, X, C, N, taps, oB, oY, oX, nPass, blockN, with
     return ok
 
 
+def split_c8(x, u, main_bf16=False):
+    """C8 planes of a tensor: 16-bit hi (fp16 / bf16), e4m3(hi * 2^u), e4m3((x - hi) * 2^(u + 11 | 8))."""
+    hi = x.to(torch.bfloat16 if main_bf16 else torch.float16)
+    lo = x - hi.float()
+    shift = 8 if main_bf16 else 11
+    h8 = (hi.float() * 2.0 ** u).clamp(-448, 448).to(torch.float8_e4m3fn)
+    l8 = (lo * 2.0 ** (u + shift)).clamp(-448, 448).to(torch.float8_e4m3fn)
+    return hi.contiguous(), h8.contiguous(), l8.contiguous()
+
+
+def conv_c8_case(lib, name, B, P, Y, X, C, N, taps, oB, oY, oX, blockN, main_bf16=False, with_bias=True,
+                 with_add=False, seed=0, uA=1, uW=6, verbose=True):
+    """16-bit main pass + two e4m3 correction passes (conv_c8.cu): tcgen05 pair kernel vs SIMT checker vs
+    an fp64 evaluation of the same planes; also reports how far the scheme is from the exact product."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn(B, P, Y, X, C, device="cuda", generator=g)
+    T = max(t[3] for t in taps) + 1
+    W = torch.randn(T, N, C, device="cuda", generator=g) * 0.05
+    A16, A8h, A8l = split_c8(A, uA, main_bf16)
+    W16, W8h, W8l = split_c8(W, uW, main_bf16)
+    shift = 8 if main_bf16 else 11
+    c2 = 2.0 ** -(uA + uW + shift)
+    bias = torch.randn(N, device="cuda", generator=g) if with_bias else None
+    addsrc = torch.randn(oB, oY, oX, N, device="cuda", generator=g) if with_add else None
+    d = torch.float64
+    ref = ref_conv(A16.to(d), W16.to(d), taps, oB, oY, oX) + c2 * (
+        ref_conv(A8h.to(d), W8l.to(d), taps, oB, oY, oX) + ref_conv(A8l.to(d), W8h.to(d), taps, oB, oY, oX))
+    exact = ref_conv(A.to(d), W.to(d), taps, oB, oY, oX)
+    scheme_err = relerr(ref, exact)
+    if bias is not None:
+        ref = ref + bias.double()
+    if addsrc is not None:
+        ref = ref + addsrc.double()
+    res = {}
+    for backend, bname in ((1, "simt"), (2, "tc2")):
+        out = torch.full((oB, oY, oX, N), float("nan"), device="cuda")
+        rc = lib.mcgvc_debug_conv_c8(ptr(A16), ptr(A8h), ptr(A8l), C, X, Y, P, B, ptr(W16), ptr(W8h), ptr(W8l),
+                                     C, N, T, oX, oY, oB, len(taps), taps_array(taps), ptr(out), ptr(bias),
+                                     ptr(addsrc), 1 if main_bf16 else 0, ctypes.c_float(1.0), ctypes.c_float(c2),
+                                     backend, blockN, ctypes.c_void_p(0))
+        if rc != 0:
+            raise RuntimeError("mcgvc_debug_conv_c8: " + lib.mcgvc_last_error().decode())
+        torch.cuda.synchronize()
+        res[bname] = (relerr(torch.nan_to_num(out), ref), torch.isnan(out).sum().item())
+    ok = all(e < 2e-5 and n == 0 for e, n in res.values())
+    if verbose:
+        print(f"[c8   ] {name:34s} main={'bf16' if main_bf16 else 'fp16'} blockN={blockN:3d} simt err={res['simt'][0]:.2e} "
+              f"nan={res['simt'][1]} | tc2 err={res['tc2'][0]:.2e} nan={res['tc2'][1]} | scheme vs exact product "
+              f"{scheme_err:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+def wgrad_c8_case(lib, name, zshape, xshape, taps, ztaps, pB, pY, pX, cTile, splitK, main_bf16=False, seed=0,
+                  uZ=4, uX=1, zscale=0.1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    zB, zY, zX, N = zshape
+    xB, xP, xY, xX, C = xshape
+    Z = torch.randn(zB, 1, zY, zX, N, device="cuda", generator=g) * zscale
+    Xa = torch.randn(xB, xP, xY, xX, C, device="cuda", generator=g)
+    Z16, Z8h, Z8l = split_c8(Z, uZ, main_bf16)
+    X16, X8h, X8l = split_c8(Xa, uX, main_bf16)
+    shift = 8 if main_bf16 else 11
+    c2 = 2.0 ** -(uZ + uX + shift)
+    d = torch.float64
+    ref = ref_wgrad(Z16.to(d), X16.to(d), taps, ztaps, pB, pY, pX) + c2 * (
+        ref_wgrad(Z8h.to(d), X8l.to(d), taps, ztaps, pB, pY, pX) + ref_wgrad(Z8l.to(d), X8h.to(d), taps, ztaps, pB, pY, pX))
+    exact = ref_wgrad(Z.to(d), Xa.to(d), taps, ztaps, pB, pY, pX)
+    scheme_err = relerr(ref, exact)
+    T = ref.shape[0]
+    res = {}
+    for backend, bname in ((1, "simt"), (2, "tc2")):
+        dw = torch.zeros(T, N, C, device="cuda")
+        rc = lib.mcgvc_debug_wgrad_c8(ptr(Z16), ptr(Z8h), ptr(Z8l), N, zX, zY, zB, ptr(X16), ptr(X8h), ptr(X8l), C, xX, xY,
+                                      xP, xB, pX, pY, pB, len(taps), taps_array(taps), taps_array(ztaps), ptr(dw), cTile,
+                                      splitK, 1 if main_bf16 else 0, ctypes.c_float(1.0), ctypes.c_float(c2), backend,
+                                      ctypes.c_void_p(0))
+        if rc != 0:
+            raise RuntimeError("mcgvc_debug_wgrad_c8: " + lib.mcgvc_last_error().decode())
+        torch.cuda.synchronize()
+        res[bname] = relerr(dw, ref)
+    ok = all(e < 2e-5 for e in res.values())
+    print(f"[wg c8] {name:34s} main={'bf16' if main_bf16 else 'fp16'} cTile={cTile:3d} splitK={splitK} simt err={res['simt']:.2e} "
+          f"| tc2 err={res['tc2']:.2e} | scheme vs exact product {scheme_err:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+def wgrad_c8_cases(lib):
+    ok = True
+    z0 = [(0, 0, 0, 0)]
+    ok &= wgrad_c8_case(lib, "1tap B2 Y4 X16 N256 C256", (2, 4, 16, 256), (2, 1, 4, 16, 256), z0, z0, 2, 4, 16, 256, 1)
+    ok &= wgrad_c8_case(lib, "5x5 s1 N512 C256", (2, 20, 16, 512), (2, 1, 20, 16, 256), taps_5x5_s1(), z0 * 25, 2, 20, 16, 256, 2)
+    ok &= wgrad_c8_case(lib, "5x5 s1 N512 C256 bf16 main", (2, 20, 16, 512), (2, 1, 20, 16, 256), taps_5x5_s1(), z0 * 25, 2, 20, 16, 256, 2, main_bf16=True)
+    ok &= wgrad_c8_case(lib, "5x5 s2 parity N256 C256 odd", (3, 10, 9, 256), (3, 4, 10, 9, 256), taps_kxk_s2(5, 2), z0 * 25, 3, 10, 9, 256, 1)
+    ok &= wgrad_c8_case(lib, "ztaps (1dto2d style) 20 taps", (4, 20, 16, 256), (4, 1, 1, 16, 256),
+                        [(0, 0, 0, h) for h in range(20)], [(0, h, 0, 0) for h in range(20)], 4, 1, 16, 256, 1)
+    ok &= wgrad_c8_case(lib, "B16 Y40 X32 N512 C256 splitK4", (16, 40, 32, 512), (16, 1, 40, 32, 256), taps_5x5_s1(), z0 * 25, 16, 40, 32, 256, 4)
+    # channel tile 128: each CTA's half is 64 channels -> 64-byte rows, 64B swizzle, MN-major
+    ok &= wgrad_c8_case(lib, "1tap N256 C128 (cTile 128)", (2, 4, 16, 256), (2, 1, 4, 16, 128), z0, z0, 2, 4, 16, 128, 1)
+    ok &= wgrad_c8_case(lib, "5x5 s2 parity N512 C128 (cTile 128)", (2, 20, 16, 512), (2, 4, 20, 16, 128), taps_kxk_s2(5, 2), z0 * 25, 2, 20, 16, 128, 2)
+    return ok
+
+
+def c8_cases(lib):
+    ok = True
+    for bn in (128, 256):
+        ok &= conv_c8_case(lib, "1tap B2 Y4 X16 C64 N256", 2, 1, 4, 16, 64, 256, [(0, 0, 0, 0)], 2, 4, 16, bn)
+        ok &= conv_c8_case(lib, "5x5 s1 B2 Y20 X16 C128 N256", 2, 1, 20, 16, 128, 256, taps_5x5_s1(), 2, 20, 16, bn, with_add=True)
+    ok &= conv_c8_case(lib, "5x5 s1 bf16 main", 2, 1, 20, 16, 128, 256, taps_5x5_s1(), 2, 20, 16, 256, main_bf16=True)
+    ok &= conv_c8_case(lib, "5x5 s1 odd B3 Y5 X17 C64 N128", 3, 1, 5, 17, 64, 128, taps_5x5_s1(), 3, 5, 17, 128)
+    ok &= conv_c8_case(lib, "5x5 s2 parity B2 40x32->20x16", 2, 4, 20, 16, 128, 256, taps_kxk_s2(5, 2), 2, 20, 16, 256)
+    ok &= conv_c8_case(lib, "5x5 s1 B16 Y40 X32 C128 N512 (waves)", 16, 1, 40, 32, 128, 512, taps_5x5_s1(), 16, 40, 32, 256)
+    ok &= conv_c8_case(lib, "same, blockN 128 (2 TMEM buffers)", 16, 1, 40, 32, 128, 512, taps_5x5_s1(), 16, 40, 32, 128)
+    return ok
+
+
 def taps_5x5_s1():
     return [(kw - 2, kh - 2, 0, kh * 5 + kw) for kh in range(5) for kw in range(5)]
 
@@ -230,6 +345,11 @@ def all_cases(lib):
 
 if __name__ == "__main__":
     lib = load_lib()
+    if len(sys.argv) > 1 and sys.argv[1] == "c8":
+        ok = c8_cases(lib)
+        ok &= wgrad_c8_cases(lib)
+        print("KERNEL_CHECK_C8", "PASS" if ok else "FAIL")
+        sys.exit(0 if ok else 1)
     ok = all_cases(lib)
     print("KERNEL_CHECK", "PASS" if ok else "FAIL")
     sys.exit(0 if ok else 1)

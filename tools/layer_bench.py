@@ -36,6 +36,28 @@ def conv_layer(name, P, Y, X, C, N, taps, oY, oX):
     Wh, Wl = kc.split_bf16(W)
     del A, W
     flops = 2.0 * B * oY * oX * N * len(taps) * C
+    # 16-bit main pass + two e4m3 correction passes (conv_c8.cu), valid numerics
+    A = Ah.float() + Al.float()
+    W = Wh.float() + Wl.float()
+    A16, A8h, A8l = kc.split_c8(A, 1)
+    W16, W8h, W8l = kc.split_c8(W, 6)
+    del A, W
+    out = torch.empty(B, oY, oX, N, device="cuda")
+    row = []
+    for bn in (128, 256):
+        if N % bn:
+            continue
+
+        def run_c8():
+            rc = lib.mcgvc_debug_conv_c8(kc.ptr(A16), kc.ptr(A8h), kc.ptr(A8l), C, X, Y, P, B, kc.ptr(W16), kc.ptr(W8h),
+                                         kc.ptr(W8l), C, N, T, oX, oY, B, len(taps), kc.taps_array(taps), kc.ptr(out),
+                                         kc.ptr(None), kc.ptr(None), 0, ctypes.c_float(1.0), ctypes.c_float(2.0 ** -18),
+                                         2, bn, ctypes.c_void_p(0))
+            assert rc == 0, lib.mcgvc_last_error()
+        ms = time_fn(run_c8)
+        row.append("pair/%d %.0fus %.0fTF" % (bn, ms * 1e3, flops / ms / 1e9))
+    print("[conv ] %-10s C8 (f16 + 2x e4m3)  %s" % (name, " | ".join(row)), flush=True)
+    del A16, A8h, A8l, W16, W8h, W8l, out
     for nPass in (3, 1):
         row = []
         for backend, bn, label in ((0, 128, "1cta/128"), (0, 256, "1cta/256"), (2, 128, "pair/128"), (2, 256, "pair/256")):
