@@ -24,6 +24,9 @@ extern "C" {
 #define MCGVC_PRECISION_PARITY 3  /* split-bf16 x3: Ah*Wh + Ah*Wl + Al*Wh, fp32 accumulate */
 #define MCGVC_PRECISION_MIXED 2   /* forward split-bf16 x3 (output parity), backward single bf16 */
 #define MCGVC_PRECISION_FAST 1    /* single bf16 pass */
+#define MCGVC_PRECISION_C8 4      /* fp16 main pass + two e4m3 correction passes (2 MMA units per MAC instead of 3):
+                                     A*W ~= Ah*Wh + 2^-s (A8h*W8l + A8l*W8h); stems and heads stay split-bf16 x3.
+                                     Weights must be packed in the mode they are used in. */
 
 const char* mcgvc_last_error(void);
 int mcgvc_set_device(int device);

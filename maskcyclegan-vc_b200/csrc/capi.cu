@@ -43,8 +43,11 @@ static DevStreams* dev_streams() {
   return &d;
 }
 static RunCfg cfg(void* stream, bool backward = false) {
-  int np = g_precision == MCGVC_PRECISION_PARITY ? 3 : (g_precision == MCGVC_PRECISION_FAST ? 1 : (backward ? 1 : 3));
-  return RunCfg{(cudaStream_t)stream, g_backend, np, nullptr, nullptr};
+  int np = (g_precision == MCGVC_PRECISION_PARITY || g_precision == MCGVC_PRECISION_C8)
+               ? 3 : (g_precision == MCGVC_PRECISION_FAST ? 1 : (backward ? 1 : 3));
+  RunCfg rc{(cudaStream_t)stream, g_backend, np, nullptr, nullptr, 0};
+  rc.c8 = g_precision == MCGVC_PRECISION_C8;   // stems / heads stay split-bf16 x3 in this mode
+  return rc;
 }
 // run a backward body on the engine streams, bracketed by event hand-offs with the caller's stream
 template <class F>
@@ -190,8 +193,9 @@ int mcgvc_set_backend(int backend) {
   return 0;
 }
 int mcgvc_set_precision(int mode) {
-  if (mode != MCGVC_PRECISION_PARITY && mode != MCGVC_PRECISION_FAST && mode != MCGVC_PRECISION_MIXED) {
-    set_error("precision must be MCGVC_PRECISION_PARITY (3), _MIXED (2) or _FAST (1)");
+  if (mode != MCGVC_PRECISION_PARITY && mode != MCGVC_PRECISION_FAST && mode != MCGVC_PRECISION_MIXED &&
+      mode != MCGVC_PRECISION_C8) {
+    set_error("precision must be MCGVC_PRECISION_PARITY (3), _MIXED (2), _FAST (1) or _C8 (4)");
     return 1;
   }
   g_precision = mode;

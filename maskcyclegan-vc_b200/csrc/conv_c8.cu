@@ -15,6 +15,7 @@
 // STATUS (round 1): kernel-level only -- reached through mcgvc_debug_conv_c8 (tests/kernel_check.py,
 // tools/layer_bench.py).  The network path still runs split-bf16; DESIGN.md section 8 has the
 // integration plan (operand planes written by the layer kernels, per-tensor scales).
+#include "epilogue.cuh"
 #include "gemm_types.cuh"
 #include "ptx.cuh"
 
@@ -247,7 +248,13 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (both CTAs)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const float c1 = g.c8OutScale, c2 = g.c8CorrScale;
+    // out = c1 * (D1 + c2 * D2): host multipliers times the operands' device-side scale records
+    // {1/S, 1/E} (S scales the 16-bit plane, E the e4m3 planes; 2^-11 = residual pre-scale)
+    float c1 = g.c8OutScale, c2 = g.c8CorrScale;
+    if (g.c8RecA && g.c8RecW) {
+      c1 *= __ldg(g.c8RecA) * __ldg(g.c8RecW);
+      c2 *= __ldg(g.c8RecA + 1) * __ldg(g.c8RecW + 1);
+    }
     int it = 0;
     for (int tile = pairIdx; tile < totalTiles; tile += numPairs, ++it) {
       const int acc = it % kAccBufs;
@@ -266,8 +273,9 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
       const int by = (row / g.BX) % g.BY;
       const int bb = row / (g.BX * g.BY);
       const int x = tx * g.BX + bx, y = ty * g.BY + by;
-      const int b = tb * g.BB + bb;
+      int b = tb * g.BB + bb;
       const bool valid = real && (x < g.oX) && (y < g.oY) && (b < g.oB);
+      if (!real) b = g.oB;
       const long long off = g.grpOutOff[grp] + (long long)b * g.sB + (long long)y * g.sY +
                             (long long)x * g.sX + (long long)(n0 / g.nSplit) * g.sNhi + (n0 % g.nSplit);
       float* orow = g.out + off;
@@ -283,25 +291,10 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
         ptx::tmem_ld32(t1 + j * 32, v1);
         ptx::tmem_ld32(t2 + j * 32, v2);
         ptx::tmem_ld_wait();
-        if (valid) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 o;
-            o.x = c1 * fmaf(c2, __uint_as_float(v2[i + 0]), __uint_as_float(v1[i + 0]));
-            o.y = c1 * fmaf(c2, __uint_as_float(v2[i + 1]), __uint_as_float(v1[i + 1]));
-            o.z = c1 * fmaf(c2, __uint_as_float(v2[i + 2]), __uint_as_float(v1[i + 2]));
-            o.w = c1 * fmaf(c2, __uint_as_float(v2[i + 3]), __uint_as_float(v1[i + 3]));
-            if (g.bias) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j * 32 + i));
-              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-            }
-            if (arow) {
-              const float4 av = *reinterpret_cast<const float4*>(arow + j * 32 + i);
-              o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w;
-            }
-            *reinterpret_cast<float4*>(orow + j * 32 + i) = o;
-          }
-        }
+        for (int i = 0; i < 32; ++i)
+          v1[i] = __float_as_uint(c1 * fmaf(c2, __uint_as_float(v2[i]), __uint_as_float(v1[i])));
+        epilogue_chunk(g, v1, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b, false, true);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -366,7 +359,7 @@ cudaError_t launch_conv_c8(const ConvGeom& g, int blockN, cudaStream_t stream) {
   if (g.a.C % kBlockK || g.a.C != g.w.K || g.cBlocks != g.a.C / kBlockK) { set_error("conv_c8: C=%d K=%d", g.a.C, g.w.K); return cudaErrorInvalidValue; }
   if (!g.a.h8 || !g.a.l8 || !g.w.h8 || !g.w.l8) { set_error("conv_c8: 8-bit planes missing"); return cudaErrorInvalidValue; }
   if (g.nTaps < 1 || g.nTaps > kMaxTaps || g.nGroups < 1 || g.nGroups > 4) { set_error("conv_c8: taps/groups"); return cudaErrorInvalidValue; }
-  if (g.statSum || g.kSplit > 1) { set_error("conv_c8: fused statistics / split-K not wired yet"); return cudaErrorInvalidValue; }
+  if (g.kSplit > 1) { set_error("conv_c8: split-K is not wired into this kernel"); return cudaErrorInvalidValue; }
   return blockN == 256 ? launch_c8_t<256>(g, stream) : launch_c8_t<128>(g, stream);
 }
 
@@ -420,7 +413,12 @@ __global__ void conv_c8_simt_kernel(const __grid_constant__ ConvGeom g) {
   }
   const long long off = g.grpOutOff[grp] + (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
                         (long long)(n / g.nSplit) * g.sNhi + (n % g.nSplit);
-  float acc = g.c8OutScale * fmaf(g.c8CorrScale, d2, d1);
+  float c1 = g.c8OutScale, c2 = g.c8CorrScale;
+  if (g.c8RecA && g.c8RecW) {
+    c1 *= g.c8RecA[0] * g.c8RecW[0];
+    c2 *= g.c8RecA[1] * g.c8RecW[1];
+  }
+  float acc = c1 * fmaf(c2, d2, d1);
   if (g.bias) acc += g.bias[n];
   if (g.addsrc) acc += g.addsrc[off];
   g.out[off] = acc;

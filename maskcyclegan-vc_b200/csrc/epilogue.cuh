@@ -1,0 +1,102 @@
+// Epilogue helpers shared by the implicit-GEMM convolution kernels (conv_igemm.cu: single-CTA and
+// CTA-pair split-bf16 / bf16 kernels; conv_c8.cu: 16-bit + e4m3 kernels).
+#pragma once
+#include "gemm_types.cuh"
+
+namespace mcgvc {
+
+// Fused InstanceNorm statistics (optional): every epilogue warp reduces its 32 rows x 32 columns
+// chunk to per-column sums of z and z^2 with a butterfly "transpose" reduction (31 shuffles per
+// quantity instead of 160) and adds them into [image][column] accumulators with atomics.  Rows of a
+// warp belong to one image when a tile's positions-per-image (BX*BY) is >= 32; for smaller planes
+// (the 1-D trunk) the reduction is segmented: SEG lanes per image, each lane ends up owning 32/SEG
+// consecutive columns of its segment's sums.
+template <int SEG>
+__device__ __forceinline__ void warp_colsum_add(float (&a)[32], float (&b)[32], int lane,
+                                                float* dstA, float* dstB, bool img_ok) {
+  int n = 32;
+#pragma unroll
+  for (int s = SEG >> 1; s >= 1; s >>= 1) {
+    n >>= 1;
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < n) {
+        const float sendA = up ? a[i] : a[i + n];
+        const float keepA = up ? a[i + n] : a[i];
+        const float sendB = up ? b[i] : b[i + n];
+        const float keepB = up ? b[i + n] : b[i];
+        a[i] = keepA + __shfl_xor_sync(0xffffffffu, sendA, s);
+        b[i] = keepB + __shfl_xor_sync(0xffffffffu, sendB, s);
+      }
+    }
+  }
+  constexpr int kPer = 32 / SEG;   // columns owned by this lane
+  if (img_ok) {
+    const int start = (lane % SEG) * kPer;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      atomicAdd(dstA + start + i, a[i]);
+      atomicAdd(dstB + start + i, b[i]);
+    }
+  }
+}
+
+// one 32-column chunk of this thread's output row: +bias, +residual, store, optional statistics
+__device__ __forceinline__ void red_add_f32x4(float* addr, float4 t) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(t.x), "f"(t.y), "f"(t.z),
+               "f"(t.w)
+               : "memory");
+}
+
+// `partial`: this work item holds one K-slice of the tile (split-K): its accumulator is ADDED to the
+// zero-initialised output with red.global.add; bias and residual ride on the first slice only.
+__device__ __forceinline__ void epilogue_chunk(const ConvGeom& g, const uint32_t (&v)[32], bool valid,
+                                               float* orow, const float* arow, int ncol0, int lane,
+                                               int b, bool partial, bool first) {
+  float o[32];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float4 t;
+    t.x = __uint_as_float(v[i + 0]);
+    t.y = __uint_as_float(v[i + 1]);
+    t.z = __uint_as_float(v[i + 2]);
+    t.w = __uint_as_float(v[i + 3]);
+    if (g.bias && first) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + ncol0 + i));
+      t.x += bv.x; t.y += bv.y; t.z += bv.z; t.w += bv.w;
+    }
+    if (valid) {
+      if (arow && first) {
+        const float4 av = *reinterpret_cast<const float4*>(arow + i);
+        t.x += av.x; t.y += av.y; t.z += av.z; t.w += av.w;
+      }
+      if (partial) red_add_f32x4(orow + i, t);
+      else *reinterpret_cast<float4*>(orow + i) = t;
+    }
+    o[i] = t.x; o[i + 1] = t.y; o[i + 2] = t.z; o[i + 3] = t.w;
+  }
+  if (g.statSum) {
+    float q[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      o[i] = valid ? o[i] : 0.f;
+      q[i] = o[i] * o[i];
+    }
+    const bool img_ok = b < g.oB;
+    const long long so = (long long)(img_ok ? b : 0) * g.w.N + ncol0;
+    float* dA = g.statSum + so;
+    float* dB = g.statSq + so;
+    switch (g.statSeg) {
+      case 32: warp_colsum_add<32>(o, q, lane, dA, dB, img_ok); break;
+      case 16: warp_colsum_add<16>(o, q, lane, dA, dB, img_ok); break;
+      case 8: warp_colsum_add<8>(o, q, lane, dA, dB, img_ok); break;
+      case 4: warp_colsum_add<4>(o, q, lane, dA, dB, img_ok); break;
+      case 2: warp_colsum_add<2>(o, q, lane, dA, dB, img_ok); break;
+      default: warp_colsum_add<1>(o, q, lane, dA, dB, img_ok); break;
+    }
+  }
+}
+
+
+}  // namespace mcgvc

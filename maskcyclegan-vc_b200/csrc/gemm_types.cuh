@@ -25,6 +25,7 @@ struct ActOperand {
   // C8 scheme only (conv_c8.cu): e4m3 planes of hi * 2^u and (v - hi) * 2^(u+11), same indexing, 1 B/elem
   const void* h8;
   const void* l8;
+  const float* rec;  // device-side {1/S, 1/E}: S scales the 16-bit plane, E the e4m3 planes
 };
 // Weight operand: bf16 hi/lo, [T][N][K] (K contiguous, K = channels per tap).
 struct WgtOperand {
@@ -33,6 +34,7 @@ struct WgtOperand {
   int K, N, T;
   const void* h8;   // C8 scheme only, see ActOperand
   const void* l8;
+  const float* rec;
 };
 
 // Implicit-GEMM convolution:  out[row(b,y,x), n] = bias[n] + addsrc[..] +
@@ -72,6 +74,8 @@ struct ConvGeom {
   // C8 scheme (conv_c8.cu): out = c8OutScale * (D1 + c8CorrScale * D2); 16-bit planes are fp16 unless mainBf16
   int mainBf16;
   float c8OutScale, c8CorrScale;
+  const float* c8RecA;  // device-side scale records {1/S, 1/E} of the two operands (null: host multipliers only)
+  const float* c8RecW;
   int timingProbe;      // set from MCGVC_F8_TIMING_PROBE by the CTA-pair launcher (measurement hack, see there)
 };
 
@@ -96,6 +100,8 @@ struct WgradGeom {
   // C8 scheme (wgrad_c8.cu): dW += c8OutScale * (D1 + c8CorrScale * D2)
   int mainBf16;
   float c8OutScale, c8CorrScale;
+  const float* c8RecZ;   // device-side scale records {1/S, 1/E} of dz and x (null: host multipliers only)
+  const float* c8RecX;
 };
 
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);

@@ -5,6 +5,8 @@
 #include "gemm_types.cuh"
 
 #include <cmath>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 namespace mcgvc {
 
@@ -40,6 +42,27 @@ __device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* l
     pl.y = *reinterpret_cast<uint32_t*>(&d);
     *reinterpret_cast<uint2*>(lo + off) = pl;
   }
+}
+
+// C8 planes (see PlaneFmt): fp16 main value and the two e4m3 correction planes living in `lo`.
+__device__ __forceinline__ void store_planes(__nv_bfloat16* hi, __nv_bfloat16* lo, const PlaneFmt& f,
+                                             long long off, float4 v) {
+  if (!f.c8) { split_store4(hi, lo, off, v); return; }
+  const float sx = v.x * f.S, sy = v.y * f.S, sz = v.z * f.S, sw = v.w * f.S;
+  const __half2 h01 = __floats2half2_rn(sx, sy), h23 = __floats2half2_rn(sz, sw);
+  uint2 ph;
+  ph.x = *reinterpret_cast<const uint32_t*>(&h01);
+  ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+  *reinterpret_cast<uint2*>(hi + off) = ph;
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const float e = f.E, el = f.E * 2048.f;
+  uint8_t* p8 = reinterpret_cast<uint8_t*>(lo);
+  const uint32_t a0 = __nv_cvt_float2_to_fp8x2(make_float2(f01.x * e, f01.y * e), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t a1 = __nv_cvt_float2_to_fp8x2(make_float2(f23.x * e, f23.y * e), __NV_SATFINITE, __NV_E4M3);
+  *reinterpret_cast<uint32_t*>(p8 + off) = a0 | (a1 << 16);
+  const uint32_t b0 = __nv_cvt_float2_to_fp8x2(make_float2((sx - f01.x) * el, (sy - f01.y) * el), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t b1 = __nv_cvt_float2_to_fp8x2(make_float2((sz - f23.x) * el, (sw - f23.y) * el), __NV_SATFINITE, __NV_E4M3);
+  *reinterpret_cast<uint32_t*>(p8 + f.elems + off) = b0 | (b1 << 16);
 }
 
 __device__ __forceinline__ long long act_off(const ActBuf& a, int img, int y, int x) {
@@ -233,7 +256,7 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const ApplyArgs a) {
       o = swish4(ss_apply(v, ka));
     }
     const long long off = act_off(a.out, img, y, x) + c;
-    if (a.out.hi) split_store4(a.out.hi, a.out.lo, off, o);
+    if (a.out.hi) store_planes(a.out.hi, a.out.lo, a.out.fmt, off, o);
     if (a.out.f32) *reinterpret_cast<float4*>(a.out.f32 + off) = o;
   }
 }
@@ -275,6 +298,9 @@ __device__ __forceinline__ float swish_grad(float yv) {
 __device__ __forceinline__ float4 swish_grad4(float4 y) {
   return make_float4(swish_grad(y.x), swish_grad(y.y), swish_grad(y.z), swish_grad(y.w));
 }
+__device__ __forceinline__ float amax4(const float4& v) {
+  return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
 __device__ __forceinline__ void acc4(float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
 __device__ __forceinline__ void fma4(float4& a, const float4& u, const float4& v) {
   a.x = fmaf(u.x, v.x, a.x); a.y = fmaf(u.y, v.y, a.y); a.z = fmaf(u.z, v.z, a.z); a.w = fmaf(u.w, v.w, a.w);
@@ -291,10 +317,16 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
   const int img = blockIdx.y;
   const bool ok = c < C;
   float4 s1a = make_float4(0.f, 0.f, 0.f, 0.f), s2a = s1a, s1g = s1a, s2g = s1a;
+  float mA = 0.f, mDy = 0.f, mXh = 0.f;   // maxima for the C8 dz scale (only used when a.mx != null)
   if (ok) {
     const Norm4 na = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, c);
     Norm4 ng = na;
     if (MODE == kGatedIN) ng = load_norm(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, C + c);
+    mA = fmaxf(fmaxf(fabsf(na.rstd.x * na.gamma.x), fabsf(na.rstd.y * na.gamma.y)),
+               fmaxf(fabsf(na.rstd.z * na.gamma.z), fabsf(na.rstd.w * na.gamma.w)));
+    if (MODE == kGatedIN)
+      mA = fmaxf(mA, fmaxf(fmaxf(fabsf(ng.rstd.x * ng.gamma.x), fabsf(ng.rstd.y * ng.gamma.y)),
+                           fmaxf(fabsf(ng.rstd.z * ng.gamma.z), fabsf(ng.rstd.w * ng.gamma.w))));
     const int P = a.dA.Y * a.dA.X;
     const int per = (P + gridDim.z - 1) / gridDim.z;
     const int pBeg = blockIdx.z * per;
@@ -322,17 +354,38 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
                                        d.z * ya.z * sg.z * (1.f - sg.z), d.w * ya.w * sg.w * (1.f - sg.w));
         acc4(s1a, dya); fma4(s2a, dya, xh);
         acc4(s1g, dyg); fma4(s2g, dyg, xg);
+        mDy = fmaxf(mDy, fmaxf(amax4(dya), amax4(dyg)));
+        mXh = fmaxf(mXh, fmaxf(amax4(xh), amax4(xg)));
       } else if (MODE == kINOnly) {
         acc4(s1a, d); fma4(s2a, d, xh);
+        mDy = fmaxf(mDy, amax4(d));
+        mXh = fmaxf(mXh, amax4(xh));
       } else {  // kINSwish, kINSwishShuffle
         const float4 g = swish_grad4(affine4(xh, na));
         const float4 dy = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
         acc4(s1a, dy); fma4(s2a, dy, xh);
+        mDy = fmaxf(mDy, amax4(dy));
+        mXh = fmaxf(mXh, amax4(xh));
       }
     }
   }
   red[0][warp][lane] = s1a; red[1][warp][lane] = s2a;
   red[2][warp][lane] = s1g; red[3][warp][lane] = s2g;
+  if (a.mx) {   // block maxima -> three atomicMax (non-negative floats order like their bit patterns)
+    __shared__ float smx[3][8];
+    for (int o = 16; o > 0; o >>= 1) {
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, o));
+      mDy = fmaxf(mDy, __shfl_xor_sync(0xffffffffu, mDy, o));
+      mXh = fmaxf(mXh, __shfl_xor_sync(0xffffffffu, mXh, o));
+    }
+    if (lane == 0) { smx[0][warp] = mA; smx[1][warp] = mDy; smx[2][warp] = mXh; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float m = 0.f;
+      for (int w = 0; w < 8; ++w) m = fmaxf(m, smx[threadIdx.x][w]);
+      if (m == m) atomicMax(a.mx + threadIdx.x, __float_as_uint(fminf(m, 3.0e38f)));
+    }
+  }
   __syncthreads();
   if (warp == 0 && ok) {
     float4 t[4];
@@ -455,6 +508,19 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
     ka = load_bwd4(a, img, (MODE == kINSwishShuffle) ? c : col, invNp);
     if (MODE == kGatedIN) kg = load_bwd4(a, img, C + col, invNp);
   }
+  // C8 dz: power-of-two scale from the bound collected by pass 1 (see ApplyBwdArgs)
+  PlaneFmt dzf = a.dzFmt;
+  if (dzf.c8) {
+    const float bound = __uint_as_float(a.mx[0]) * __uint_as_float(a.mx[1]) * (2.f + __uint_as_float(a.mx[2]));
+    float S = 1.f;
+    if (bound > 0.f && bound < 3.0e38f) S = exp2f(fminf(fmaxf(14.f - ceilf(log2f(bound)), -100.f), 100.f));
+    dzf.S = S;
+    dzf.E = 0.015625f;   // 2^-6: |hi| <= 2^14 maps into e4m3's range (<= 2^8)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      a.dzRec[0] = 1.f / S;
+      a.dzRec[1] = 64.f;
+    }
+  }
   const float* zimg = a.z + (long long)img * zP * a.Nz;
   float4 bsa = make_float4(0.f, 0.f, 0.f, 0.f), bsg = bsa;
   for (int p = blockIdx.x * rows + r; p < zP; p += gridDim.x * rows) {
@@ -470,8 +536,8 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
       const float4 dza = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
       const float4 dzg = make_float4(d.x * va.x * sg.x * (1.f - sg.x), d.y * va.y * sg.y * (1.f - sg.y),
                                      d.z * va.z * sg.z * (1.f - sg.z), d.w * va.w * sg.w * (1.f - sg.w));
-      split_store4(a.dz_hi, a.dz_lo, orow + col, dza);
-      split_store4(a.dz_hi, a.dz_lo, orow + C + col, dzg);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow + col, dza);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow + C + col, dzg);
       acc4(bsa, dza); acc4(bsg, dzg);
     } else if (MODE == kGatedIN) {
       const float4 xa = xhat_b(ld4(zr + col), ka), xg = xhat_b(ld4(zr + C + col), kg);
@@ -481,8 +547,8 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
       const float4 dyg = make_float4(d.x * ya.x * sg.x * (1.f - sg.x), d.y * ya.y * sg.y * (1.f - sg.y),
                                      d.z * ya.z * sg.z * (1.f - sg.z), d.w * ya.w * sg.w * (1.f - sg.w));
       const float4 dza = in_bwd4(dya, xa, ka), dzg = in_bwd4(dyg, xg, kg);
-      split_store4(a.dz_hi, a.dz_lo, orow + col, dza);
-      split_store4(a.dz_hi, a.dz_lo, orow + C + col, dzg);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow + col, dza);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow + C + col, dzg);
       acc4(bsa, dza); acc4(bsg, dzg);
     } else {
       const float4 xh = xhat_b(ld4(zr + col), ka);
@@ -492,7 +558,7 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
         dy = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
       }
       const float4 dz = in_bwd4(dy, xh, ka);
-      split_store4(a.dz_hi, a.dz_lo, orow + col, dz);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow + col, dz);
       acc4(bsa, dz);
     }
   }
@@ -640,7 +706,7 @@ __global__ void __launch_bounds__(256) d_stem_fwd_kernel(const float* __restrict
         z[c] = acc * sigmoidf_(acc);
       }
       const long long off = ((w & 1) ? base1 : base0) + (long long)(w >> 1) * out.C;
-      split_store4(out.hi, out.lo, off, make_float4(z[0], z[1], z[2], z[3]));
+      store_planes(out.hi, out.lo, out.fmt, off, make_float4(z[0], z[1], z[2], z[3]));
     }
   }
 }
@@ -941,13 +1007,47 @@ __device__ __forceinline__ PackArgs entry_args(const PackEntry& e) {
   a.Np = e.Np; a.Cp = e.Cp; a.Tp = e.Tp; a.Cd = e.Cd;
   return a;
 }
+// c8 mode, pass 1: per-conv max |w| (float bits, atomicMax) into the conv's record
+__global__ void pack_amax_table_kernel(const __grid_constant__ PackTable t, const float* __restrict__ params,
+                                       float* __restrict__ f32) {
+  const PackEntry& e = t.e[blockIdx.y];
+  if (!e.c8) return;
+  const float* ref = params + e.refOff;
+  const long long total = (long long)e.N * e.C * e.T;
+  float m = 0.f;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(ref[idx]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m == m)
+    atomicMax(reinterpret_cast<unsigned int*>(f32 + e.rec + 2), __float_as_uint(fminf(m, 3.0e38f)));
+}
+__device__ __forceinline__ uint8_t to_e4m3(float v) {
+  return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+}
 __global__ void pack_weights_table_kernel(const __grid_constant__ PackTable t,
                                           const float* __restrict__ params,
-                                          __nv_bfloat16* __restrict__ packed) {
+                                          __nv_bfloat16* __restrict__ packed, float* __restrict__ f32) {
   const PackEntry& e = t.e[blockIdx.y];
   const PackArgs a = entry_args(e);
   const float* ref = params + e.refOff;
   const long long total = (long long)e.N * e.C * e.T;
+  float E = 1.f;
+  if (e.c8) {
+    const float amax = __uint_as_float(reinterpret_cast<const unsigned int*>(f32)[e.rec + 2]);
+    if (amax > 0.f) E = exp2f(floorf(log2f(224.f / amax)));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      f32[e.rec + 0] = 1.f;
+      f32[e.rec + 1] = 1.f / E;
+      f32[e.rec + 3] = E;
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && t.actRec >= 0) {
+    f32[t.actRec + 0] = 1.f;     // activations: S = 1
+    f32[t.actRec + 1] = 0.5f;    //              E = 2
+  }
+  __half* p16 = reinterpret_cast<__half*>(packed);
+  uint8_t* p8 = reinterpret_cast<uint8_t*>(packed);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int tt = (int)(idx % e.T);
@@ -956,24 +1056,45 @@ __global__ void pack_weights_table_kernel(const __grid_constant__ PackTable t,
     int tp, np, cp;
     pack_map(a, n, c, tt, &tp, &np, &cp);
     const float v = ref[idx];
+    const long long fo = ((long long)tp * e.Np + np) * e.Cp + cp;
+    const long long dO = (e.kind == kPack1dTo2d)
+                             ? ((long long)(np / 256) * e.Cd + cp) * 256 + (np % 256)
+                             : ((long long)tp * e.Cd + cp) * e.Np + np;
+    if (e.c8) {
+      const __half h = __float2half_rn(v);
+      const float hf = __half2float(h);
+      const uint8_t h8 = to_e4m3(hf * E), l8 = to_e4m3((v - hf) * E * 2048.f);
+      p16[e.fHi + fo] = h;
+      p8[2LL * e.fLo + fo] = h8;
+      p8[2LL * e.fLo + e.fElems + fo] = l8;
+      if (e.dHi >= 0) {
+        p16[e.dHi + dO] = h;
+        p8[2LL * e.dLo + dO] = h8;
+        p8[2LL * e.dLo + e.dElems + dO] = l8;
+      }
+      continue;
+    }
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-    const long long fo = ((long long)tp * e.Np + np) * e.Cp + cp;
     packed[e.fHi + fo] = h;
     packed[e.fLo + fo] = l;
     if (e.dHi >= 0) {
-      const long long dO = (e.kind == kPack1dTo2d)
-                               ? ((long long)(np / 256) * e.Cd + cp) * 256 + (np % 256)
-                               : ((long long)tp * e.Cd + cp) * e.Np + np;
       packed[e.dHi + dO] = h;
       packed[e.dLo + dO] = l;
     }
   }
 }
 cudaError_t launch_pack_weights_table(const PackTable& t, const float* params, __nv_bfloat16* packed,
-                                      cudaStream_t s) {
+                                      float* packedF32, cudaStream_t s) {
   dim3 grid(592, t.count);
-  pack_weights_table_kernel<<<grid, 256, 0, s>>>(t, params, packed);
+  bool any = false;
+  for (int i = 0; i < t.count; ++i) any = any || t.e[i].c8;
+  if (any) {
+    pack_amax_table_kernel<<<grid, 256, 0, s>>>(t, params, packedF32);
+    cudaError_t e = launched();
+    if (e != cudaSuccess) return e;
+  }
+  pack_weights_table_kernel<<<grid, 256, 0, s>>>(t, params, packed, packedF32);
   return launched();
 }
 __global__ void unpack_wgrads_table_kernel(const __grid_constant__ PackTable t,

@@ -11,12 +11,21 @@ namespace mcgvc {
 // Activation tensor in engine layout.  Logical index (img, y, x, c); memory is either plain
 // [img][Y][X][C] or parity-split [img][4][ceil(Y/2)][ceil(X/2)][C] (plane = (y&1)*2 + (x&1)), the
 // form a stride-2 convolution consumes through TMA without element strides.
+// How a value v is written into an operand's planes.  c8 = 0: split-bf16 (hi = bf16(v), lo =
+// bf16(v - hi)).  c8 = 1 (conv_c8.cu / wgrad_c8.cu): hi = fp16(v*S); the `lo` storage (2 B/elem) holds
+// two e4m3 planes of `elems` bytes each: e4m3(hi*E) and e4m3((v*S - hi)*E*2^11).
+struct PlaneFmt {
+  int c8;
+  float S, E;
+  long long elems;
+};
 struct ActBuf {
   __nv_bfloat16* hi;
   __nv_bfloat16* lo;
   float* f32;
   int nImg, Y, X, C;
   int parity;
+  PlaneFmt fmt;
 };
 
 enum ApplyMode {
@@ -55,6 +64,13 @@ struct ApplyBwdArgs {
   float* t1;            // [nImg][Nstat] sum dy        (written by reduce, read by apply)
   float* t2;            // [nImg][Nstat] sum dy*xhat
   int prezeroed;        // t1/t2 were zero-filled by the caller (one memset per backward call)
+  // C8 output of dz (dzFmt.c8 = 1): pass 1 collects {max |rstd*gamma|, max |dy|, max |xhat|} (float bits,
+  // atomicMax, zero-filled by the caller) in mx[0..2]; pass 2 derives the power-of-two scale S with
+  // |dz*S| <= 2^14 from the bound |dz| <= mx0*mx1*(2 + mx2), writes the planes with it and publishes
+  // the scale record {1/S, 1/E} for the GEMMs that consume dz.
+  PlaneFmt dzFmt;
+  unsigned int* mx;
+  float* dzRec;
   float* dgamma;        // engine order, accumulated (+=) over images
   float* dbeta;
   __nv_bfloat16* dz_hi; // [rows][Nz]
@@ -127,9 +143,14 @@ struct PackEntry {
   int refOff;             // float offset in the reference-order flat buffer
   int fHi, fLo, dHi, dLo; // bf16 element offsets in the packed blob (dHi < 0: no data-gradient copy)
   int gW;                 // float offset in the engine-layout gradient blob
+  // C8 planes (c8 = 1): the fHi/dHi regions hold fp16, the fLo/dLo regions two e4m3 planes of
+  // fElems / dElems bytes; rec = float offset (packed fp32 area) of the conv's record
+  // {1/S = 1, 1/E, amax bits, E}; E = largest power of two with amax*E <= 224
+  int c8, rec, fElems, dElems;
 };
 struct PackTable {
   int count;
+  int actRec;             // float offset of the static activation record {1, 1/2} (c8 mode), or -1
   PackEntry e[32];
 };
 struct VecEntry {
@@ -140,7 +161,7 @@ struct VecTable {
   VecEntry e[96];
 };
 cudaError_t launch_pack_weights_table(const PackTable& t, const float* params, __nv_bfloat16* packed,
-                                      cudaStream_t s);
+                                      float* packedF32, cudaStream_t s);
 cudaError_t launch_unpack_wgrads_table(const PackTable& t, const float* gblob, float* gradFlat,
                                        cudaStream_t s);
 cudaError_t launch_pack_vecs_table(const VecTable& t, const float* params, float* eng, cudaStream_t s);

@@ -37,7 +37,8 @@ struct DescBuilder {
   ModelDesc d;
   const ParamTable& pt;
   explicit DescBuilder(const ParamTable& p) : pt(p) {
-    d.packedBf16 = d.packedF32 = d.gradFloats = 0;
+    d.packedBf16 = d.gradFloats = 0;
+    d.actRec = 0; d.packedF32 = 64;   // first slot of the fp32 area: static activation record
     d.paramCount = p.total;
   }
   void conv(const std::string& name, std::vector<std::string> parts, int refN, int refC, int refT,
@@ -62,6 +63,9 @@ struct DescBuilder {
     } else {
       c.dHi = c.dLo = -1;
     }
+    c.fElems = fsz; c.dElems = dsz;
+    c.c8Eligible = (kind != kPackStemG && kind != kPackHead && kind != kPackStemD) ? 1 : 0;
+    c.c8Rec = d.packedF32; d.packedF32 += 64;
     c.biasEng = d.packedF32; d.packedF32 += align_up(Np, 64);
     c.gW = d.gradFloats; d.gradFloats += align_up((long long)Tp * Np * Cp, 64);
     c.gB = d.gradFloats; d.gradFloats += align_up(Np, 64);
@@ -262,20 +266,41 @@ struct StatPool {
     off += 2 * imgs * nz;
     return p;
   }
+  float* take_raw(long long n) {
+    float* p = base + off;
+    off += n;
+    return p;
+  }
 };
-long long gen_stat_pool_floats(int B) { return 2LL * B * (512 + 512 + 256 + 6 * (1024 + 256) + 5120 + 1024 + 512); }
-long long dis_stat_pool_floats(int B) { return 2LL * B * (256 + 512 + 1024); }
+constexpr long long kPoolExtra = 256;   // C8: 4 floats of dz-scale maxima per normalised layer
+long long gen_stat_pool_floats(int B) { return 2LL * B * (512 + 512 + 256 + 6 * (1024 + 256) + 5120 + 1024 + 512) + kPoolExtra; }
+long long dis_stat_pool_floats(int B) { return 2LL * B * (256 + 512 + 1024) + kPoolExtra; }
 
 struct Weights {   // views into the packed blob
   const __nv_bfloat16* bf;
   const float* f32;
-  Weights(const void* packed, const ModelDesc& d)
+  int c8;
+  const ModelDesc& d;
+  Weights(const void* packed, const ModelDesc& md, int c8mode)
       : bf(reinterpret_cast<const __nv_bfloat16*>(packed)),
-        f32(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) +
-                                           d.packedBf16 * 2)) {}
-  WgtOperand fwd(const ConvDesc& c) const { return WgtOperand{bf + c.fHi, bf + c.fLo, c.Cp, c.Np, c.Tp}; }
-  // data-gradient operand viewed as [T][N=Cd][K=Np]
-  WgtOperand bwd(const ConvDesc& c) const { return WgtOperand{bf + c.dHi, bf + c.dLo, c.Np, c.Cd, c.Tp}; }
+        f32(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + md.packedBf16 * 2)),
+        c8(c8mode), d(md) {}
+  bool is_c8(const ConvDesc& c) const { return c8 && c.c8Eligible; }
+  const float* act_rec() const { return f32 + d.actRec; }
+  // operand over the forward layout [T][N][K] / the data-gradient layout viewed as [T][N=Cd][K=Np]
+  // (or any other (K, N, T) view of the same storage, for the two flatten layers)
+  WgtOperand view(const ConvDesc& c, bool dgrad, int K, int N, int T) const {
+    const long long hi = dgrad ? c.dHi : c.fHi, lo = dgrad ? c.dLo : c.fLo, el = dgrad ? c.dElems : c.fElems;
+    WgtOperand w{bf + hi, bf + lo, K, N, T};
+    if (is_c8(c)) {
+      w.h8 = reinterpret_cast<const uint8_t*>(bf + lo);
+      w.l8 = reinterpret_cast<const uint8_t*>(bf + lo) + el;
+      w.rec = f32 + c.c8Rec;
+    }
+    return w;
+  }
+  WgtOperand fwd(const ConvDesc& c) const { return view(c, false, c.Cp, c.Np, c.Tp); }
+  WgtOperand bwd(const ConvDesc& c) const { return view(c, true, c.Np, c.Cd, c.Tp); }
   const float* bias(const ConvDesc& c) const { return f32 + c.biasEng; }
   const float* gamma(const NormDesc& n) const { return f32 + n.gammaEng; }
   const float* beta(const NormDesc& n) const { return f32 + n.betaEng; }
@@ -365,10 +390,34 @@ ConvGeom conv_geom(Run& r, const ActOperand& a, const WgtOperand& w, const TapLi
   return g;
 }
 
+// C8 operands (fp16 + 2 x e4m3 planes on both sides) run on the C8 kernels; everything else on the
+// split-bf16 / bf16 kernels.
+bool is_c8(const ConvGeom& g) { return g.a.h8 != nullptr && g.w.h8 != nullptr; }
+cudaError_t launch_conv_any(Run& r, ConvGeom& g) {
+  if (is_c8(g)) {
+    g.c8OutScale = 1.f;
+    g.c8CorrScale = 1.f / 2048.f;   // 2^-11: pre-scale of the residual planes
+    g.c8RecA = g.a.rec;
+    g.c8RecW = g.w.rec;
+    g.mainBf16 = 0;
+    g.kSplit = 1;
+    if (r.rc.backend != 0) return launch_conv_c8_simt(g, r.rc.stream);
+    // 256-wide tiles when they still fill the chip, else 128-wide (two TMEM buffer pairs)
+    const long long mPairs = ((long long)g.tilesX * g.tilesY * g.tilesB + 1) / 2;
+    const bool wide = g.w.N % 256 == 0 && g.nSplit % 256 == 0 && mPairs * (g.w.N / 256) * g.nGroups >= 74;
+    return launch_conv_c8(g, wide ? 256 : 128, r.rc.stream);
+  }
+  if ((g.a.h8 != nullptr) != (g.w.h8 != nullptr)) {
+    set_error("conv: activation and weight operands disagree on the C8 format");
+    return cudaErrorInvalidValue;
+  }
+  return r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream);
+}
+
 // Split-K (tensor-core backend only): when the planner finds that K-slices fill the SM waves
 // better, zero-fill the `splitFloats` floats at g.out and let the slices add into it.
 void plan_split(Run& r, ConvGeom& g, long long splitFloats, double minGain, const char* what) {
-  if (!r.ok || splitFloats <= 0 || r.rc.backend != 0) return;
+  if (!r.ok || splitFloats <= 0 || r.rc.backend != 0 || is_c8(g)) return;
   const int s = conv_plan_ksplit(g, minGain);
   if (s <= 1) return;
   r.check(cudaMemsetAsync(g.out, 0, (size_t)splitFloats * sizeof(float), r.rc.stream), what);
@@ -387,7 +436,7 @@ void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& t
   g.statSum = r.rc.backend == 0 ? statSum : nullptr;
   g.statSq = statSq;
   if (!g.statSum) plan_split(r, g, splitFloats, 0.08, what);
-  r.check(r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream), what);
+  r.check(launch_conv_any(r, g), what);
 }
 
 
@@ -438,29 +487,69 @@ void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList&
   g.nPass = r.rc.nPass;
   g.algoFlops = 2.0 * pB * pY * pX * (double)g.N * g.C * xtaps.n * algoFrac;
   cudaStream_t ws = r.wgrad_stream();
+  if (dz.h8 && x.h8) {
+    g.cTile = x.C % 256 == 0 ? 256 : 128;
+    g.c8OutScale = 1.f;
+    g.c8CorrScale = 1.f / 2048.f;
+    g.c8RecZ = dz.rec;
+    g.c8RecX = x.rec;
+    g.mainBf16 = 0;
+    if (g.N % 256 || x.C % 128) { r.ok = false; set_error("%s: C8 wgrad needs N %% 256 == 0 and C %% 128 == 0", what); return; }
+    // wave-aware split-K for the pair tiling of the C8 kernel
+    const long long unitsC8 = (long long)xtaps.n * (g.N / 256) * (g.C / g.cTile);
+    int best = 1;
+    double bestC = 1e30;
+    for (long long sk = 1; sk <= maxSplit; ++sk) {
+      const double waves = (double)(unitsC8 * sk) / 74.0;
+      const double rounds = (double)((unitsC8 * sk + 73) / 74);
+      const double cost = rounds / waves * (1.0 + 0.01 * (double)sk) + (waves < 1.0 ? 1.0 / waves : 0.0);
+      if (cost < bestC - 1e-9) { bestC = cost; best = (int)sk; }
+    }
+    g.splitK = best;
+    r.check(r.rc.backend == 0 ? launch_wgrad_c8(g, ws) : launch_wgrad_c8_simt(g, ws), what);
+    return;
+  }
+  if ((dz.h8 != nullptr) != (x.h8 != nullptr)) { r.ok = false; set_error("%s: dz and x disagree on the C8 format", what); return; }
   r.check(r.rc.backend == 0 ? launch_wgrad_tc(g, ws) : launch_wgrad_simt(g, ws), what);
-}
-
-ActOperand plain_op(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int B, int Y, int X, int C) {
-  return ActOperand{hi, lo, C, X, Y, 1, B};
-}
-ActOperand parity_op(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int B, int Y, int X, int C) {
-  return ActOperand{hi, lo, C, (X + 1) / 2, (Y + 1) / 2, 4, B};
-}
-long long parity_elems(int B, int Y, int X, int C) {
-  return (long long)B * 4 * ((Y + 1) / 2) * ((X + 1) / 2) * C;
 }
 
 struct BfPair {
   __nv_bfloat16* hi;
   __nv_bfloat16* lo;
+  long long elems;     // elements per plane
+  int c8;              // C8 planes (fp16 in hi, two e4m3 planes in lo) instead of split-bf16
+  const float* rec;    // C8: device-side scale record {1/S, 1/E} the consuming GEMMs read
 };
-BfPair take_pair(Arena& a, long long elems, const char* name) {
+BfPair take_pair(Arena& a, long long elems, const char* name, int c8 = 0, const float* rec = nullptr) {
   BfPair p;
   p.hi = a.takeT<__nv_bfloat16>(elems, name);
   p.lo = a.takeT<__nv_bfloat16>(elems);
+  p.elems = elems;
+  p.c8 = c8;
+  p.rec = rec;
   return p;
 }
+PlaneFmt plane_fmt(const BfPair& p) { return PlaneFmt{p.c8, 1.f, 2.f, p.elems}; }   // activations: S = 1, E = 2
+void set_c8(ActOperand& o, const BfPair& p) {
+  if (!p.c8) return;
+  o.h8 = reinterpret_cast<const uint8_t*>(p.lo);
+  o.l8 = reinterpret_cast<const uint8_t*>(p.lo) + p.elems;
+  o.rec = p.rec;
+}
+ActOperand plain_op(const BfPair& p, int B, int Y, int X, int C) {
+  ActOperand o{p.hi, p.lo, C, X, Y, 1, B};
+  set_c8(o, p);
+  return o;
+}
+ActOperand parity_op(const BfPair& p, int B, int Y, int X, int C) {
+  ActOperand o{p.hi, p.lo, C, (X + 1) / 2, (Y + 1) / 2, 4, B};
+  set_c8(o, p);
+  return o;
+}
+long long parity_elems(int B, int Y, int X, int C) {
+  return (long long)B * 4 * ((Y + 1) / 2) * ((X + 1) / 2) * C;
+}
+
 struct Stat {
   float* mean;
   float* rstd;
@@ -507,7 +596,7 @@ void run_dgrad_s2(Run& r, const ActOperand& dz, const WgtOperand& w, int K, int 
   g.statSum = nullptr; g.statSq = nullptr; g.statSeg = 32;
   g.kSplit = 1;
   plan_split(r, g, (long long)B * 4 * Yp * Xp * Cin, 0.08, what);
-  r.check(r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream), what);
+  r.check(launch_conv_any(r, g), what);
 }
 
 // Convolution whose output feeds an InstanceNorm: the statistics come out of the conv epilogue
@@ -529,7 +618,7 @@ void run_conv_in(Run& r, const ActOperand& a, const WgtOperand& w, const TapList
     // layers a little over one SM wave (Discriminator ds3: 80 pair tiles on 74 pairs): split-K plus
     // one stand-alone statistics pass over z beats paying a second, nearly empty round
     ConvGeom g = conv_geom(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0);
-    if (r.ok && conv_plan_ksplit(g, 0.2) > 1) fused = false;
+    if (r.ok && !is_c8(g) && conv_plan_ksplit(g, 0.2) > 1) fused = false;
   }
   if (!fused && r.rc.backend == 0 && splitFloats > 0) {
     run_conv(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0, nullptr, nullptr, splitFloats);
@@ -568,6 +657,9 @@ ApplyBwdArgs mk_bwd(int mode, const float* z, int Nz, int zY, int zX, const Stat
   a.prezeroed = 1;
   a.dgamma = dgamma; a.dbeta = dbeta;
   a.dz_hi = dz.hi; a.dz_lo = dz.lo; a.dbias = dbias;
+  a.dzFmt = PlaneFmt{dz.c8, 1.f, 1.f, dz.elems};
+  a.mx = dz.c8 ? reinterpret_cast<unsigned int*>(tp.take_raw(4)) : nullptr;
+  a.dzRec = const_cast<float*>(dz.rec);
   return a;
 }
 void run_bwd(Run& r, const ApplyBwdArgs& a, const char* what) {
@@ -581,8 +673,9 @@ void run_bwd(Run& r, const ApplyBwdArgs& a, const char* what) {
 // ================================================================================================
 // packing
 namespace {
-PackTable make_pack_table(const ModelDesc& d) {
+PackTable make_pack_table(const ModelDesc& d, int c8 = 0) {
   PackTable t{};
+  t.actRec = c8 ? (int)d.actRec : -1;
   for (const ConvDesc& c : d.convs)
     for (int p = 0; p < c.nParts; ++p) {
       PackEntry& e = t.e[t.count++];
@@ -592,6 +685,10 @@ PackTable make_pack_table(const ModelDesc& d) {
       e.fHi = (int)c.fHi; e.fLo = (int)c.fLo;
       e.dHi = c.Cd ? (int)c.dHi : -1; e.dLo = c.Cd ? (int)c.dLo : -1;
       e.gW = (int)c.gW;
+      e.c8 = c8 && c.c8Eligible;
+      e.rec = (int)c.c8Rec;
+      e.fElems = (int)c.fElems;
+      e.dElems = (int)c.dElems;
     }
   return t;
 }
@@ -616,10 +713,10 @@ int pack_model(const ModelDesc& d, const float* params, void* packed, const RunC
   float* f32 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + d.packedBf16 * 2);
   // padding elements (unused taps / channels) must be zero
   r.check(launch_fill_zero(packed, (size_t)d.packed_bytes(), rc.stream), "pack: zero");
-  const PackTable pt = make_pack_table(d);
+  const PackTable pt = make_pack_table(d, rc.c8);
   const VecTable vt = make_vec_table(d, false);
   if (pt.count > 32 || vt.count > 96) { set_error("pack tables too small"); return 1; }
-  r.check(launch_pack_weights_table(pt, params, bf, rc.stream), "pack: weights");
+  r.check(launch_pack_weights_table(pt, params, bf, f32, rc.stream), "pack: weights");
   r.check(launch_pack_vecs_table(vt, params, f32, rc.stream), "pack: vectors");
   return r.ok ? 0 : 1;
 }
@@ -661,7 +758,13 @@ struct GenSaved {
   long long total;
 };
 
-GenSaved plan_gen_saved(const GenDims& d, void* base, std::vector<SavedEntry>* layout) {
+const float* act_rec_of(const void* packed, const ModelDesc& md) {
+  return reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + md.packedBf16 * 2) + md.actRec;
+}
+
+// c8: the operands of every layer but the stem and the head are kept as C8 planes (same bytes)
+GenSaved plan_gen_saved(const GenDims& d, void* base, std::vector<SavedEntry>* layout, int c8 = 0,
+                        const float* rec = nullptr) {
   Arena a(base);
   a.layout = layout;
   GenSaved s{};
@@ -670,32 +773,32 @@ GenSaved plan_gen_saved(const GenDims& d, void* base, std::vector<SavedEntry>* l
                   M7 = (long long)d.B * 40 * d.X1, M8 = (long long)d.B * 80 * d.X2;
   s.X15 = take_pair(a, M0 * 64, "X15");
   s.z0 = a.takeT<float>(M0 * 256, "z0");
-  s.A0 = take_pair(a, parity_elems(d.B, 80, d.T, 128), "A0");
+  s.A0 = take_pair(a, parity_elems(d.B, 80, d.T, 128), "A0", c8, rec);
   s.z1 = a.takeT<float>(M1 * 512, "z1");
   s.st1 = take_stat(a, d.B * 512);
-  s.A1 = take_pair(a, parity_elems(d.B, 40, d.W1, 256), "A1");
+  s.A1 = take_pair(a, parity_elems(d.B, 40, d.W1, 256), "A1", c8, rec);
   s.z2 = a.takeT<float>(M2 * 512, "z2");
   s.st2 = take_stat(a, d.B * 512);
-  s.A2 = take_pair(a, M2 * 256, "A2");
+  s.A2 = take_pair(a, M2 * 256, "A2", c8, rec);
   s.z3 = a.takeT<float>(L * 256, "z3");
   s.st3 = take_stat(a, d.B * 256);
   for (int i = 0; i < 7; ++i) {
     s.Rf[i] = a.takeT<float>(L * 256, i == 0 ? "R0" : (i == 6 ? "R6" : nullptr));
-    s.R[i] = take_pair(a, L * 256, nullptr);
+    s.R[i] = take_pair(a, L * 256, nullptr, c8, rec);
   }
   for (int i = 0; i < 6; ++i) {
     s.z4[i] = a.takeT<float>(L * 1024, i == 0 ? "z4_0" : nullptr);
     s.st4[i] = take_stat(a, d.B * 1024);
-    s.H[i] = take_pair(a, L * 512, nullptr);
+    s.H[i] = take_pair(a, L * 512, nullptr, c8, rec);
     s.z5[i] = a.takeT<float>(L * 256, i == 0 ? "z5_0" : nullptr);
     s.st5[i] = take_stat(a, d.B * 256);
   }
   s.z6 = a.takeT<float>(M2 * 256, "z6");
   s.st6 = take_stat(a, (long long)d.B * 20 * 256);
-  s.U0 = take_pair(a, M2 * 256, "U0");
+  s.U0 = take_pair(a, M2 * 256, "U0", c8, rec);
   s.z7 = a.takeT<float>(M2 * 1024, "z7");
   s.st7 = take_stat(a, d.B * 256);
-  s.U1 = take_pair(a, M7 * 256, "U1");
+  s.U1 = take_pair(a, M7 * 256, "U1", c8, rec);
   s.z8 = a.takeT<float>(M7 * 512, "z8");
   s.st8 = take_stat(a, d.B * 128);
   s.U2 = take_pair(a, M8 * 128, "U2");
@@ -704,10 +807,10 @@ GenSaved plan_gen_saved(const GenDims& d, void* base, std::vector<SavedEntry>* l
 }
 
 ActBuf abuf(BfPair p, float* f32, int nImg, int Y, int X, int C, int parity) {
-  return ActBuf{p.hi, p.lo, f32, nImg, Y, X, C, parity};
+  return ActBuf{p.hi, p.lo, f32, nImg, Y, X, C, parity, plane_fmt(p)};
 }
 ActBuf gbuf(float* f32, int nImg, int Y, int X, int C, int parity) {
-  return ActBuf{nullptr, nullptr, f32, nImg, Y, X, C, parity};
+  return ActBuf{nullptr, nullptr, f32, nImg, Y, X, C, parity, PlaneFmt{0, 1.f, 1.f, 0}};
 }
 
 }  // namespace
@@ -727,8 +830,8 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
                       float* out, void* saved, void* ws, const RunCfg& rc) {
   const ModelDesc& md = generator_desc();
   const GenDims d(B, T);
-  GenSaved s = plan_gen_saved(d, saved, nullptr);
-  Weights W(packed, md);
+  GenSaved s = plan_gen_saved(d, saved, nullptr, rc.c8, act_rec_of(packed, md));
+  Weights W(packed, md, rc.c8);
   Run r{rc};
   cudaStream_t st = rc.stream;
   const auto& cv = md.convs;
@@ -750,26 +853,26 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
 
   // stem: stack(x*mask, mask) -> 5x15 conv || gates -> a * sigmoid(g)            model.py:241-242
   r.check(launch_prep_g(x, mask, B, T, s.X15.hi, s.X15.lo, st), "prep_g");
-  run_conv(r, plain_op(s.X15.hi, s.X15.lo, B, 80, T, 64), W.fwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, 1),
+  run_conv(r, plain_op(s.X15, B, 80, T, 64), W.fwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, 1),
            B, 80, T, plain_out(s.z0, 80, T, 256), W.bias(cv[G_STEM]), nullptr, "G stem conv", 150.0 / 320.0);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedNoNorm, s.z0, 256, 80, T, Stat{nullptr, nullptr}, 0,
                                               nullptr, nullptr, 1, nullptr,
                                               abuf(s.A0, nullptr, B, 80, T, 128, 1)), st), "G stem glu");
   // downSample1 / downSample2: 5x5 stride 2 conv || gates, IN, gated GLU         model.py:245-246
-  run_conv_in(r, parity_op(s.A0.hi, s.A0.lo, B, 80, T, 128), W.fwd(cv[G_DS1]), taps_s2_fwd(5, 2), B, 40,
+  run_conv_in(r, parity_op(s.A0, B, 80, T, 128), W.fwd(cv[G_DS1]), taps_s2_fwd(5, 2), B, 40,
               d.W1, plain_out(s.z1, 40, d.W1, 512), W.bias(cv[G_DS1]), "G ds1 conv", sp.take(B, 512), ssq, B, 512, 1,
               40 * d.W1, s.st1, s.z1, (long long)B * 40 * d.W1 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z1, 512, 40, d.W1, s.st1, 512, W.gamma(nm[GN_DS1]),
                                               W.beta(nm[GN_DS1]), 1, nullptr,
                                               abuf(s.A1, nullptr, B, 40, d.W1, 256, 1)), st), "G ds1 glu");
-  run_conv_in(r, parity_op(s.A1.hi, s.A1.lo, B, 40, d.W1, 256), W.fwd(cv[G_DS2]), taps_s2_fwd(5, 2), B,
+  run_conv_in(r, parity_op(s.A1, B, 40, d.W1, 256), W.fwd(cv[G_DS2]), taps_s2_fwd(5, 2), B,
               20, d.W2, plain_out(s.z2, 20, d.W2, 512), W.bias(cv[G_DS2]), "G ds2 conv", sp.take(B, 512), ssq, B, 512, 1,
               20 * d.W2, s.st2, s.z2, (long long)B * 20 * d.W2 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[GN_DS2]),
                                               W.beta(nm[GN_DS2]), 1, nullptr,
                                               abuf(s.A2, nullptr, B, 20, d.W2, 256, 0)), st), "G ds2 glu");
   // 2D -> 1D: view (c*20+h), Conv1d k1 5120->256, IN1d                           model.py:249-255
-  run_conv_in(r, plain_op(s.A2.hi, s.A2.lo, B, 20, d.W2, 256), W.fwd(cv[G_2DTO1D]), taps_rows(20, 1), B,
+  run_conv_in(r, plain_op(s.A2, B, 20, d.W2, 256), W.fwd(cv[G_2DTO1D]), taps_rows(20, 1), B,
               1, d.W2, plain_out(s.z3, 1, d.W2, 256), W.bias(cv[G_2DTO1D]), "G 2dto1d conv", sp.take(B, 256), ssq, B, 256,
               1, d.W2, s.st3, s.z3);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z3, 256, 1, d.W2, s.st3, 256, W.gamma(nm[GN_2DTO1D]),
@@ -782,13 +885,13 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
     const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
     const NormDesc& na = nm[GN_RES0 + 2 * i];
     const NormDesc& nb = nm[GN_RES0 + 2 * i + 1];
-    run_conv_in(r, plain_op(s.R[i].hi, s.R[i].lo, B, 1, d.W2, 256), W.fwd(ca), k3, B, 1, d.W2,
+    run_conv_in(r, plain_op(s.R[i], B, 1, d.W2, 256), W.fwd(ca), k3, B, 1, d.W2,
                 plain_out(s.z4[i], 1, d.W2, 1024), W.bias(ca), "G res conv a", sp.take(B, 1024), ssq, B, 1024, 1, d.W2,
                 s.st4[i], s.z4[i]);
     if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedIN, s.z4[i], 1024, 1, d.W2, s.st4[i], 1024, W.gamma(na),
                                                 W.beta(na), 1, nullptr,
                                                 abuf(s.H[i], nullptr, B, 1, d.W2, 512, 0)), st), "G res glu");
-    run_conv_in(r, plain_op(s.H[i].hi, s.H[i].lo, B, 1, d.W2, 512), W.fwd(cb), k3, B, 1, d.W2,
+    run_conv_in(r, plain_op(s.H[i], B, 1, d.W2, 512), W.fwd(cb), k3, B, 1, d.W2,
                 plain_out(s.z5[i], 1, d.W2, 256), W.bias(cb), "G res conv b", sp.take(B, 256), ssq, B, 256, 1, d.W2,
                 s.st5[i], s.z5[i]);
     if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z5[i], 256, 1, d.W2, s.st5[i], 256, W.gamma(nb),
@@ -798,7 +901,7 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   // 1D -> 2D: Conv1d k1 256->5120, IN1d over time per (c,h) row, view (256,20,W)   model.py:266-271
   {
     OutAddr o{s.z6, (long long)20 * d.W2 * 256, 0, 256, 256, (long long)d.W2 * 256};
-    run_conv_in(r, plain_op(s.R[6].hi, s.R[6].lo, B, 1, d.W2, 256), W.fwd(cv[G_1DTO2D]), taps_one(), B, 1,
+    run_conv_in(r, plain_op(s.R[6], B, 1, d.W2, 256), W.fwd(cv[G_1DTO2D]), taps_one(), B, 1,
                 d.W2, o, W.bias(cv[G_1DTO2D]), "G 1dto2d conv", sp.take(B * 20, 256), ssq, B * 20, 256, 1, d.W2, s.st6, s.z6);
   }
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINOnly, s.z6, 256, 1, d.W2, s.st6, 256, W.gamma(nm[GN_1DTO2D]),
@@ -806,13 +909,13 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
                                               abuf(s.U0, nullptr, B * 20, 1, d.W2, 256, 0)), st), "G 1dto2d IN");
   // upSample1 / upSample2: 5x5 conv, PixelShuffle(2), IN, swish                  model.py:274-275
   const TapList k55 = taps_s1(5, 5, 2, 2, 1);
-  run_conv_in(r, plain_op(s.U0.hi, s.U0.lo, B, 20, d.W2, 256), W.fwd(cv[G_UP1]), k55, B, 20, d.W2,
+  run_conv_in(r, plain_op(s.U0, B, 20, d.W2, 256), W.fwd(cv[G_UP1]), k55, B, 20, d.W2,
               plain_out(s.z7, 20, d.W2, 1024), W.bias(cv[G_UP1]), "G up1 conv", sp.take(B, 1024), ssq, B, 1024, 4,
               20 * d.W2, s.st7, s.z7, (long long)B * 20 * d.W2 * 1024);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z7, 1024, 20, d.W2, s.st7, 256, W.gamma(nm[GN_UP1]),
                                               W.beta(nm[GN_UP1]), 1, nullptr,
                                               abuf(s.U1, nullptr, B, 40, d.X1, 256, 0)), st), "G up1 act");
-  run_conv_in(r, plain_op(s.U1.hi, s.U1.lo, B, 40, d.X1, 256), W.fwd(cv[G_UP2]), k55, B, 40, d.X1,
+  run_conv_in(r, plain_op(s.U1, B, 40, d.X1, 256), W.fwd(cv[G_UP2]), k55, B, 40, d.X1,
               plain_out(s.z8, 40, d.X1, 512), W.bias(cv[G_UP2]), "G up2 conv", sp.take(B, 512), ssq, B, 512, 4,
               40 * d.X1, s.st8, s.z8, (long long)B * 40 * d.X1 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwishShuffle, s.z8, 512, 40, d.X1, s.st8, 128, W.gamma(nm[GN_UP2]),
@@ -820,7 +923,7 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
                                               abuf(s.U2, nullptr, B, 80, d.X2, 128, 0)), st), "G up2 act");
   // head: 5x15 conv 128->1 as per-tap GEMM + shifted sum                          model.py:278-279
   float* P = wa.takeT<float>((long long)B * 80 * d.X2 * 128);
-  run_conv(r, plain_op(s.U2.hi, s.U2.lo, B, 80, d.X2, 128), W.fwd(cv[G_HEAD]), taps_one(), B, 80, d.X2,
+  run_conv(r, plain_op(s.U2, B, 80, d.X2, 128), W.fwd(cv[G_HEAD]), taps_one(), B, 80, d.X2,
            plain_out(P, 80, d.X2, 128), nullptr, nullptr, "G head gemm", 75.0 / 128.0);
   if (r.ok) r.check(launch_head_g_fwd(P, W.bias(cv[G_HEAD]), B, 80, d.X2, out, st), "G head sum");
   return r.ok ? 0 : 1;
@@ -851,6 +954,7 @@ long long generator_bwd_ws_bytes(int B, int T) {
   add(M0 * 256 * 2); add(M0 * 256 * 2);          // dz0
   add(M0 * 64 * 4);                              // dX15
   add(gen_stat_pool_floats(B) * 4);              // t1 / t2 reduction pool
+  add(64 * 4);                                   // dz scale records (C8 mode)
   add(2 * 5120 * 4);                             // affine-grad sink
   return align_up(b, 256) + 4096;
 }
@@ -860,8 +964,8 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
                        const RunCfg& rc) {
   const ModelDesc& md = generator_desc();
   const GenDims d(B, T);
-  GenSaved s = plan_gen_saved(d, const_cast<void*>(saved), nullptr);
-  Weights W(packed, md);
+  GenSaved s = plan_gen_saved(d, const_cast<void*>(saved), nullptr, rc.c8, act_rec_of(packed, md));
+  Weights W(packed, md, rc.c8);
   Run r{rc};
   cudaStream_t st = rc.stream;
   const auto& cv = md.convs;
@@ -877,42 +981,46 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   auto gB = [&](int ci) -> float* { return needWgrad ? gblob + cv[ci].gB : nullptr; };
   auto gGa = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gGamma : junk; };
   auto gBe = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gBeta : junk + 5120; };
+  // C8 mode: the dz of every normalised layer is written as C8 planes with its own scale record
+  float* dzRecs = a.takeT<float>(2 * 32);
+  int nRec = 0;
+  auto dz_pair = [&](long long elems) { return take_pair(a, elems, nullptr, rc.c8, rc.c8 ? dzRecs + 2 * nRec++ : nullptr); };
   const TapList one = taps_one();
 
   // ---- head                                                                    model.py:278
   BfPair dP = take_pair(a, M8 * 128, nullptr);
   r.check(launch_head_g_bwd(dout, B, 80, d.X2, dP.hi, dP.lo, gB(G_HEAD), st), "G head bwd");
   float* dU2 = a.takeT<float>(M8 * 128);
-  run_conv(r, plain_op(dP.hi, dP.lo, B, 80, d.X2, 128), W.bwd(cv[G_HEAD]), one, B, 80, d.X2,
+  run_conv(r, plain_op(dP, B, 80, d.X2, 128), W.bwd(cv[G_HEAD]), one, B, 80, d.X2,
            plain_out(dU2, 80, d.X2, 128), nullptr, nullptr, "G head dgrad", 75.0 / 128.0, nullptr, nullptr, M8 * 128);
   if (needWgrad)
-    run_wgrad(r, plain_op(dP.hi, dP.lo, B, 80, d.X2, 128), plain_op(s.U2.hi, s.U2.lo, B, 80, d.X2, 128),
+    run_wgrad(r, plain_op(dP, B, 80, d.X2, 128), plain_op(s.U2, B, 80, d.X2, 128),
               one, nullptr, B, 80, d.X2, gW(G_HEAD), "G head wgrad", 75.0 / 128.0);
   // ---- upSample2
   const TapList k55f = taps_s1(5, 5, 2, 2, 1), k55b = taps_s1(5, 5, 2, 2, -1);
-  BfPair dz8 = take_pair(a, M7 * 512, nullptr);
+  BfPair dz8 = dz_pair(M7 * 512);
   run_bwd(r, mk_bwd(kINSwishShuffle, s.z8, 512, 40, d.X1, s.st8, 128, W.gamma(nm[GN_UP2]), W.beta(nm[GN_UP2]),
                     1, gbuf(dU2, B, 80, d.X2, 128, 0), tp, gGa(GN_UP2), gBe(GN_UP2), dz8, gB(G_UP2)),
           "G up2 bwd");
   float* dU1 = a.takeT<float>(M7 * 256);
-  run_conv(r, plain_op(dz8.hi, dz8.lo, B, 40, d.X1, 512), W.bwd(cv[G_UP2]), k55b, B, 40, d.X1,
+  run_conv(r, plain_op(dz8, B, 40, d.X1, 512), W.bwd(cv[G_UP2]), k55b, B, 40, d.X1,
            plain_out(dU1, 40, d.X1, 256), nullptr, nullptr, "G up2 dgrad", 1.0, nullptr, nullptr, M7 * 256);
   if (needWgrad)
-    run_wgrad(r, plain_op(dz8.hi, dz8.lo, B, 40, d.X1, 512), plain_op(s.U1.hi, s.U1.lo, B, 40, d.X1, 256),
+    run_wgrad(r, plain_op(dz8, B, 40, d.X1, 512), plain_op(s.U1, B, 40, d.X1, 256),
               k55f, nullptr, B, 40, d.X1, gW(G_UP2), "G up2 wgrad");
   // ---- upSample1
-  BfPair dz7 = take_pair(a, M2 * 1024, nullptr);
+  BfPair dz7 = dz_pair(M2 * 1024);
   run_bwd(r, mk_bwd(kINSwishShuffle, s.z7, 1024, 20, d.W2, s.st7, 256, W.gamma(nm[GN_UP1]), W.beta(nm[GN_UP1]),
                     1, gbuf(dU1, B, 40, d.X1, 256, 0), tp, gGa(GN_UP1), gBe(GN_UP1), dz7, gB(G_UP1)),
           "G up1 bwd");
   float* dU0 = a.takeT<float>(M2 * 256);
-  run_conv(r, plain_op(dz7.hi, dz7.lo, B, 20, d.W2, 1024), W.bwd(cv[G_UP1]), k55b, B, 20, d.W2,
+  run_conv(r, plain_op(dz7, B, 20, d.W2, 1024), W.bwd(cv[G_UP1]), k55b, B, 20, d.W2,
            plain_out(dU0, 20, d.W2, 256), nullptr, nullptr, "G up1 dgrad", 1.0, nullptr, nullptr, M2 * 256);
   if (needWgrad)
-    run_wgrad(r, plain_op(dz7.hi, dz7.lo, B, 20, d.W2, 1024), plain_op(s.U0.hi, s.U0.lo, B, 20, d.W2, 256),
+    run_wgrad(r, plain_op(dz7, B, 20, d.W2, 1024), plain_op(s.U0, B, 20, d.W2, 256),
               k55f, nullptr, B, 20, d.W2, gW(G_UP1), "G up1 wgrad");
   // ---- 1D -> 2D
-  BfPair dz6 = take_pair(a, M2 * 256, nullptr);
+  BfPair dz6 = dz_pair(M2 * 256);
   run_bwd(r, mk_bwd(kINOnly, s.z6, 256, 1, d.W2, s.st6, 256, W.gamma(nm[GN_1DTO2D]), W.beta(nm[GN_1DTO2D]), 20,
                     gbuf(dU0, B * 20, 1, d.W2, 256, 0), tp, gGa(GN_1DTO2D), gBe(GN_1DTO2D), dz6, nullptr),
           "G 1dto2d bwd");
@@ -922,13 +1030,13 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   {
     // dR6[(b,w), cin] = sum_h sum_c dz6[b,h,w,c] * W[c*20+h][cin]: 20 row taps over the (c,w,h) view
     const ConvDesc& c = cv[G_1DTO2D];
-    WgtOperand wop{W.bf + c.dHi, W.bf + c.dLo, 256, c.Cd, 20};
-    run_conv(r, plain_op(dz6.hi, dz6.lo, B, 20, d.W2, 256), wop, rows20, B, 1, d.W2,
+    const WgtOperand wop = W.view(c, true, 256, c.Cd, 20);
+    run_conv(r, plain_op(dz6, B, 20, d.W2, 256), wop, rows20, B, 1, d.W2,
              plain_out(dR[6], 1, d.W2, 256), nullptr, nullptr, "G 1dto2d dgrad");
     if (needWgrad) {
       TapList xt;  // x operand (R6) is not shifted; dz operand walks the 20 rows; slice = row
       for (int h = 0; h < 20; ++h) xt.add(0, 0, 0, h);
-      run_wgrad(r, plain_op(dz6.hi, dz6.lo, B, 20, d.W2, 256), plain_op(s.R[6].hi, s.R[6].lo, B, 1, d.W2, 256),
+      run_wgrad(r, plain_op(dz6, B, 20, d.W2, 256), plain_op(s.R[6], B, 1, d.W2, 256),
                 xt, &rows20, B, 1, d.W2, gW(G_1DTO2D), "G 1dto2d wgrad");
     }
   }
@@ -938,29 +1046,29 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   for (int i = 5; i >= 0; --i) {
     // one dz pair per block: the weight-gradient GEMMs read them from the side stream while the
     // main stream already works on the next block
-    BfPair dz5 = take_pair(a, L * 256, nullptr);
-    BfPair dz4 = take_pair(a, L * 1024, nullptr);
+    BfPair dz5 = dz_pair(L * 256);
+    BfPair dz4 = dz_pair(L * 1024);
     const ConvDesc& ca = cv[G_RES0 + 2 * i];
     const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
     const int na = GN_RES0 + 2 * i, nb = GN_RES0 + 2 * i + 1;
     run_bwd(r, mk_bwd(kINOnly, s.z5[i], 256, 1, d.W2, s.st5[i], 256, W.gamma(nm[nb]), W.beta(nm[nb]), 1,
                       gbuf(dR[i + 1], B, 1, d.W2, 256, 0), tp, gGa(nb), gBe(nb), dz5, nullptr), "G res bwd b");
-    run_conv(r, plain_op(dz5.hi, dz5.lo, B, 1, d.W2, 256), W.bwd(cb), k3b, B, 1, d.W2,
+    run_conv(r, plain_op(dz5, B, 1, d.W2, 256), W.bwd(cb), k3b, B, 1, d.W2,
              plain_out(dH, 1, d.W2, 512), nullptr, nullptr, "G res dgrad b");
     if (needWgrad)
-      run_wgrad(r, plain_op(dz5.hi, dz5.lo, B, 1, d.W2, 256), plain_op(s.H[i].hi, s.H[i].lo, B, 1, d.W2, 512),
+      run_wgrad(r, plain_op(dz5, B, 1, d.W2, 256), plain_op(s.H[i], B, 1, d.W2, 512),
                 k3f, nullptr, B, 1, d.W2, gblob + cb.gW, "G res wgrad b");
     run_bwd(r, mk_bwd(kGatedIN, s.z4[i], 1024, 1, d.W2, s.st4[i], 1024, W.gamma(nm[na]), W.beta(nm[na]), 1,
                       gbuf(dH, B, 1, d.W2, 512, 0), tp, gGa(na), gBe(na), dz4, nullptr), "G res bwd a");
     // dR[i] = dR[i+1] (skip connection) + dgrad
-    run_conv(r, plain_op(dz4.hi, dz4.lo, B, 1, d.W2, 1024), W.bwd(ca), k3b, B, 1, d.W2,
+    run_conv(r, plain_op(dz4, B, 1, d.W2, 1024), W.bwd(ca), k3b, B, 1, d.W2,
              plain_out(dR[i], 1, d.W2, 256), nullptr, dR[i + 1], "G res dgrad a");
     if (needWgrad)
-      run_wgrad(r, plain_op(dz4.hi, dz4.lo, B, 1, d.W2, 1024), plain_op(s.R[i].hi, s.R[i].lo, B, 1, d.W2, 256),
+      run_wgrad(r, plain_op(dz4, B, 1, d.W2, 1024), plain_op(s.R[i], B, 1, d.W2, 256),
                 k3f, nullptr, B, 1, d.W2, gblob + ca.gW, "G res wgrad a");
   }
   // ---- 2D -> 1D
-  BfPair dz3 = take_pair(a, L * 256, nullptr);
+  BfPair dz3 = dz_pair(L * 256);
   run_bwd(r, mk_bwd(kINOnly, s.z3, 256, 1, d.W2, s.st3, 256, W.gamma(nm[GN_2DTO1D]), W.beta(nm[GN_2DTO1D]), 1,
                     gbuf(dR[0], B, 1, d.W2, 256, 0), tp, gGa(GN_2DTO1D), gBe(GN_2DTO1D), dz3, nullptr),
           "G 2dto1d bwd");
@@ -968,33 +1076,33 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   {
     // dA2[b,h,w,c] = sum_n dz3[(b,w), n] * W[n][c*20+h]: one tap, N = (h,c) = 5120 split back over h
     const ConvDesc& c = cv[G_2DTO1D];
-    WgtOperand wop{W.bf + c.dHi, W.bf + c.dLo, 256, 5120, 1};
+    const WgtOperand wop = W.view(c, true, 256, 5120, 1);
     OutAddr o{dA2, (long long)20 * d.W2 * 256, 0, 256, 256, (long long)d.W2 * 256};
-    run_conv(r, plain_op(dz3.hi, dz3.lo, B, 1, d.W2, 256), wop, one, B, 1, d.W2, o, nullptr, nullptr,
+    run_conv(r, plain_op(dz3, B, 1, d.W2, 256), wop, one, B, 1, d.W2, o, nullptr, nullptr,
              "G 2dto1d dgrad");
     if (needWgrad)
-      run_wgrad(r, plain_op(dz3.hi, dz3.lo, B, 1, d.W2, 256), plain_op(s.A2.hi, s.A2.lo, B, 20, d.W2, 256),
+      run_wgrad(r, plain_op(dz3, B, 1, d.W2, 256), plain_op(s.A2, B, 20, d.W2, 256),
                 rows20, nullptr, B, 1, d.W2, gW(G_2DTO1D), "G 2dto1d wgrad");
   }
   // ---- downSample2
-  BfPair dz2 = take_pair(a, M2 * 512, nullptr);
+  BfPair dz2 = dz_pair(M2 * 512);
   run_bwd(r, mk_bwd(kGatedIN, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[GN_DS2]), W.beta(nm[GN_DS2]), 1,
                     gbuf(dA2, B, 20, d.W2, 256, 0), tp, gGa(GN_DS2), gBe(GN_DS2), dz2, nullptr), "G ds2 bwd");
   float* dA1 = a.takeT<float>(parity_elems(B, 40, d.W1, 256));
-  run_dgrad_s2(r, plain_op(dz2.hi, dz2.lo, B, 20, d.W2, 512), W.bwd(cv[G_DS2]), 5, 2, B, 20, (d.W1 + 1) / 2, 256,
+  run_dgrad_s2(r, plain_op(dz2, B, 20, d.W2, 512), W.bwd(cv[G_DS2]), 5, 2, B, 20, (d.W1 + 1) / 2, 256,
                dA1, "G ds2 dgrad");
   if (needWgrad)
-    run_wgrad(r, plain_op(dz2.hi, dz2.lo, B, 20, d.W2, 512), parity_op(s.A1.hi, s.A1.lo, B, 40, d.W1, 256),
+    run_wgrad(r, plain_op(dz2, B, 20, d.W2, 512), parity_op(s.A1, B, 40, d.W1, 256),
               taps_s2_fwd(5, 2), nullptr, B, 20, d.W2, gW(G_DS2), "G ds2 wgrad");
   // ---- downSample1
-  BfPair dz1 = take_pair(a, M1 * 512, nullptr);
+  BfPair dz1 = dz_pair(M1 * 512);
   run_bwd(r, mk_bwd(kGatedIN, s.z1, 512, 40, d.W1, s.st1, 512, W.gamma(nm[GN_DS1]), W.beta(nm[GN_DS1]), 1,
                     gbuf(dA1, B, 40, d.W1, 256, 1), tp, gGa(GN_DS1), gBe(GN_DS1), dz1, nullptr), "G ds1 bwd");
   float* dA0 = a.takeT<float>(parity_elems(B, 80, d.T, 128));
-  run_dgrad_s2(r, plain_op(dz1.hi, dz1.lo, B, 40, d.W1, 512), W.bwd(cv[G_DS1]), 5, 2, B, 40, (d.T + 1) / 2, 128,
+  run_dgrad_s2(r, plain_op(dz1, B, 40, d.W1, 512), W.bwd(cv[G_DS1]), 5, 2, B, 40, (d.T + 1) / 2, 128,
                dA0, "G ds1 dgrad");
   if (needWgrad)
-    run_wgrad(r, plain_op(dz1.hi, dz1.lo, B, 40, d.W1, 512), parity_op(s.A0.hi, s.A0.lo, B, 80, d.T, 128),
+    run_wgrad(r, plain_op(dz1, B, 40, d.W1, 512), parity_op(s.A0, B, 80, d.T, 128),
               taps_s2_fwd(5, 2), nullptr, B, 40, d.W1, gW(G_DS1), "G ds1 wgrad");
   // ---- stem
   BfPair dz0 = take_pair(a, M0 * 256, nullptr);
@@ -1002,11 +1110,11 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
                     gbuf(dA0, B, 80, d.T, 128, 1), tp, nullptr, nullptr, dz0, gB(G_STEM)),
           "G stem bwd");
   if (needWgrad)
-    run_wgrad(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 256), plain_op(s.X15.hi, s.X15.lo, B, 80, d.T, 64),
+    run_wgrad(r, plain_op(dz0, B, 80, d.T, 256), plain_op(s.X15, B, 80, d.T, 64),
               taps_s1(5, 1, 2, 0, 1), nullptr, B, 80, d.T, gW(G_STEM), "G stem wgrad", 150.0 / 320.0);
   if (dx) {
     float* dX15 = a.takeT<float>(M0 * 64);
-    run_conv(r, plain_op(dz0.hi, dz0.lo, B, 80, d.T, 256), W.bwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, -1), B, 80,
+    run_conv(r, plain_op(dz0, B, 80, d.T, 256), W.bwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, -1), B, 80,
              d.T, plain_out(dX15, 80, d.T, 64), nullptr, nullptr, "G stem dgrad", 150.0 / 320.0);
     if (r.ok) r.check(launch_col2im_g(dX15, mask, B, d.T, dx, st), "G col2im");
   }
@@ -1034,20 +1142,21 @@ struct DisSaved {
   BfPair D3;
   long long total;
 };
-DisSaved plan_dis_saved(const DisDims& d, void* base, std::vector<SavedEntry>* layout) {
+DisSaved plan_dis_saved(const DisDims& d, void* base, std::vector<SavedEntry>* layout, int c8 = 0,
+                        const float* rec = nullptr) {
   Arena a(base);
   a.layout = layout;
   DisSaved s{};
   const long long M0 = (long long)d.B * 80 * d.T, M1 = (long long)d.B * 40 * d.W1,
                   M2 = (long long)d.B * 20 * d.W2, M3 = (long long)d.B * 10 * d.W3;
   s.xin = a.takeT<float>(M0, "xin");
-  s.D0 = take_pair(a, parity_elems(d.B, 80, d.T, 128), "D0");
+  s.D0 = take_pair(a, parity_elems(d.B, 80, d.T, 128), "D0", c8, rec);
   s.z1 = a.takeT<float>(M1 * 256, "z1");
   s.st1 = take_stat(a, d.B * 256);
-  s.D1 = take_pair(a, parity_elems(d.B, 40, d.W1, 256), "D1");
+  s.D1 = take_pair(a, parity_elems(d.B, 40, d.W1, 256), "D1", c8, rec);
   s.z2 = a.takeT<float>(M2 * 512, "z2");
   s.st2 = take_stat(a, d.B * 512);
-  s.D2 = take_pair(a, parity_elems(d.B, 20, d.W2, 512), "D2");
+  s.D2 = take_pair(a, parity_elems(d.B, 20, d.W2, 512), "D2", c8, rec);
   s.z3 = a.takeT<float>(M3 * 1024, "z3");
   s.st3 = take_stat(a, d.B * 1024);
   s.D3 = take_pair(a, M3 * 1024, "D3");
@@ -1071,8 +1180,8 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
                           void* ws, const RunCfg& rc) {
   const ModelDesc& md = discriminator_desc();
   const DisDims d(B, T);
-  DisSaved s = plan_dis_saved(d, saved, nullptr);
-  Weights W(packed, md);
+  DisSaved s = plan_dis_saved(d, saved, nullptr, rc.c8, act_rec_of(packed, md));
+  Weights W(packed, md, rc.c8);
   Run r{rc};
   cudaStream_t st = rc.stream;
   const auto& cv = md.convs;
@@ -1099,24 +1208,24 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
                             abuf(s.D0, nullptr, B, 80, T, 128, 1), st), "D stem");
   // downSample1..3: 3x3 stride 2 conv + IN + swish                                 model.py:345-347
   const TapList k33 = taps_s2_fwd(3, 1);
-  run_conv_in(r, parity_op(s.D0.hi, s.D0.lo, B, 80, T, 128), W.fwd(cv[D_DS1]), k33, B, 40, d.W1,
+  run_conv_in(r, parity_op(s.D0, B, 80, T, 128), W.fwd(cv[D_DS1]), k33, B, 40, d.W1,
               plain_out(s.z1, 40, d.W1, 256), W.bias(cv[D_DS1]), "D ds1 conv", sp.take(B, 256), ssq, B, 256, 1, 40 * d.W1,
               s.st1, s.z1, (long long)B * 40 * d.W1 * 256);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z1, 256, 40, d.W1, s.st1, 256, W.gamma(nm[DN_DS1]),
                                               W.beta(nm[DN_DS1]), 1, nullptr, abuf(s.D1, nullptr, B, 40, d.W1, 256, 1)), st), "D ds1 act");
-  run_conv_in(r, parity_op(s.D1.hi, s.D1.lo, B, 40, d.W1, 256), W.fwd(cv[D_DS2]), k33, B, 20, d.W2,
+  run_conv_in(r, parity_op(s.D1, B, 40, d.W1, 256), W.fwd(cv[D_DS2]), k33, B, 20, d.W2,
               plain_out(s.z2, 20, d.W2, 512), W.bias(cv[D_DS2]), "D ds2 conv", sp.take(B, 512), ssq, B, 512, 1, 20 * d.W2,
               s.st2, s.z2, (long long)B * 20 * d.W2 * 512);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z2, 512, 20, d.W2, s.st2, 512, W.gamma(nm[DN_DS2]),
                                               W.beta(nm[DN_DS2]), 1, nullptr, abuf(s.D2, nullptr, B, 20, d.W2, 512, 1)), st), "D ds2 act");
-  run_conv_in(r, parity_op(s.D2.hi, s.D2.lo, B, 20, d.W2, 512), W.fwd(cv[D_DS3]), k33, B, 10, d.W3,
+  run_conv_in(r, parity_op(s.D2, B, 20, d.W2, 512), W.fwd(cv[D_DS3]), k33, B, 10, d.W3,
               plain_out(s.z3, 10, d.W3, 1024), W.bias(cv[D_DS3]), "D ds3 conv", sp.take(B, 1024), ssq, B, 1024, 1, 10 * d.W3,
               s.st3, s.z3, (long long)B * 10 * d.W3 * 1024);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kINSwish, s.z3, 1024, 10, d.W3, s.st3, 1024, W.gamma(nm[DN_DS3]),
                                               W.beta(nm[DN_DS3]), 1, nullptr, abuf(s.D3, nullptr, B, 10, d.W3, 1024, 0)), st), "D ds3 act");
   // outputConvLayer 1x3 1024->1 + sigmoid                                          model.py:323-327,348
   float* P = wa.takeT<float>((long long)B * 10 * d.W3 * 128);
-  run_conv(r, plain_op(s.D3.hi, s.D3.lo, B, 10, d.W3, 1024), W.fwd(cv[D_HEAD]), taps_one(), B, 10, d.W3,
+  run_conv(r, plain_op(s.D3, B, 10, d.W3, 1024), W.fwd(cv[D_HEAD]), taps_one(), B, 10, d.W3,
            plain_out(P, 10, d.W3, 128), nullptr, nullptr, "D head gemm", 3.0 / 128.0);
   if (r.ok) r.check(launch_head_d_fwd(P, W.bias(cv[D_HEAD]), B, 10, d.W3, out, st), "D head sum");
   return r.ok ? 0 : 1;
@@ -1129,6 +1238,7 @@ long long discriminator_bwd_ws_bytes(int B, int T) {
   long long b = 0;
   auto add = [&](long long bytes) { b = align_up(b, 256) + bytes; };
   add(dis_stat_pool_floats(B) * 4);                            // t1 / t2 reduction pool
+  add(64 * 4);                                                 // dz scale records (C8 mode)
   add(2 * 1024 * 4);                                           // affine-grad sink
   add(M3 * 128 * 2); add(M3 * 128 * 2);                        // dP
   add(M3 * 1024 * 4);                                          // dD3
@@ -1147,8 +1257,8 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
                            const RunCfg& rc) {
   const ModelDesc& md = discriminator_desc();
   const DisDims d(B, T);
-  DisSaved s = plan_dis_saved(d, const_cast<void*>(saved), nullptr);
-  Weights W(packed, md);
+  DisSaved s = plan_dis_saved(d, const_cast<void*>(saved), nullptr, rc.c8, act_rec_of(packed, md));
+  Weights W(packed, md, rc.c8);
   Run r{rc};
   cudaStream_t st = rc.stream;
   const auto& cv = md.convs;
@@ -1163,16 +1273,18 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
   auto gB = [&](int ci) -> float* { return needWgrad ? gblob + cv[ci].gB : nullptr; };
   auto gGa = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gGamma : junk; };
   auto gBe = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gBeta : junk + 1024; };
+  float* dzRecs = a.takeT<float>(2 * 32);
+  int nRec = 0;
   const TapList one = taps_one();
   const TapList k33 = taps_s2_fwd(3, 1);
 
   BfPair dP = take_pair(a, M3 * 128, nullptr);
   r.check(launch_head_d_bwd(dout, out, B, 10, d.W3, dP.hi, dP.lo, gB(D_HEAD), st), "D head bwd");
   float* dD3 = a.takeT<float>(M3 * 1024);
-  run_conv(r, plain_op(dP.hi, dP.lo, B, 10, d.W3, 128), W.bwd(cv[D_HEAD]), one, B, 10, d.W3,
+  run_conv(r, plain_op(dP, B, 10, d.W3, 128), W.bwd(cv[D_HEAD]), one, B, 10, d.W3,
            plain_out(dD3, 10, d.W3, 1024), nullptr, nullptr, "D head dgrad", 3.0 / 128.0, nullptr, nullptr, M3 * 1024);
   if (needWgrad)
-    run_wgrad(r, plain_op(dP.hi, dP.lo, B, 10, d.W3, 128), plain_op(s.D3.hi, s.D3.lo, B, 10, d.W3, 1024), one,
+    run_wgrad(r, plain_op(dP, B, 10, d.W3, 128), plain_op(s.D3, B, 10, d.W3, 1024), one,
               nullptr, B, 10, d.W3, gW(D_HEAD), "D head wgrad", 3.0 / 128.0);
 
   struct Lvl { int ci, ni, Nz, Cin, Yo, Xo, Yi, Xi; const float* z; Stat st; BfPair xin; };
@@ -1186,15 +1298,15 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
   for (int l = 0; l < 3; ++l) {
     const Lvl& v = lv[l];
     const long long Mo = (long long)B * v.Yo * v.Xo;
-    BfPair dz = take_pair(a, Mo * v.Nz, nullptr);
+    BfPair dz = take_pair(a, Mo * v.Nz, nullptr, rc.c8, rc.c8 ? dzRecs + 2 * nRec++ : nullptr);
     run_bwd(r, mk_bwd(kINSwish, v.z, v.Nz, v.Yo, v.Xo, v.st, v.Nz, W.gamma(nm[v.ni]), W.beta(nm[v.ni]), 1,
                       gbuf(dAct, B, v.Yo, v.Xo, v.Nz, dActParity), tp, gGa(v.ni), gBe(v.ni), dz, nullptr),
             "D ds bwd");
     float* dIn = a.takeT<float>(parity_elems(B, v.Yi, v.Xi, v.Cin));
-    run_dgrad_s2(r, plain_op(dz.hi, dz.lo, B, v.Yo, v.Xo, v.Nz), W.bwd(cv[v.ci]), 3, 1, B, (v.Yi + 1) / 2,
+    run_dgrad_s2(r, plain_op(dz, B, v.Yo, v.Xo, v.Nz), W.bwd(cv[v.ci]), 3, 1, B, (v.Yi + 1) / 2,
                  (v.Xi + 1) / 2, v.Cin, dIn, "D ds dgrad");
     if (needWgrad)
-      run_wgrad(r, plain_op(dz.hi, dz.lo, B, v.Yo, v.Xo, v.Nz), parity_op(v.xin.hi, v.xin.lo, B, v.Yi, v.Xi, v.Cin),
+      run_wgrad(r, plain_op(dz, B, v.Yo, v.Xo, v.Nz), parity_op(v.xin, B, v.Yi, v.Xi, v.Cin),
                 k33, nullptr, B, v.Yo, v.Xo, gW(v.ci), "D ds wgrad");
     dAct = dIn;
     dActParity = 1;

@@ -24,6 +24,11 @@ struct ConvDesc {
   long long fHi, fLo, dHi, dLo;  // bf16 element offsets in the packed weight blob
   long long biasEng;          // float offset in the packed small-vector area
   long long gW, gB;           // float offsets in the engine-layout gradient blob
+  // C8 precision mode: every conv except the stems and heads keeps fp16 + 2 x e4m3 planes in the
+  // same storage (fHi/dHi = fp16, fLo/dLo = two e4m3 planes of fElems / dElems bytes)
+  int c8Eligible;
+  long long fElems, dElems;   // elements per plane of the two layouts
+  long long c8Rec;            // float offset (packed fp32 area) of {1/S, 1/E, amax bits, E}
 };
 struct NormDesc {
   std::string name;
@@ -44,6 +49,7 @@ struct ModelDesc {
   long long packedBf16;       // bf16 elements in the packed blob (weights)
   long long packedF32;        // floats in the packed blob (small vectors), placed after the bf16 area
   long long gradFloats;       // floats in the engine-layout gradient blob
+  long long actRec;           // float offset (packed fp32 area) of the static activation record {1, 1/2}
   long long packed_bytes() const { return packedBf16 * 2 + packedF32 * 4; }
 };
 
@@ -56,6 +62,7 @@ struct RunCfg {
   int nPass;     // passes used by the call: 3 = split-bf16, 1 = bf16 (capi picks it per direction)
   cudaStream_t side;  // stream for the weight-gradient GEMMs of a backward pass, or null (same stream)
   cudaEvent_t forkEvent;  // persistent event used to fork to / join from the side stream
+  int c8;        // 1 = C8 precision mode: fp16 main pass + two e4m3 correction passes (stems / heads: split-bf16)
 };
 
 // sizes (bytes) of the per-call buffers the caller provides

@@ -226,7 +226,11 @@ wgrad_c8_kernel(const __grid_constant__ CUtensorMap tmZ16, const __grid_constant
       const int quad = warp & 3;
       const int n = n0 + quad * 32 + lane;
       float* drow = g.dw + ((long long)tap.w * g.N + n) * g.C + c0;
-      const float c1 = g.c8OutScale, c2 = g.c8CorrScale;
+      float c1 = g.c8OutScale, c2 = g.c8CorrScale;
+      if (g.c8RecZ && g.c8RecX) {
+        c1 *= __ldg(g.c8RecZ) * __ldg(g.c8RecX);
+        c2 *= __ldg(g.c8RecZ + 1) * __ldg(g.c8RecX + 1);
+      }
       ptx::mbar_wait(tfull, 0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -333,7 +337,12 @@ __global__ void wgrad_c8_simt_kernel(const __grid_constant__ WgradGeom g) {
       }
     }
   }
-  atomicAdd(g.dw + ((long long)tap.w * g.N + n) * g.C + c, g.c8OutScale * fmaf(g.c8CorrScale, d2, d1));
+  float c1 = g.c8OutScale, c2 = g.c8CorrScale;
+  if (g.c8RecZ && g.c8RecX) {
+    c1 *= g.c8RecZ[0] * g.c8RecX[0];
+    c2 *= g.c8RecZ[1] * g.c8RecX[1];
+  }
+  atomicAdd(g.dw + ((long long)tap.w * g.N + n) * g.C + c, c1 * fmaf(c2, d2, d1));
 }
 }  // namespace
 

@@ -15,6 +15,7 @@ BACKEND_SIMT = 1
 PRECISION_PARITY = 3   # split-bf16 x3 (default; meets the 1e-3 parity gate)
 PRECISION_MIXED = 2    # forward split-bf16 x3, backward single bf16 pass
 PRECISION_FAST = 1     # single bf16 pass
+PRECISION_C8 = 4       # fp16 main pass + two e4m3 correction passes (2 MMA units per MAC); parity-class accuracy
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcgvc.so")
 _lib = None

@@ -121,7 +121,8 @@ class _EngineModule(nn.Module):
             self._anchor = torch.zeros(1, device=dev, requires_grad=True)
 
     def _version(self):
-        return self._weights_epoch * 1000003 + sum(p._version for p in self._unique_params())
+        # the packed layout depends on the precision mode (C8 keeps fp16 + e4m3 planes)
+        return (engine.get_precision(), self._weights_epoch * 1000003 + sum(p._version for p in self._unique_params()))
 
     def _packed_weights(self):
         self._ensure_device_state()

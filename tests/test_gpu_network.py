@@ -286,6 +286,63 @@ def test_split_k_layers_agree_with_simt_backend_at_batch16(env):
         assert rel(got, want) < 2e-4, key
 
 
+def test_c8_precision_mode_meets_the_parity_gate(env):
+    """PRECISION_C8: fp16 main pass + two e4m3 correction passes (2 MMA units per MAC instead of 3) on
+    every layer but the stems and heads.  Same gate as the default mode: outputs, input gradient and
+    packed parameter gradients within 1e-3 of the reference; and the SIMT checker of the same planes
+    agrees with the tcgen05 kernels."""
+    import net_check
+    e = env["pkg"].engine
+    e.set_precision(e.PRECISION_C8)
+    try:
+        for B, T in ((2, 64), (1, 65)):
+            bwd = net_check.check_backward(env["G"], env["D"], env["gs"], env["ds"], B, T, verbose=False)
+            for k, v in bwd.items():
+                assert v < TOL, (B, T, k, v)
+        x, m, _, _ = O.synthetic_batch(2, 64, seed=3)
+        with torch.no_grad():
+            y_tc = env["G"](x.cuda(), m.cuda())
+            d_tc = env["D"](x.cuda())
+            e.set_backend(e.BACKEND_SIMT)
+            try:
+                y_simt = env["G"](x.cuda(), m.cuda())
+                d_simt = env["D"](x.cuda())
+            finally:
+                e.set_backend(e.BACKEND_TCGEN05)
+        assert rel(y_tc, y_simt) < 1e-4 and rel(d_tc, d_simt) < 1e-4
+        ref = O.generator_forward(env["gs"], x, m)
+        assert rel(y_tc, ref) < TOL
+    finally:
+        e.set_precision(e.PRECISION_PARITY)
+
+
+def test_c8_train_steps_track_the_parity_mode(env):
+    """Two full train steps at batch 16 in C8 mode (pair kernels, dynamic dz scales, C8 weight-gradient
+    GEMMs) against the same steps in the default mode: losses and updated weights agree closely."""
+    pkg = env["pkg"]
+    e = pkg.engine
+    from maskcyclegan_vc_b200 import trainstep as ts
+    out = {}
+    for name, mode in (("parity", e.PRECISION_PARITY), ("c8", e.PRECISION_C8)):
+        e.set_precision(mode)
+        try:
+            models = ts.build_models(pkg.Generator, pkg.Discriminator, torch.device("cuda"), seed=0)
+            g_opt, d_opt = ts.build_optimizers(models)
+            losses = []
+            for step in range(2):
+                batch = [t.cuda() for t in O.synthetic_batch(16, 64, seed=500 + step)]
+                gl, dl = ts.train_step(models, g_opt, d_opt, batch)
+                losses.append((gl.item(), dl.item()))
+            out[name] = (losses, [m._flat.detach().clone() for m in models])
+        finally:
+            e.set_precision(e.PRECISION_PARITY)
+    for (ga, da), (gb, db) in zip(out["parity"][0], out["c8"][0]):
+        assert abs(ga - gb) <= 2e-3 * abs(ga) and abs(da - db) <= 2e-3 * abs(da) + 1e-5
+    for wa, wb in zip(out["parity"][1], out["c8"][1]):
+        # Adam moves every weight by ~lr per step whatever the gradient's size: compare the update, loosely
+        assert rel(wb, wa) < 1e-3
+
+
 def test_fast_precision_mode_is_labelled_and_bounded(env):
     """bf16 single pass: faster, ~1e-2 relative error -- NOT within the 1e-3 gate."""
     e = env["pkg"].engine

@@ -25,7 +25,7 @@ from bench import synthetic_batch_host  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--precision", default="parity", choices=["parity", "mixed", "fast"])
+    ap.add_argument("--precision", default="parity", choices=["parity", "c8", "mixed", "fast"])
     ap.add_argument("--lean", type=int, default=0)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.md"))
@@ -34,7 +34,7 @@ def main():
     eng = pkg.engine
     from maskcyclegan_vc_b200 import trainstep as ts
     eng.lib()
-    eng.set_precision({"parity": eng.PRECISION_PARITY, "mixed": eng.PRECISION_MIXED, "fast": eng.PRECISION_FAST}[args.precision])
+    eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "mixed": eng.PRECISION_MIXED, "fast": eng.PRECISION_FAST}[args.precision])
     pkg.set_lean(bool(args.lean))
     dev = torch.device("cuda", 0)
     models = ts.build_models(pkg.Generator, pkg.Discriminator, dev, seed=0)
