@@ -12,13 +12,17 @@
 // The main products accumulate in one TMEM accumulator (D1), the scaled corrections in a second
 // (D2); the epilogue merges them:  out = c1 * (D1 + c2 * D2) + bias + residual.
 //
-// STATUS (round 1): kernel-level only -- reached through mcgvc_debug_conv_c8 (tests/kernel_check.py,
-// tools/layer_bench.py).  The network path still runs split-bf16; DESIGN.md section 8 has the
-// integration plan (operand planes written by the layer kernels, per-tensor scales).
+// Selected with mcgvc_set_precision(MCGVC_PRECISION_C8) for every layer but the stems, heads and the
+// 1-D trunk (network.cu); also reachable in isolation through mcgvc_debug_conv_c8
+// (tests/kernel_check.py, tools/layer_bench.py).  256-wide tiles use all 512 TMEM columns for D1 + D2,
+// so their epilogue is not overlapped with the next tile's MMAs; a two-phase variant (all correction
+// MMAs first, D2 parked as bf16 in shared memory, then the main pass) that restores the overlap was
+// built and measured slower in isolation (up2: 787 us vs 759 us), so it is not kept.
 #include "epilogue.cuh"
 #include "gemm_types.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -167,6 +171,8 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
   const int pairM = (mTiles + 1) / 2;
   const int tilesPerGroup = nTiles * pairM;
   const int totalTiles = tilesPerGroup * g.nGroups;
+  const int kSplit = g.kSplit > 1 ? g.kSplit : 1;   // split-K work items (tile, K slice), see conv_tc_kernel
+  const int totalItems = totalTiles * kSplit;
   const int pairIdx = blockIdx.x >> 1;
   const int numPairs = gridDim.x >> 1;
 
@@ -174,7 +180,9 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = pairIdx; tile < totalTiles; tile += numPairs) {
+    for (int item = pairIdx; item < totalItems; item += numPairs) {
+      const int tile = item / kSplit;
+      const int ks = item - tile * kSplit;
       const int grp = tile / tilesPerGroup;
       const int tl = tile - grp * tilesPerGroup;
       const int nt = tl % nTiles;
@@ -188,23 +196,25 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
         x0 = 0; y0 = 0; b0 = g.tilesB * g.BB;
       }
       const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
-      const int tapEnd = g.grpTapStart[grp] + g.grpTapCount[grp];
-      for (int t = g.grpTapStart[grp]; t < tapEnd; ++t) {
+      const int numK = g.grpTapCount[grp] * g.cBlocks;
+      const int kBeg = ks * numK / kSplit, kEnd = (ks + 1) * numK / kSplit;
+      int t = g.grpTapStart[grp] + kBeg / g.cBlocks;
+      int cb = kBeg % g.cBlocks;
+      for (int kb = kBeg; kb < kEnd; ++kb) {
         const Tap tap = g.taps[t];
-        for (int cb = 0; cb < g.cBlocks; ++cb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* st = smem + stage * Cfg::kStageBytes;
-          if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
-          const int c0 = cb * kBlockK, xx = x0 + tap.dx, yy = y0 + tap.dy;
-          ptx::tma_load_5d_2sm(st, &tmA16, &full[stage], c0, xx, yy, tap.plane, b0);
-          ptx::tma_load_3d_2sm(st + Cfg::kOffW16, &tmW16, &full[stage], c0, n0, tap.w);
-          ptx::tma_load_5d_2sm(st + Cfg::kOffA8h, &tmA8h, &full[stage], c0, xx, yy, tap.plane, b0);
-          ptx::tma_load_5d_2sm(st + Cfg::kOffA8l, &tmA8l, &full[stage], c0, xx, yy, tap.plane, b0);
-          ptx::tma_load_3d_2sm(st + Cfg::kOffW8h, &tmW8h, &full[stage], c0, n0, tap.w);
-          ptx::tma_load_3d_2sm(st + Cfg::kOffW8l, &tmW8l, &full[stage], c0, n0, tap.w);
-          if (!leader) ptx::mbar_arrive_remote(&full[stage], 0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+        const int c0 = cb * kBlockK, xx = x0 + tap.dx, yy = y0 + tap.dy;
+        ptx::tma_load_5d_2sm(st, &tmA16, &full[stage], c0, xx, yy, tap.plane, b0);
+        ptx::tma_load_3d_2sm(st + Cfg::kOffW16, &tmW16, &full[stage], c0, n0, tap.w);
+        ptx::tma_load_5d_2sm(st + Cfg::kOffA8h, &tmA8h, &full[stage], c0, xx, yy, tap.plane, b0);
+        ptx::tma_load_5d_2sm(st + Cfg::kOffA8l, &tmA8l, &full[stage], c0, xx, yy, tap.plane, b0);
+        ptx::tma_load_3d_2sm(st + Cfg::kOffW8h, &tmW8h, &full[stage], c0, n0, tap.w);
+        ptx::tma_load_3d_2sm(st + Cfg::kOffW8l, &tmW8l, &full[stage], c0, n0, tap.w);
+        if (!leader) ptx::mbar_arrive_remote(&full[stage], 0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++cb == g.cBlocks) { cb = 0; ++t; }
       }
     }
   } else if (warp == 1 && lane == 0 && leader) {
@@ -214,14 +224,17 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = pairIdx; tile < totalTiles; tile += numPairs, ++it) {
+    for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
+      const int tile = item / kSplit;
+      const int ks = item - tile * kSplit;
       const int acc = it % kAccBufs;
       const uint32_t aphase = (it / kAccBufs) & 1;
       ptx::mbar_wait(&tempty[acc], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d1 = tmem_base + acc * 2 * BLOCK_N;
       const uint32_t d2 = d1 + BLOCK_N;
-      const int numK = g.grpTapCount[tile / tilesPerGroup] * g.cBlocks;
+      const int numKg = g.grpTapCount[tile / tilesPerGroup] * g.cBlocks;
+      const int numK = (ks + 1) * numKg / kSplit - ks * numKg / kSplit;
       for (int kb = 0; kb < numK; ++kb) {
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
@@ -256,7 +269,9 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
       c2 *= __ldg(g.c8RecA + 1) * __ldg(g.c8RecW + 1);
     }
     int it = 0;
-    for (int tile = pairIdx; tile < totalTiles; tile += numPairs, ++it) {
+    for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
+      const int tile = item / kSplit;
+      const int ks = item - tile * kSplit;
       const int acc = it % kAccBufs;
       const uint32_t aphase = (it / kAccBufs) & 1;
       const int grp = tile / tilesPerGroup;
@@ -294,7 +309,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           v1[i] = __float_as_uint(c1 * fmaf(c2, __uint_as_float(v2[i]), __uint_as_float(v1[i])));
-        epilogue_chunk(g, v1, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b, false, true);
+        epilogue_chunk(g, v1, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b, kSplit > 1, ks == 0);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -309,6 +324,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
   ptx::cluster_sync();
   if (warp == 2) ptx::tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
 }
+
 
 int num_sms_c8() {
   static int n = 0;
@@ -341,7 +357,7 @@ cudaError_t launch_c8_t(const ConvGeom& g, cudaStream_t stream) {
     attr_set = true;
   }
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
-  const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups;
+  const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups * (g.kSplit > 1 ? g.kSplit : 1);
   const int maxPairs = num_sms_c8() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
   profile_begin(0, g.algoFlops, stream);
@@ -359,7 +375,11 @@ cudaError_t launch_conv_c8(const ConvGeom& g, int blockN, cudaStream_t stream) {
   if (g.a.C % kBlockK || g.a.C != g.w.K || g.cBlocks != g.a.C / kBlockK) { set_error("conv_c8: C=%d K=%d", g.a.C, g.w.K); return cudaErrorInvalidValue; }
   if (!g.a.h8 || !g.a.l8 || !g.w.h8 || !g.w.l8) { set_error("conv_c8: 8-bit planes missing"); return cudaErrorInvalidValue; }
   if (g.nTaps < 1 || g.nTaps > kMaxTaps || g.nGroups < 1 || g.nGroups > 4) { set_error("conv_c8: taps/groups"); return cudaErrorInvalidValue; }
-  if (g.kSplit > 1) { set_error("conv_c8: split-K is not wired into this kernel"); return cudaErrorInvalidValue; }
+  if (g.kSplit > 1) {
+    if (g.statSum) { set_error("conv_c8: split-K cannot feed the fused statistics"); return cudaErrorInvalidValue; }
+    for (int i = 0; i < g.nGroups; ++i)
+      if (g.kSplit > g.grpTapCount[i] * g.cBlocks) { set_error("conv_c8: kSplit=%d exceeds the k-blocks of group %d", g.kSplit, i); return cudaErrorInvalidValue; }
+  }
   return blockN == 256 ? launch_c8_t<256>(g, stream) : launch_c8_t<128>(g, stream);
 }
 

@@ -783,11 +783,10 @@ static int env_ksplit() {
   return v;
 }
 
-int conv_plan_ksplit(const ConvGeom& g, double minGain) {
+// wave arithmetic shared by the planners: `tiles` work items before splitting, `slots` concurrent ones
+int plan_ksplit_waves(long long tiles, int slots, const ConvGeom& g, double minGain) {
   if (!env_ksplit() || g.statSum) return 1;
-  if (g_force_block_n == 0 && env_block_n() != 0) g_force_block_n = env_block_n();
-  const ConvVariant v = conv_variant(g);
-  if (v.tiles < v.slots) return 1;             // sub-wave layers are latency-bound, not wave-bound
+  if (tiles < slots) return 1;                 // sub-wave layers are latency-bound, not wave-bound
   int minK = 1 << 30;
   for (int i = 0; i < g.nGroups; ++i) {
     const int k = g.grpTapCount[i] * g.cBlocks;
@@ -796,8 +795,8 @@ int conv_plan_ksplit(const ConvGeom& g, double minGain) {
   int maxS = minK / 4;                          // at least 4 k-blocks per slice
   if (maxS > 8) maxS = 8;
   auto cost = [&](int s) {
-    const double waves = (double)(v.tiles * s) / v.slots;
-    const double rounds = (double)((v.tiles * s + v.slots - 1) / v.slots);
+    const double waves = (double)(tiles * s) / slots;
+    const double rounds = (double)((tiles * s + slots - 1) / slots);
     return rounds / waves + 0.01 * (s - 1);
   };
   int best = 1;
@@ -808,6 +807,12 @@ int conv_plan_ksplit(const ConvGeom& g, double minGain) {
   }
   if (best > 1 && cost(1) - bestCost < minGain * cost(1)) best = 1;
   return best;
+}
+
+int conv_plan_ksplit(const ConvGeom& g, double minGain) {
+  if (g_force_block_n == 0 && env_block_n() != 0) g_force_block_n = env_block_n();
+  const ConvVariant v = conv_variant(g);
+  return plan_ksplit_waves(v.tiles, v.slots, g, minGain);
 }
 
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream) {

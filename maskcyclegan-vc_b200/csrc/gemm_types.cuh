@@ -110,6 +110,7 @@ cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);
 // rounds for 1.08 rounds of work.  `minGain` = required relative time saving (the zero-fill and the
 // atomic merge are not free).
 int conv_plan_ksplit(const ConvGeom& g, double minGain);
+int plan_ksplit_waves(long long tiles, int slots, const ConvGeom& g, double minGain);
 cudaError_t launch_conv_simt(const ConvGeom& g, cudaStream_t stream);
 // 16-bit main pass + two e4m3 correction passes (CTA-pair kernel, blockN 128 or 256) and its SIMT checker
 cudaError_t launch_conv_c8(const ConvGeom& g, int blockN, cudaStream_t stream);

@@ -64,7 +64,9 @@ struct DescBuilder {
       c.dHi = c.dLo = -1;
     }
     c.fElems = fsz; c.dElems = dsz;
-    c.c8Eligible = (kind != kPackStemG && kind != kPackHead && kind != kPackStemD) ? 1 : 0;
+    // C8 planes only where the MMA time dominates: the big 2-D layers.  Stems / heads (padded K or N)
+    // and the 1-D trunk with its two flatten layers (latency-bound small GEMMs) stay split-bf16.
+    c.c8Eligible = (kind == kPackShuffle || (kind == kPackStd && name.compare(0, 3, "res") != 0)) ? 1 : 0;
     c.c8Rec = d.packedF32; d.packedF32 += 64;
     c.biasEng = d.packedF32; d.packedF32 += align_up(Np, 64);
     c.gW = d.gradFloats; d.gradFloats += align_up((long long)Tp * Np * Cp, 64);
@@ -393,6 +395,15 @@ ConvGeom conv_geom(Run& r, const ActOperand& a, const WgtOperand& w, const TapLi
 // C8 operands (fp16 + 2 x e4m3 planes on both sides) run on the C8 kernels; everything else on the
 // split-bf16 / bf16 kernels.
 bool is_c8(const ConvGeom& g) { return g.a.h8 != nullptr && g.w.h8 != nullptr; }
+// C8 pair kernel tile width: 256-wide tiles when they still fill the chip, else 128-wide (two TMEM
+// buffer pairs, epilogue overlapped)
+long long c8_pair_tiles(const ConvGeom& g, int bn) {
+  return (((long long)g.tilesX * g.tilesY * g.tilesB + 1) / 2) * (g.w.N / bn) * g.nGroups;
+}
+int c8_block_n(const ConvGeom& g) {
+  const bool wide = g.w.N % 256 == 0 && g.nSplit % 256 == 0 && c8_pair_tiles(g, 256) >= 74;
+  return wide ? 256 : 128;
+}
 cudaError_t launch_conv_any(Run& r, ConvGeom& g) {
   if (is_c8(g)) {
     g.c8OutScale = 1.f;
@@ -400,12 +411,8 @@ cudaError_t launch_conv_any(Run& r, ConvGeom& g) {
     g.c8RecA = g.a.rec;
     g.c8RecW = g.w.rec;
     g.mainBf16 = 0;
-    g.kSplit = 1;
-    if (r.rc.backend != 0) return launch_conv_c8_simt(g, r.rc.stream);
-    // 256-wide tiles when they still fill the chip, else 128-wide (two TMEM buffer pairs)
-    const long long mPairs = ((long long)g.tilesX * g.tilesY * g.tilesB + 1) / 2;
-    const bool wide = g.w.N % 256 == 0 && g.nSplit % 256 == 0 && mPairs * (g.w.N / 256) * g.nGroups >= 74;
-    return launch_conv_c8(g, wide ? 256 : 128, r.rc.stream);
+    if (r.rc.backend != 0) { g.kSplit = 1; return launch_conv_c8_simt(g, r.rc.stream); }
+    return launch_conv_c8(g, c8_block_n(g), r.rc.stream);
   }
   if ((g.a.h8 != nullptr) != (g.w.h8 != nullptr)) {
     set_error("conv: activation and weight operands disagree on the C8 format");
@@ -417,8 +424,8 @@ cudaError_t launch_conv_any(Run& r, ConvGeom& g) {
 // Split-K (tensor-core backend only): when the planner finds that K-slices fill the SM waves
 // better, zero-fill the `splitFloats` floats at g.out and let the slices add into it.
 void plan_split(Run& r, ConvGeom& g, long long splitFloats, double minGain, const char* what) {
-  if (!r.ok || splitFloats <= 0 || r.rc.backend != 0 || is_c8(g)) return;
-  const int s = conv_plan_ksplit(g, minGain);
+  if (!r.ok || splitFloats <= 0 || r.rc.backend != 0) return;
+  const int s = is_c8(g) ? plan_ksplit_waves(c8_pair_tiles(g, c8_block_n(g)), 74, g, minGain) : conv_plan_ksplit(g, minGain);
   if (s <= 1) return;
   r.check(cudaMemsetAsync(g.out, 0, (size_t)splitFloats * sizeof(float), r.rc.stream), what);
   g.kSplit = s;
@@ -618,7 +625,12 @@ void run_conv_in(Run& r, const ActOperand& a, const WgtOperand& w, const TapList
     // layers a little over one SM wave (Discriminator ds3: 80 pair tiles on 74 pairs): split-K plus
     // one stand-alone statistics pass over z beats paying a second, nearly empty round
     ConvGeom g = conv_geom(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0);
-    if (r.ok && !is_c8(g) && conv_plan_ksplit(g, 0.2) > 1) fused = false;
+    if (r.ok) {
+      ConvGeom gw = g;
+      gw.w = w;   // conv_geom copied it already; operands decide the kernel family
+      const int sp = is_c8(gw) ? plan_ksplit_waves(c8_pair_tiles(gw, c8_block_n(gw)), 74, gw, 0.2) : conv_plan_ksplit(gw, 0.2);
+      if (sp > 1) fused = false;
+    }
   }
   if (!fused && r.rc.backend == 0 && splitFloats > 0) {
     run_conv(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0, nullptr, nullptr, splitFloats);
@@ -779,17 +791,17 @@ GenSaved plan_gen_saved(const GenDims& d, void* base, std::vector<SavedEntry>* l
   s.A1 = take_pair(a, parity_elems(d.B, 40, d.W1, 256), "A1", c8, rec);
   s.z2 = a.takeT<float>(M2 * 512, "z2");
   s.st2 = take_stat(a, d.B * 512);
-  s.A2 = take_pair(a, M2 * 256, "A2", c8, rec);
+  s.A2 = take_pair(a, M2 * 256, "A2");   // feeds the 2D->1D flatten layer (split-bf16, like the whole 1-D trunk)
   s.z3 = a.takeT<float>(L * 256, "z3");
   s.st3 = take_stat(a, d.B * 256);
   for (int i = 0; i < 7; ++i) {
     s.Rf[i] = a.takeT<float>(L * 256, i == 0 ? "R0" : (i == 6 ? "R6" : nullptr));
-    s.R[i] = take_pair(a, L * 256, nullptr, c8, rec);
+    s.R[i] = take_pair(a, L * 256, nullptr);
   }
   for (int i = 0; i < 6; ++i) {
     s.z4[i] = a.takeT<float>(L * 1024, i == 0 ? "z4_0" : nullptr);
     s.st4[i] = take_stat(a, d.B * 1024);
-    s.H[i] = take_pair(a, L * 512, nullptr, c8, rec);
+    s.H[i] = take_pair(a, L * 512, nullptr);
     s.z5[i] = a.takeT<float>(L * 256, i == 0 ? "z5_0" : nullptr);
     s.st5[i] = take_stat(a, d.B * 256);
   }
@@ -1020,7 +1032,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
     run_wgrad(r, plain_op(dz7, B, 20, d.W2, 1024), plain_op(s.U0, B, 20, d.W2, 256),
               k55f, nullptr, B, 20, d.W2, gW(G_UP1), "G up1 wgrad");
   // ---- 1D -> 2D
-  BfPair dz6 = dz_pair(M2 * 256);
+  BfPair dz6 = take_pair(a, M2 * 256, nullptr);
   run_bwd(r, mk_bwd(kINOnly, s.z6, 256, 1, d.W2, s.st6, 256, W.gamma(nm[GN_1DTO2D]), W.beta(nm[GN_1DTO2D]), 20,
                     gbuf(dU0, B * 20, 1, d.W2, 256, 0), tp, gGa(GN_1DTO2D), gBe(GN_1DTO2D), dz6, nullptr),
           "G 1dto2d bwd");
@@ -1046,8 +1058,8 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   for (int i = 5; i >= 0; --i) {
     // one dz pair per block: the weight-gradient GEMMs read them from the side stream while the
     // main stream already works on the next block
-    BfPair dz5 = dz_pair(L * 256);
-    BfPair dz4 = dz_pair(L * 1024);
+    BfPair dz5 = take_pair(a, L * 256, nullptr);
+    BfPair dz4 = take_pair(a, L * 1024, nullptr);
     const ConvDesc& ca = cv[G_RES0 + 2 * i];
     const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
     const int na = GN_RES0 + 2 * i, nb = GN_RES0 + 2 * i + 1;
@@ -1068,7 +1080,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
                 k3f, nullptr, B, 1, d.W2, gblob + ca.gW, "G res wgrad a");
   }
   // ---- 2D -> 1D
-  BfPair dz3 = dz_pair(L * 256);
+  BfPair dz3 = take_pair(a, L * 256, nullptr);
   run_bwd(r, mk_bwd(kINOnly, s.z3, 256, 1, d.W2, s.st3, 256, W.gamma(nm[GN_2DTO1D]), W.beta(nm[GN_2DTO1D]), 1,
                     gbuf(dR[0], B, 1, d.W2, 256, 0), tp, gGa(GN_2DTO1D), gBe(GN_2DTO1D), dz3, nullptr),
           "G 2dto1d bwd");

@@ -10,7 +10,8 @@
 // 64-channel boxes with the 64B swizzle when a CTA's half of the channel tile is only 64 wide
 // (CTILE = 128).  kind::f8f6f4 consumes K = 32 positions per instruction.
 //
-// STATUS (round 1): kernel-level only (mcgvc_debug_wgrad_c8), see conv_c8.cu.
+// Selected with mcgvc_set_precision(MCGVC_PRECISION_C8), see conv_c8.cu; mcgvc_debug_wgrad_c8 reaches it
+// in isolation.
 #include "gemm_types.cuh"
 #include "ptx.cuh"
 

@@ -15,7 +15,7 @@ pkg = mcgvc_loader.load()
 eng = pkg.engine
 mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-eng.set_precision({"parity": eng.PRECISION_PARITY, "fast": eng.PRECISION_FAST, "mixed": eng.PRECISION_MIXED}[mode])
+eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "fast": eng.PRECISION_FAST, "mixed": eng.PRECISION_MIXED}[mode])
 torch.manual_seed(0)
 G = pkg.Generator().to("cuda")
 x = torch.randn(B, 80, 64, device="cuda")

@@ -57,7 +57,7 @@ def main():
         if ev.device_type != torch.autograd.DeviceType.CUDA:
             continue
         dur = float(ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total)
-        name = ev.name
+        name = ev.name.replace("(anonymous namespace)::", "")
         short = name.split("(")[0]
         if short.startswith("void "):
             short = short[5:]
