@@ -401,7 +401,9 @@ long long c8_pair_tiles(const ConvGeom& g, int bn) {
   return (((long long)g.tilesX * g.tilesY * g.tilesB + 1) / 2) * (g.w.N / bn) * g.nGroups;
 }
 int c8_block_n(const ConvGeom& g) {
-  const bool wide = g.w.N % 256 == 0 && g.nSplit % 256 == 0 && c8_pair_tiles(g, 256) >= 74;
+  static int minWide = -1;   // MCGVC_C8_WIDE_MIN: fewest 256-wide pair tiles for which the wide kernel is used
+  if (minWide < 0) { const char* e = getenv("MCGVC_C8_WIDE_MIN"); minWide = e ? atoi(e) : 74; }
+  const bool wide = g.w.N % 256 == 0 && g.nSplit % 256 == 0 && c8_pair_tiles(g, 256) >= minWide;
   return wide ? 256 : 128;
 }
 cudaError_t launch_conv_any(Run& r, ConvGeom& g) {
