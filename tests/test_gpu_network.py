@@ -316,6 +316,27 @@ def test_c8_precision_mode_meets_the_parity_gate(env):
         e.set_precision(e.PRECISION_PARITY)
 
 
+@pytest.mark.parametrize("B,T", [(2, 17), (1, 100), (2, 512), (64, 64)])
+def test_c8_forward_shapes_and_lengths(env, B, T):
+    """C8 mode over the shapes the reference meets: short and odd frame counts (zero-padded parity
+    planes), config 5's long utterances, and the full batch (CTA-pair tiles, several waves).
+    (Below ~16 frames the network itself is ill-conditioned -- InstanceNorm over 2-3 positions -- and
+    every mode, the fp32 reference included, is only comparable through test_tiny_frame_counts.)"""
+    e = env["pkg"].engine
+    x, m, _, _ = O.synthetic_batch(B, T, seed=600 + T, max_mask_len=min(25, max(2, T // 3)))
+    e.set_precision(e.PRECISION_C8)
+    try:
+        with torch.no_grad():
+            y = env["G"](x.cuda(), m.cuda())
+            d = env["D"](x.cuda())
+    finally:
+        e.set_precision(e.PRECISION_PARITY)
+    k = min(B, 2)
+    assert rel(y[:k], O.generator_forward(env["gs"], x[:k], m[:k])) < TOL
+    assert rel(d[:k], O.discriminator_forward(env["ds"], x[:k])) < TOL
+    assert torch.isfinite(y).all() and torch.isfinite(d).all()
+
+
 def test_c8_train_steps_track_the_parity_mode(env):
     """Two full train steps at batch 16 in C8 mode (pair kernels, dynamic dz scales, C8 weight-gradient
     GEMMs) against the same steps in the default mode: losses and updated weights agree closely."""

@@ -44,7 +44,11 @@ def cpu_time(fn, warm=1, reps=3):
 
 
 def main():
-    out = {"cores": os.cpu_count(), "precision": "parity"}
+    mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
+    eng.lib()
+    eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "mixed": eng.PRECISION_MIXED,
+                       "fast": eng.PRECISION_FAST}[mode])
+    out = {"cores": os.cpu_count(), "precision": mode}
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
     G, D = pkg.Generator().cuda(), pkg.Discriminator().cuda()
