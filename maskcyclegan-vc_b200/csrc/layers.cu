@@ -1027,13 +1027,61 @@ __global__ void pack_amax_table_kernel(const __grid_constant__ PackTable t, cons
 __device__ __forceinline__ uint8_t to_e4m3(float v) {
   return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
 }
-__global__ void pack_weights_table_kernel(const __grid_constant__ PackTable t,
-                                          const float* __restrict__ params,
-                                          __nv_bfloat16* __restrict__ packed, float* __restrict__ f32) {
+// One reference value -> its planes in the forward layout (offset fo) and the data-gradient layout
+// (offset dO, when the entry has one): split-bf16, or fp16 + 2 x e4m3 for C8 entries.
+__device__ __forceinline__ void pack_store(const PackEntry& e, __nv_bfloat16* packed, float v, float E,
+                                           long long fo, long long dO, bool fwd, bool dgrad) {
+  if (e.c8) {
+    __half* p16 = reinterpret_cast<__half*>(packed);
+    uint8_t* p8 = reinterpret_cast<uint8_t*>(packed);
+    const __half h = __float2half_rn(v);
+    const float hf = __half2float(h);
+    const uint8_t h8 = to_e4m3(hf * E), l8 = to_e4m3((v - hf) * E * 2048.f);
+    if (fwd) {
+      p16[e.fHi + fo] = h;
+      p8[2LL * e.fLo + fo] = h8;
+      p8[2LL * e.fLo + e.fElems + fo] = l8;
+    }
+    if (dgrad && e.dHi >= 0) {
+      p16[e.dHi + dO] = h;
+      p8[2LL * e.dLo + dO] = h8;
+      p8[2LL * e.dLo + e.dElems + dO] = l8;
+    }
+    return;
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  if (fwd) {
+    packed[e.fHi + fo] = h;
+    packed[e.fLo + fo] = l;
+  }
+  if (dgrad && e.dHi >= 0) {
+    packed[e.dHi + dO] = h;
+    packed[e.dLo + dO] = l;
+  }
+}
+
+// Tiled path for the plain [N][C][T] -> [T][N'][C] / [T][C][N'] re-layouts (kPackStd / kPackShuffle: all
+// the large tensors).  A block stages a 16 (engine rows n') x 16 (channels) x T tile of the reference
+// tensor in shared memory with coalesced reads (each n' row of the tile is one contiguous run of 16*T
+// floats), then writes it tap by tap: 16 lanes along c for the forward layout and 16 lanes along n'
+// for the data-gradient layout, so every store instruction fills whole 32-byte sectors instead of
+// scattering 2-byte elements.
+constexpr int kPackTile = 16;
+constexpr int kPackMaxT = 25;
+__device__ __forceinline__ bool pack_tiled_ok(const PackEntry& e) {
+  return (e.kind == kPackStd || e.kind == kPackShuffle) && e.T <= kPackMaxT && e.C % kPackTile == 0 &&
+         e.N % (4 * kPackTile) == 0;
+}
+
+__global__ void __launch_bounds__(256) pack_weights_table_kernel(const __grid_constant__ PackTable t,
+                                                                 const float* __restrict__ params,
+                                                                 __nv_bfloat16* __restrict__ packed,
+                                                                 float* __restrict__ f32) {
+  __shared__ float tile[kPackTile * (kPackTile * kPackMaxT + 1)];
   const PackEntry& e = t.e[blockIdx.y];
   const PackArgs a = entry_args(e);
   const float* ref = params + e.refOff;
-  const long long total = (long long)e.N * e.C * e.T;
   float E = 1.f;
   if (e.c8) {
     const float amax = __uint_as_float(reinterpret_cast<const unsigned int*>(f32)[e.rec + 2]);
@@ -1048,8 +1096,39 @@ __global__ void pack_weights_table_kernel(const __grid_constant__ PackTable t,
     f32[t.actRec + 0] = 1.f;     // activations: S = 1
     f32[t.actRec + 1] = 0.5f;    //              E = 2
   }
-  __half* p16 = reinterpret_cast<__half*>(packed);
-  uint8_t* p8 = reinterpret_cast<uint8_t*>(packed);
+  if (pack_tiled_ok(e)) {
+    const int T = e.T, rowLen = kPackTile * T, pitch = rowLen + 1;
+    const int cTiles = e.C / kPackTile, nTiles = e.N / kPackTile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int quarter = e.N >> 2;
+    for (int tl = blockIdx.x; tl < cTiles * nTiles; tl += gridDim.x) {
+      const int c0 = (tl % cTiles) * kPackTile;
+      const int np0 = (tl / cTiles) * kPackTile;          // engine row (before nOffset) of the tile's first row
+      // reference row of engine row np: identity, or the PixelShuffle grouping n' = (n%4)*(N/4) + n/4
+      auto ref_row = [&](int np) { return e.kind == kPackShuffle ? 4 * (np % quarter) + np / quarter : np; };
+      __syncthreads();
+      for (int r = warp; r < kPackTile; r += 8) {
+        const float* src = ref + ((long long)ref_row(np0 + r) * e.C + c0) * T;
+        for (int i = lane; i < rowLen; i += 32) tile[r * pitch + i] = src[i];
+      }
+      __syncthreads();
+      const int hiIdx = threadIdx.x >> 4, loIdx = threadIdx.x & 15;
+      for (int tt = 0; tt < T; ++tt) {
+        {   // forward layout: lanes along c
+          const int r = hiIdx, cl = loIdx;
+          const long long fo = ((long long)tt * e.Np + np0 + r + e.nOffset) * e.Cp + c0 + cl;
+          pack_store(e, packed, tile[r * pitch + cl * T + tt], E, fo, 0, true, false);
+        }
+        if (e.dHi >= 0) {   // data-gradient layout: lanes along n'
+          const int cl = hiIdx, r = loIdx;
+          const long long dO = ((long long)tt * e.Cd + c0 + cl) * e.Np + np0 + r + e.nOffset;
+          pack_store(e, packed, tile[r * pitch + cl * T + tt], E, 0, dO, false, true);
+        }
+      }
+    }
+    return;
+  }
+  const long long total = (long long)e.N * e.C * e.T;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int tt = (int)(idx % e.T);
@@ -1057,33 +1136,11 @@ __global__ void pack_weights_table_kernel(const __grid_constant__ PackTable t,
     const int n = (int)(idx / ((long long)e.T * e.C));
     int tp, np, cp;
     pack_map(a, n, c, tt, &tp, &np, &cp);
-    const float v = ref[idx];
     const long long fo = ((long long)tp * e.Np + np) * e.Cp + cp;
     const long long dO = (e.kind == kPack1dTo2d)
                              ? ((long long)(np / 256) * e.Cd + cp) * 256 + (np % 256)
                              : ((long long)tp * e.Cd + cp) * e.Np + np;
-    if (e.c8) {
-      const __half h = __float2half_rn(v);
-      const float hf = __half2float(h);
-      const uint8_t h8 = to_e4m3(hf * E), l8 = to_e4m3((v - hf) * E * 2048.f);
-      p16[e.fHi + fo] = h;
-      p8[2LL * e.fLo + fo] = h8;
-      p8[2LL * e.fLo + e.fElems + fo] = l8;
-      if (e.dHi >= 0) {
-        p16[e.dHi + dO] = h;
-        p8[2LL * e.dLo + dO] = h8;
-        p8[2LL * e.dLo + e.dElems + dO] = l8;
-      }
-      continue;
-    }
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-    packed[e.fHi + fo] = h;
-    packed[e.fLo + fo] = l;
-    if (e.dHi >= 0) {
-      packed[e.dHi + dO] = h;
-      packed[e.dLo + dO] = l;
-    }
+    pack_store(e, packed, ref[idx], E, fo, dO, true, true);
   }
 }
 cudaError_t launch_pack_weights_table(const PackTable& t, const float* params, __nv_bfloat16* packed,
@@ -1099,13 +1156,35 @@ cudaError_t launch_pack_weights_table(const PackTable& t, const float* params, _
   pack_weights_table_kernel<<<grid, 256, 0, s>>>(t, params, packed, packedF32);
   return launched();
 }
-__global__ void unpack_wgrads_table_kernel(const __grid_constant__ PackTable t,
-                                           const float* __restrict__ gblob,
-                                           float* __restrict__ gradFlat) {
+__global__ void __launch_bounds__(256) unpack_wgrads_table_kernel(const __grid_constant__ PackTable t,
+                                                                  const float* __restrict__ gblob,
+                                                                  float* __restrict__ gradFlat) {
+  __shared__ float tile[kPackTile * (kPackTile * kPackMaxT + 1)];
   const PackEntry& e = t.e[blockIdx.y];
   const PackArgs a = entry_args(e);
   const float* dw = gblob + e.gW;
   float* dref = gradFlat + e.refOff;
+  if (pack_tiled_ok(e)) {   // mirror of the tiled pack path: 64-byte gathers along c, coalesced += along (c, t)
+    const int T = e.T, rowLen = kPackTile * T, pitch = rowLen + 1;
+    const int cTiles = e.C / kPackTile, nTiles = e.N / kPackTile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int quarter = e.N >> 2;
+    for (int tl = blockIdx.x; tl < cTiles * nTiles; tl += gridDim.x) {
+      const int c0 = (tl % cTiles) * kPackTile;
+      const int np0 = (tl / cTiles) * kPackTile;
+      auto ref_row = [&](int np) { return e.kind == kPackShuffle ? 4 * (np % quarter) + np / quarter : np; };
+      __syncthreads();
+      const int r = threadIdx.x >> 4, cl = threadIdx.x & 15;
+      for (int tt = 0; tt < T; ++tt)
+        tile[r * pitch + cl * T + tt] = dw[((long long)tt * e.Np + np0 + r + e.nOffset) * e.Cp + c0 + cl];
+      __syncthreads();
+      for (int rr = warp; rr < kPackTile; rr += 8) {
+        float* dst = dref + ((long long)ref_row(np0 + rr) * e.C + c0) * T;
+        for (int i = lane; i < rowLen; i += 32) dst[i] += tile[rr * pitch + i];
+      }
+    }
+    return;
+  }
   const long long total = (long long)e.N * e.C * e.T;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
