@@ -91,6 +91,31 @@ int mcgvc_graph_stats(long long* captures, long long* replays);
 int mcgvc_profile_enable(int on);
 int mcgvc_profile_collect(double* out6);
 
+/* Device-side data feed: replaces the crop + frame-in-fill mask work of
+ * dataset/vc_dataset.py:44-56 and the host->device copies of mask_cyclegan_vc/train.py:187-190.
+ * pool: every utterance as a (80, T_u) row-major float array, back to back, on the device; utt_off[u]
+ * = float offset of utterance u, utt_frames[u] = T_u.  sel = int[4][batch] on the device: utterance,
+ * crop start (0 <= start <= T_u - n_frames), mask start, mask size (mask_start + mask_size <= n_frames).
+ * Writes x[batch][80][n_frames] (the crop) and mask[batch][80][n_frames] (0 inside the mask span, else
+ * 1).  A selection outside those bounds never reads outside the pool (its sample comes out as zeros);
+ * bad_count (device int, may be null) receives how many there were. */
+int mcgvc_crop_mask(const float* pool, const long long* utt_off, const int* utt_frames, int n_utts,
+                    const int* sel, int batch, int n_frames, float* x, float* mask, int* bad_count,
+                    void* stream);
+
+/* Loss tail: one weighted term of the generator / discriminator losses of
+ * mask_cyclegan_vc/train.py:219-237 and :276-294, accumulated into the device scalar *total (which the
+ * caller zero-fills once per phase).  L1: total += weight * mean|a - b| (cycle / identity terms, :219-224);
+ * LSGAN: total += weight * mean (target - a)^2 (adversarial terms, :227-232 and :276-288; b unused).
+ * mcgvc_loss_term_grad writes d total / d a for one term (grad_total: device scalar with the upstream
+ * gradient, or null for 1). */
+#define MCGVC_LOSS_L1 0
+#define MCGVC_LOSS_LSGAN 1
+int mcgvc_loss_term(const float* a, const float* b, long long n, int kind, float target, float weight,
+                    float* total, void* stream);
+int mcgvc_loss_term_grad(const float* a, const float* b, long long n, int kind, float target, float weight,
+                         const float* grad_total, float* grad_a, void* stream);
+
 /* Introspection for layer-by-layer parity tests: the index-th named tensor inside the saved blob.
  * Returns 0 and fills name/offset/bytes, or 1 when index is past the end. */
 int mcgvc_saved_layout(int model, int batch, int frames, int index, char* name, int name_cap,

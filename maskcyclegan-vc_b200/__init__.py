@@ -8,3 +8,5 @@ from . import engine  # noqa: F401
 from .model import Discriminator, Generator, is_lean, set_lean  # noqa: F401
 from .parallel import GradSync, shard_batch  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .datafeed import DeviceVCDataFeed, draw_selection  # noqa: F401
+from . import losses  # noqa: F401

@@ -288,7 +288,6 @@ struct Weights {   // views into the packed blob
         f32(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + md.packedBf16 * 2)),
         c8(c8mode), d(md) {}
   bool is_c8(const ConvDesc& c) const { return c8 && c.c8Eligible; }
-  const float* act_rec() const { return f32 + d.actRec; }
   // operand over the forward layout [T][N][K] / the data-gradient layout viewed as [T][N=Cd][K=Np]
   // (or any other (K, N, T) view of the same storage, for the two flatten layers)
   WgtOperand view(const ConvDesc& c, bool dgrad, int K, int N, int T) const {

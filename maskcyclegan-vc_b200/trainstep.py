@@ -26,8 +26,11 @@ def build_optimizers(models, g_lr=2e-4, d_lr=1e-4):
     return g_opt, d_opt
 
 
-def train_step(models, g_opt, d_opt, batch, cycle_lambda=10.0, identity_lambda=5.0):
-    """Returns (g_loss, d_loss) as 0-dim tensors (no host sync here)."""
+def train_step(models, g_opt, d_opt, batch, cycle_lambda=10.0, identity_lambda=5.0, fused_losses=False):
+    """Returns (g_loss, d_loss) as 0-dim tensors (no host sync here).  fused_losses=True evaluates the
+    loss tail with the engine's one-launch-per-term kernels (losses.py) instead of torch ops."""
+    if fused_losses:
+        from . import losses as fl
     G_A2B, G_B2A, D_A, D_B, D_A2, D_B2 = models
     real_A, mask_A, real_B, mask_B = batch
     # ---- generator phase (train.py:195-242)
@@ -43,11 +46,15 @@ def train_step(models, g_opt, d_opt, batch, cycle_lambda=10.0, identity_lambda=5
     d_fake_B = D_B(fake_B)
     d_fake_cycle_A = D_A2(cycle_A)
     d_fake_cycle_B = D_B2(cycle_B)
-    cycle_loss = torch.mean(torch.abs(real_A - cycle_A)) + torch.mean(torch.abs(real_B - cycle_B))
-    identity_loss = torch.mean(torch.abs(real_A - identity_A)) + torch.mean(torch.abs(real_B - identity_B))
-    g_loss = torch.mean((1 - d_fake_B) ** 2) + torch.mean((1 - d_fake_A) ** 2) + \
-        torch.mean((1 - d_fake_cycle_B) ** 2) + torch.mean((1 - d_fake_cycle_A) ** 2) + \
-        cycle_lambda * cycle_loss + identity_lambda * identity_loss
+    if fused_losses:
+        g_loss = fl.generator_loss(real_A, real_B, cycle_A, cycle_B, identity_A, identity_B, d_fake_A, d_fake_B,
+                                   d_fake_cycle_A, d_fake_cycle_B, cycle_lambda, identity_lambda)
+    else:
+        cycle_loss = torch.mean(torch.abs(real_A - cycle_A)) + torch.mean(torch.abs(real_B - cycle_B))
+        identity_loss = torch.mean(torch.abs(real_A - identity_A)) + torch.mean(torch.abs(real_B - identity_B))
+        g_loss = torch.mean((1 - d_fake_B) ** 2) + torch.mean((1 - d_fake_A) ** 2) + \
+            torch.mean((1 - d_fake_cycle_B) ** 2) + torch.mean((1 - d_fake_cycle_A) ** 2) + \
+            cycle_lambda * cycle_loss + identity_lambda * identity_loss
     g_opt.zero_grad()
     d_opt.zero_grad()
     g_loss.backward()
@@ -67,11 +74,15 @@ def train_step(models, g_opt, d_opt, batch, cycle_lambda=10.0, identity_lambda=5
     d_fake_B = D_B(generated_B)
     cycled_A = G_B2A(generated_B, torch.ones_like(generated_B))
     d_cycled_A = D_A2(cycled_A)
-    d_loss_A = (torch.mean((1 - d_real_A) ** 2) + torch.mean((0 - d_fake_A) ** 2)) / 2.0
-    d_loss_B = (torch.mean((1 - d_real_B) ** 2) + torch.mean((0 - d_fake_B) ** 2)) / 2.0
-    d_loss_A_2nd = (torch.mean((1 - d_real_A2) ** 2) + torch.mean((0 - d_cycled_A) ** 2)) / 2.0
-    d_loss_B_2nd = (torch.mean((1 - d_real_B2) ** 2) + torch.mean((0 - d_cycled_B) ** 2)) / 2.0
-    d_loss = (d_loss_A + d_loss_B) / 2.0 + (d_loss_A_2nd + d_loss_B_2nd) / 2.0
+    if fused_losses:
+        d_loss = fl.discriminator_loss(d_real_A, d_real_B, d_real_A2, d_real_B2, d_fake_A, d_fake_B, d_cycled_A,
+                                       d_cycled_B)
+    else:
+        d_loss_A = (torch.mean((1 - d_real_A) ** 2) + torch.mean((0 - d_fake_A) ** 2)) / 2.0
+        d_loss_B = (torch.mean((1 - d_real_B) ** 2) + torch.mean((0 - d_fake_B) ** 2)) / 2.0
+        d_loss_A_2nd = (torch.mean((1 - d_real_A2) ** 2) + torch.mean((0 - d_cycled_A) ** 2)) / 2.0
+        d_loss_B_2nd = (torch.mean((1 - d_real_B2) ** 2) + torch.mean((0 - d_cycled_B) ** 2)) / 2.0
+        d_loss = (d_loss_A + d_loss_B) / 2.0 + (d_loss_A_2nd + d_loss_B_2nd) / 2.0
     g_opt.zero_grad()
     d_opt.zero_grad()
     d_loss.backward()

@@ -207,6 +207,22 @@ def synthetic_batch(B, T, seed, max_mask_len=25):
     return real_A, mask_A, real_B, mask_B
 
 
+def crop_and_mask(dataset, sel, n_frames=64):
+    """numpy restatement of the per-sample crop + frame-in-fill mask of the reference's training
+    dataset (dataset/vc_dataset.py:44-56) for given draws: sel = int[4][B] (utterance, crop start,
+    mask start, mask size).  Returns (x, mask), each (B, 80, n_frames) float32."""
+    import numpy as np
+    xs, ms = [], []
+    for u, start, mstart, msize in zip(*[list(r) for r in sel]):
+        data = np.asarray(dataset[u])
+        crop = data[:, start:start + n_frames]                 # vc_dataset.py:48-49,55
+        mask = np.ones_like(crop)                              # vc_dataset.py:53
+        mask[:, mstart:mstart + msize] = 0.                    # vc_dataset.py:54
+        xs.append(crop)
+        ms.append(mask)
+    return np.array(xs, dtype=np.float32), np.array(ms, dtype=np.float32)
+
+
 def train_step(G_A2B, G_B2A, D_A, D_B, D_A2, D_B2, g_opt, d_opt, batch,
                cycle_lambda=10.0, identity_lambda=5.0):
     """One optimisation step with the semantics of train.py:186-299 for any modules that expose
