@@ -603,17 +603,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           if (NPASS == 3) {
             const uint64_t dAl = ptx::umma_smem_desc_sw128(sAl + k * 32, 0, 1024);
             const uint64_t dBl = ptx::umma_smem_desc_sw128(sBl + k * 32, 0, 1024);
-            if (g.timingProbe == 0) {
-              ptx::umma_bf16_2cta(d_tmem, dAh, dBl, idesc, 1);
-              ptx::umma_bf16_2cta(d_tmem, dAl, dBh, idesc, 1);
-            } else if (k < 2) {
-              // TIMING PROBE ONLY (numerically meaningless): the two correction products issued as
-              // e4m3 MMAs over half of the staged bytes -- the instruction / smem / power mix a
-              // bf16 main pass + 8-bit correction passes scheme would have
-              constexpr uint32_t idesc8 = ptx::umma_idesc_e4m3(2 * kTileM, BLOCK_N);
-              ptx::umma_f8_2cta(d_tmem, dAh, dBl, idesc8, 1);
-              ptx::umma_f8_2cta(d_tmem, dAl, dBh, idesc8, 1);
-            }
+            ptx::umma_bf16_2cta(d_tmem, dAh, dBl, idesc, 1);
+            ptx::umma_bf16_2cta(d_tmem, dAl, dBh, idesc, 1);
           }
         }
         ptx::umma_commit_2cta(&empty[stage], 0x3);
@@ -707,14 +698,8 @@ static cudaError_t launch_conv_tc2_t(const ConvGeom& g, cudaStream_t stream) {
   const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups * (g.kSplit > 1 ? g.kSplit : 1);
   const int maxPairs = num_sms() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
-  ConvGeom gl = g;
-  {
-    static int probe = -1;   // MCGVC_F8_TIMING_PROBE=1: tools/layer_bench.py only, results are garbage
-    if (probe < 0) { const char* e = getenv("MCGVC_F8_TIMING_PROBE"); probe = e ? atoi(e) : 0; }
-    gl.timingProbe = probe;
-  }
   profile_begin(0, g.algoFlops, stream);
-  conv_tc2_kernel<BLOCK_N, NPASS><<<2 * pairs, 256, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, gl);
+  conv_tc2_kernel<BLOCK_N, NPASS><<<2 * pairs, 256, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
   profile_end(stream);
   return launched();
 }

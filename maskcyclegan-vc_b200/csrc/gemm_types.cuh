@@ -76,7 +76,6 @@ struct ConvGeom {
   float c8OutScale, c8CorrScale;
   const float* c8RecA;  // device-side scale records {1/S, 1/E} of the two operands (null: host multipliers only)
   const float* c8RecW;
-  int timingProbe;      // set from MCGVC_F8_TIMING_PROBE by the CTA-pair launcher (measurement hack, see there)
 };
 
 // Weight-gradient GEMM:  dW[w_t][n][c] += sum over positions (b,y,x) in this CTA's K-slice of
