@@ -128,6 +128,9 @@ int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY,
                      int oB, int nTaps, const int8_t* taps4, float* out, long long sB,
                      long long sY, long long sX, int nSplit, long long sNhi, const float* bias,
                      const float* addsrc, int nPass, int backend, int blockN, void* stream);
+/* Host-side split-K planner for a convolution geometry (output grid oB x oY x oX, C input channels, N
+ * output columns, nTaps filter taps) on the split-bf16 kernels; needs no GPU (assumes 148 SMs then). */
+int mcgvc_debug_plan_ksplit(int oB, int oY, int oX, int C, int N, int nSplit, int nTaps, double minGain);
 /* split-K factor used by the following mcgvc_debug_conv calls on the tensor-core backends: every tile's
  * k-blocks run as `k` work items that are added into `out` (which the caller zero-fills); 1 = off. */
 int mcgvc_debug_set_conv_ksplit(int k);

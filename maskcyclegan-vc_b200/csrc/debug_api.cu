@@ -18,6 +18,22 @@ int mcgvc_debug_set_conv_ksplit(int k) {
   return 0;
 }
 
+/* Split-K factor the planner picks for a convolution geometry on the split-bf16 kernels (host logic only:
+ * works without a GPU, assuming 148 SMs). */
+int mcgvc_debug_plan_ksplit(int oB, int oY, int oX, int C, int N, int nSplit, int nTaps, double minGain) {
+  ConvGeom g{};
+  g.a.C = C; g.w.K = C; g.w.N = N;
+  g.oX = oX; g.oY = oY; g.oB = oB;
+  if (!choose_box(oB, oY, oX, kTileM, &g.BX, &g.BY, &g.BB)) return -1;
+  g.tilesX = (oX + g.BX - 1) / g.BX;
+  g.tilesY = (oY + g.BY - 1) / g.BY;
+  g.tilesB = (oB + g.BB - 1) / g.BB;
+  g.nTaps = nTaps; g.cBlocks = C / kBlockK;
+  g.nGroups = 1; g.grpTapStart[0] = 0; g.grpTapCount[0] = nTaps;
+  g.nSplit = nSplit;
+  return conv_plan_ksplit(g, minGain);
+}
+
 int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY, int aP, int aB,
                      const void* w_hi, const void* w_lo, int wK, int wN, int wT, int oX, int oY,
                      int oB, int nTaps, const int8_t* taps4, float* out, long long sB,

@@ -627,9 +627,7 @@ void run_conv_in(Run& r, const ActOperand& a, const WgtOperand& w, const TapList
     // one stand-alone statistics pass over z beats paying a second, nearly empty round
     ConvGeom g = conv_geom(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0);
     if (r.ok) {
-      ConvGeom gw = g;
-      gw.w = w;   // conv_geom copied it already; operands decide the kernel family
-      const int sp = is_c8(gw) ? plan_ksplit_waves(c8_pair_tiles(gw, c8_block_n(gw)), 74, gw, 0.2) : conv_plan_ksplit(gw, 0.2);
+      const int sp = is_c8(g) ? plan_ksplit_waves(c8_pair_tiles(g, c8_block_n(g)), 74, g, 0.2) : conv_plan_ksplit(g, 0.2);
       if (sp > 1) fused = false;
     }
   }

@@ -178,6 +178,14 @@ class _EngineModule(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------
+def _check_mode(ctx):
+    # packed weights and saved operands are laid out for the precision mode of the forward pass
+    # (split-bf16 planes vs. the C8 fp16 + e4m3 planes): a backward pass in another mode would misread them
+    if engine.get_precision() != ctx.precision:
+        raise engine.EngineError("precision mode changed between forward (%d) and backward (%d) of one graph"
+                                 % (ctx.precision, engine.get_precision()))
+
+
 class _GeneratorFn(Function):
     @staticmethod
     def forward(ctx, x, mask, anchor, module):
@@ -188,6 +196,7 @@ class _GeneratorFn(Function):
         ctx.module = module
         ctx.packed = packed
         ctx.saved = saved
+        ctx.precision = engine.get_precision()
         ctx.save_for_backward(mask)
         ctx.dims = (x.shape[0], x.shape[2])
         return out
@@ -197,6 +206,7 @@ class _GeneratorFn(Function):
         module = ctx.module
         B, T = ctx.dims
         (mask,) = ctx.saved_tensors
+        _check_mode(ctx)
         need_w = module._need_wgrad()
         dx = engine.generator_backward(ctx.packed, ctx.saved, mask, dout.contiguous(), B, T,
                                        ctx.needs_input_grad[0], module._gblob if need_w else None, need_w)
@@ -215,6 +225,7 @@ class _DiscriminatorFn(Function):
         ctx.module = module
         ctx.packed = packed
         ctx.saved = saved
+        ctx.precision = engine.get_precision()
         ctx.save_for_backward(out)
         ctx.dims = (x.shape[0], x.shape[2])
         return out
@@ -224,6 +235,7 @@ class _DiscriminatorFn(Function):
         module = ctx.module
         B, T = ctx.dims
         (out,) = ctx.saved_tensors
+        _check_mode(ctx)
         need_w = module._need_wgrad()
         dx = engine.discriminator_backward(ctx.packed, ctx.saved, out, dout.contiguous(), B, T,
                                            ctx.needs_input_grad[0], module._gblob if need_w else None, need_w)

@@ -98,3 +98,24 @@ def test_shim_overrides_reference_module_path():
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
     assert "shim" in out.splitlines()[0]
     assert "maskcyclegan_vc_b200" in out.splitlines()[1]
+
+
+def test_split_k_planner_fills_whole_waves(pkg):
+    """Host logic of the split-K planner (csrc/conv_igemm.cu), no GPU needed: layers a little over one
+    wave of the 74 CTA pairs get split, multi-wave and sub-wave layers are left alone."""
+    import ctypes
+    lib = pkg.engine.lib()
+    plan = lib.mcgvc_debug_plan_ksplit
+    plan.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double]
+    # up1 data gradient at batch 64: 20480 positions x 256 columns = 80 pair tiles, 25 taps x 16 k-blocks
+    assert plan(64, 20, 16, 1024, 256, 256, 25, 0.08) == 8
+    # up2 data gradient: 320 pair tiles (4.3 waves) -> 3 slices = 12.97 waves
+    assert plan(64, 40, 32, 512, 256, 256, 25, 0.08) == 3
+    # head data gradient: 1280 tiles of a 2-k-block GEMM -> nothing to gain
+    assert plan(64, 80, 64, 128, 128, 128, 1, 0.08) == 1
+    # 1-D trunk (sub-wave, latency-bound) and batch-1 layers are never split
+    assert plan(64, 1, 16, 1024, 256, 256, 3, 0.08) == 1
+    assert plan(1, 40, 32, 512, 256, 256, 25, 0.08) == 1
+    # a forward layer needs a bigger gain (it gives up the fused statistics): Discriminator ds3 qualifies
+    assert plan(64, 10, 8, 512, 1024, 1024, 9, 0.2) > 1
+
