@@ -426,7 +426,11 @@ cudaError_t launch_conv_any(Run& r, ConvGeom& g) {
 // better, zero-fill the `splitFloats` floats at g.out and let the slices add into it.
 void plan_split(Run& r, ConvGeom& g, long long splitFloats, double minGain, const char* what) {
   if (!r.ok || splitFloats <= 0 || r.rc.backend != 0) return;
-  const int s = is_c8(g) ? plan_ksplit_waves(c8_pair_tiles(g, c8_block_n(g)), 74, g, minGain) : conv_plan_ksplit(g, minGain);
+  // 256-wide C8 tiles cannot overlap their epilogue with the next item's MMAs (D1 + D2 fill TMEM), so
+  // the red.add epilogues of K slices land on the critical path: measured 124.9 -> 121.4 ms per step
+  // with split-K off in C8 mode.  Only the 128-wide (double-buffered) C8 tiles may split.
+  if (is_c8(g) && c8_block_n(g) == 256) return;
+  const int s = is_c8(g) ? plan_ksplit_waves(c8_pair_tiles(g, 128), 74, g, minGain) : conv_plan_ksplit(g, minGain);
   if (s <= 1) return;
   r.check(cudaMemsetAsync(g.out, 0, (size_t)splitFloats * sizeof(float), r.rc.stream), what);
   g.kSplit = s;
@@ -626,10 +630,7 @@ void run_conv_in(Run& r, const ActOperand& a, const WgtOperand& w, const TapList
     // layers a little over one SM wave (Discriminator ds3: 80 pair tiles on 74 pairs): split-K plus
     // one stand-alone statistics pass over z beats paying a second, nearly empty round
     ConvGeom g = conv_geom(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0);
-    if (r.ok) {
-      const int sp = is_c8(g) ? plan_ksplit_waves(c8_pair_tiles(g, c8_block_n(g)), 74, g, 0.2) : conv_plan_ksplit(g, 0.2);
-      if (sp > 1) fused = false;
-    }
+    if (r.ok && !is_c8(g) && conv_plan_ksplit(g, 0.2) > 1) fused = false;   // C8 layers keep the fused statistics
   }
   if (!fused && r.rc.backend == 0 && splitFloats > 0) {
     run_conv(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0, nullptr, nullptr, splitFloats);
