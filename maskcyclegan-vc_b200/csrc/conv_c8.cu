@@ -21,6 +21,7 @@
 #include "epilogue.cuh"
 #include "gemm_types.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 #include <cstdlib>
 #include <cuda_bf16.h>
@@ -28,62 +29,7 @@
 
 namespace mcgvc {
 
-// from conv_igemm.cu
-bool make_act_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int BX, int BY, int BB);
-bool make_wgt_tmap(CUtensorMap* m, const void* base, const WgtOperand& w, int boxN);
-
 namespace {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
-    set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
-    return nullptr;
-  }
-  fn = reinterpret_cast<EncodeTiledFn>(p);
-  return fn;
-}
-
-// 8-bit plane of an activation [B][P][Y][X][C]: box (64 B, BX, BY, 1, BB), 64-byte swizzle.
-bool make_act8_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int BX, int BY, int BB) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.X, (cuuint64_t)a.Y, (cuuint64_t)a.P, (cuuint64_t)a.B};
-  cuuint64_t strides[4];
-  strides[0] = (cuuint64_t)a.C;
-  strides[1] = strides[0] * a.X;
-  strides[2] = strides[1] * a.Y;
-  strides[3] = strides[2] * a.P;
-  cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)BX, (cuuint32_t)BY, 1u, (cuuint32_t)BB};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act8 C=%d X=%d Y=%d) failed: %d", a.C, a.X, a.Y, (int)r); return false; }
-  return true;
-}
-// 8-bit plane of the weights [T][N][K]: box (64 B, boxN, 1), 64-byte swizzle.
-bool make_wgt8_tmap(CUtensorMap* m, const void* base, const WgtOperand& w, int boxN) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)w.K, (cuuint64_t)w.N, (cuuint64_t)w.T};
-  cuuint64_t strides[2] = {(cuuint64_t)w.K, (cuuint64_t)w.K * w.N};
-  cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)boxN, 1u};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(wgt8 K=%d N=%d T=%d) failed: %d", w.K, w.N, w.T, (int)r); return false; }
-  return true;
-}
 
 // UMMA shared-memory descriptor, K-major, 64-byte swizzle: 8-row x 64-byte atoms, 512 B apart.
 __device__ __forceinline__ uint64_t umma_smem_desc_sw64(uint32_t smem_addr) {
@@ -343,8 +289,8 @@ cudaError_t launch_c8_t(const ConvGeom& g, cudaStream_t stream) {
   CUtensorMap tmA16, tmA8h, tmA8l, tmW16, tmW8h, tmW8l;
   if (!make_act_tmap(&tmA16, g.a.hi, g.a, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
   if (!make_wgt_tmap(&tmW16, g.w.hi, g.w, BLOCK_N / 2)) return cudaErrorInvalidValue;
-  if (!make_act8_tmap(&tmA8h, g.a.h8, g.a, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
-  if (!make_act8_tmap(&tmA8l, g.a.l8, g.a, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_plane8_tmap(&tmA8h, g.a.h8, g.a, kBlockK, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_plane8_tmap(&tmA8l, g.a.l8, g.a, kBlockK, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
   if (!make_wgt8_tmap(&tmW8h, g.w.h8, g.w, BLOCK_N / 2)) return cudaErrorInvalidValue;
   if (!make_wgt8_tmap(&tmW8l, g.w.l8, g.w, BLOCK_N / 2)) return cudaErrorInvalidValue;
   static bool attr_done[64] = {};

@@ -18,6 +18,7 @@
 #include "epilogue.cuh"
 #include "gemm_types.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 #include <atomic>
 #include <cstdarg>
@@ -154,6 +155,43 @@ bool make_wgt_tmap(CUtensorMap* m, const void* base, const WgtOperand& w, int bo
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(wgt K=%d N=%d T=%d boxN=%d) failed: %d", w.K, w.N, w.T, boxN,
               (int)r);
+    return false;
+  }
+  return true;
+}
+
+bool make_plane8_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int boxC, int BX, int BY, int BB) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.X, (cuuint64_t)a.Y, (cuuint64_t)a.P, (cuuint64_t)a.B};
+  cuuint64_t strides[4];
+  strides[0] = (cuuint64_t)a.C;
+  strides[1] = strides[0] * a.X;
+  strides[2] = strides[1] * a.Y;
+  strides[3] = strides[2] * a.P;
+  cuuint32_t box[5] = {(cuuint32_t)boxC, (cuuint32_t)BX, (cuuint32_t)BY, 1u, (cuuint32_t)BB};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, boxC == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(plane8 C=%d X=%d Y=%d box %d) failed: %d", a.C, a.X, a.Y, boxC, (int)r);
+    return false;
+  }
+  return true;
+}
+bool make_wgt8_tmap(CUtensorMap* m, const void* base, const WgtOperand& w, int boxN) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)w.K, (cuuint64_t)w.N, (cuuint64_t)w.T};
+  cuuint64_t strides[2] = {(cuuint64_t)w.K, (cuuint64_t)w.K * w.N};
+  cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)boxN, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(wgt8 K=%d N=%d T=%d) failed: %d", w.K, w.N, w.T, (int)r);
     return false;
   }
   return true;

@@ -14,55 +14,16 @@
 // in isolation.
 #include "gemm_types.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 #include <cuda_fp16.h>
 
 namespace mcgvc {
 
-bool make_act_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int BX, int BY, int BB);
-
 namespace {
 
 constexpr int kPos = 64;                       // positions per k-block
 constexpr int kChunk16 = kPos * kBlockK * 2;   // 64 positions x 64 channels x 2 B = 8 KB
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
-    set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
-    return nullptr;
-  }
-  fn = reinterpret_cast<EncodeTiledFn>(p);
-  return fn;
-}
-
-// 8-bit plane [B][P][Y][X][C]: box (boxC bytes, BX, BY, 1, BB); 128B swizzle for 128-channel boxes,
-// 64B swizzle for 64-channel boxes.
-bool make_plane8_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int boxC, int BX, int BY, int BB) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.X, (cuuint64_t)a.Y, (cuuint64_t)a.P, (cuuint64_t)a.B};
-  cuuint64_t strides[4];
-  strides[0] = (cuuint64_t)a.C;
-  strides[1] = strides[0] * a.X;
-  strides[2] = strides[1] * a.Y;
-  strides[3] = strides[2] * a.P;
-  cuuint32_t box[5] = {(cuuint32_t)boxC, (cuuint32_t)BX, (cuuint32_t)BY, 1u, (cuuint32_t)BB};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, boxC == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(plane8 C=%d box %d) failed: %d", a.C, boxC, (int)r); return false; }
-  return true;
-}
 
 // MN-major UMMA descriptor: rows of `rowBytes` (128 -> 128B swizzle, 64 -> 64B swizzle), 8-row groups
 // rowBytes * 8 apart (stride byte offset), next chunk along the MN dimension `lbo` bytes away.

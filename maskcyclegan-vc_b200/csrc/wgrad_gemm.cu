@@ -14,12 +14,12 @@
 // backward pass.
 #include "gemm_types.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 #include <cstdlib>
 
 namespace mcgvc {
 
-bool make_act_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int BX, int BY, int BB);
 
 constexpr int kWgBlockPos = 64;                          // positions per k-block
 constexpr int kChunkBytes = kWgBlockPos * kBlockK * 2;   // one 64-pos x 64-ch box = 8 KB
