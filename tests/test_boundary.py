@@ -119,3 +119,21 @@ def test_split_k_planner_fills_whole_waves(pkg):
     # a forward layer needs a bigger gain (it gives up the fused statistics): Discriminator ds3 qualifies
     assert plan(64, 10, 8, 512, 1024, 1024, 9, 0.2) > 1
 
+
+def test_opt_in_entry_points_validate_their_arguments(pkg):
+    """Argument checks of the f2 / f3 entry points happen before any CUDA call: status 1 + message."""
+    import ctypes
+    lib = pkg.engine.lib()
+    null = ctypes.c_void_p(0)
+    assert lib.mcgvc_crop_mask(null, null, null, 1, null, 1, 64, null, null, null, null) == 1
+    assert b"null pointer" in lib.mcgvc_last_error()
+    one = (ctypes.c_float * 1)()
+    p = ctypes.cast(one, ctypes.c_void_p)
+    assert lib.mcgvc_loss_term(p, null, ctypes.c_longlong(1), 0, ctypes.c_float(0), ctypes.c_float(1), p, null) == 1   # L1 needs b
+    assert lib.mcgvc_loss_term(p, null, ctypes.c_longlong(0), 1, ctypes.c_float(0), ctypes.c_float(1), p, null) == 1   # n < 1
+    assert lib.mcgvc_loss_term(p, null, ctypes.c_longlong(1), 7, ctypes.c_float(0), ctypes.c_float(1), p, null) == 1   # unknown kind
+    assert b"loss_term" in lib.mcgvc_last_error()
+    assert lib.mcgvc_set_precision(4) == 0 and lib.mcgvc_get_precision() == 4      # MCGVC_PRECISION_C8
+    assert lib.mcgvc_set_precision(5) == 1
+    assert lib.mcgvc_set_precision(3) == 0
+
