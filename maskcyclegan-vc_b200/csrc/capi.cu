@@ -10,7 +10,17 @@
 using namespace mcgvc;
 
 static int g_backend = MCGVC_BACKEND_TCGEN05;
-static int g_precision = MCGVC_PRECISION_PARITY;
+// default precision mode: MCGVC_PRECISION=parity|c8|mixed|fast in the environment (the unchanged reference
+// train.py has no other way to choose), else parity
+static int initial_precision() {
+  const char* e = getenv("MCGVC_PRECISION");
+  if (!e) return MCGVC_PRECISION_PARITY;
+  if (!strcmp(e, "c8") || !strcmp(e, "4")) return MCGVC_PRECISION_C8;
+  if (!strcmp(e, "mixed") || !strcmp(e, "2")) return MCGVC_PRECISION_MIXED;
+  if (!strcmp(e, "fast") || !strcmp(e, "1")) return MCGVC_PRECISION_FAST;
+  return MCGVC_PRECISION_PARITY;
+}
+static int g_precision = initial_precision();
 
 // parity: every GEMM split-bf16 x3; fast: every GEMM single bf16; mixed: forward x3, backward x1
 // Backward passes run on two engine-owned streams per device: a HIGH-priority main stream for the

@@ -137,3 +137,15 @@ def test_opt_in_entry_points_validate_their_arguments(pkg):
     assert lib.mcgvc_set_precision(5) == 1
     assert lib.mcgvc_set_precision(3) == 0
 
+
+def test_precision_mode_from_the_environment():
+    """MCGVC_PRECISION selects the default mode at library load (for the unchanged reference train.py)."""
+    import subprocess
+    import sys
+    code = ("import ctypes; l = ctypes.CDLL(%r); print(l.mcgvc_get_precision())"
+            % os.path.join(ROOT, "maskcyclegan-vc_b200", "libmcgvc.so"))
+    for val, want in (("c8", 4), ("mixed", 2), ("fast", 1), ("parity", 3), ("bogus", 3)):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MCGVC_PRECISION=val),
+                             capture_output=True, text=True, check=True).stdout.strip()
+        assert int(out) == want, (val, out)
+
