@@ -1,0 +1,43 @@
+"""CPU: the arithmetic of the C8 precision scheme (csrc/conv_c8.cu, wgrad_c8.cu), restated with torch
+dtypes, against exact fp64 products -- independent of any GPU kernel.
+
+    A*W ~= Ah*Wh + 2^-(uA+uW+11) * (A8h*W8l + A8l*W8h),   Xh = fp16(X), X8h = e4m3(Xh * 2^u),
+                                                          X8l = e4m3((X - Xh) * 2^(u+11))
+"""
+import torch
+
+import kernel_check as kc
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_c8_scheme_error_class():
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(96, 640, generator=g)                 # activations ~ N(0, 1)
+    W = torch.randn(128, 640, generator=g) * 0.02         # weights ~ U(+-1/sqrt(fan_in)) scale
+    exact = A.double() @ W.double().t()
+    uA, uW = 1, 6
+    A16, A8h, A8l = kc.split_c8(A, uA)
+    W16, W8h, W8l = kc.split_c8(W, uW)
+    d = torch.float64
+    c8 = A16.to(d) @ W16.to(d).t() + 2.0 ** -(uA + uW + 11) * (A8h.to(d) @ W8l.to(d).t() + A8l.to(d) @ W8h.to(d).t())
+    fp16_only = A16.to(d) @ W16.to(d).t()
+    Ah, Al = kc.split_bf16(A)
+    Wh, Wl = kc.split_bf16(W)
+    bf16x3 = Ah.to(d) @ Wh.to(d).t() + Ah.to(d) @ Wl.to(d).t() + Al.to(d) @ Wh.to(d).t()
+    bf16_only = Ah.to(d) @ Wh.to(d).t()
+    e_c8, e_f16, e_x3, e_bf = _rel(c8, exact), _rel(fp16_only, exact), _rel(bf16x3, exact), _rel(bf16_only, exact)
+    # measured on the GPU kernels: 1.04e-5 (tests/kernel_check.py c8); the corrections buy ~30x over fp16 alone
+    assert e_c8 < 2e-5 and e_c8 < e_f16 / 15
+    assert e_x3 < e_c8 < e_f16 < e_bf          # split-bf16 x3 < C8 < one fp16 pass < one bf16 pass
+    assert e_bf > 1e-3                         # why a single bf16 pass cannot meet the 1e-3 output gate over ~30 layers
+
+
+def test_c8_planes_saturate_and_keep_sign():
+    x = torch.tensor([0.0, -0.0, 1e-9, -3.5, 300.0, -1e6, 7e4])
+    hi, h8, l8 = kc.split_c8(x, 1)
+    assert torch.isfinite(h8.float()).all() and torch.isfinite(l8.float()).all()
+    assert h8.float()[4] == 448.0 and h8.float()[5] == -448.0       # e4m3 saturates instead of overflowing
+    assert torch.equal(torch.sign(h8.float()[3:6]), torch.sign(x[3:6]))
