@@ -1085,7 +1085,7 @@ __global__ void __launch_bounds__(256) pack_weights_table_kernel(const __grid_co
   float E = 1.f;
   if (e.c8) {
     const float amax = __uint_as_float(reinterpret_cast<const unsigned int*>(f32)[e.rec + 2]);
-    if (amax > 0.f) E = exp2f(floorf(log2f(224.f / amax)));
+    if (amax > 0.f) E = exp2f(fminf(fmaxf(floorf(log2f(224.f / amax)), -100.f), 100.f));   // finite for any amax
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       f32[e.rec + 0] = 1.f;
       f32[e.rec + 1] = 1.f / E;
