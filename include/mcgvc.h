@@ -56,6 +56,15 @@ int mcgvc_pack_weights(int model, const float* params_flat, void* packed, void* 
 /* grad_flat (reference order) += engine-layout gradient blob.  Replaces autograd's AccumulateGrad
  * for the module's parameters (train.py:241,298). */
 int mcgvc_unpack_grads(int model, const float* grad_blob, float* grad_flat, void* stream);
+/* Parameters that never receive a gradient: the Discriminator's downSample4 (constructed at
+ * model.py:316-320, never called by forward :340-349; train.py's Adam skips it because its .grad stays
+ * None).  [begin, begin + len) is its float range in the reference-order flat buffer (len = 0 for the
+ * Generator).  The "live" gradient layout is the flat layout with that range cut out: it is what the
+ * data-parallel all-reduce moves (24 811 524 instead of 66 766 852 floats for the four discriminators). */
+int mcgvc_dead_param_range(int model, long long* begin, long long* len);
+/* grad_live (live layout) += scale * engine-layout gradient blob.  scale = 1/world_size folds the
+ * data-parallel average into this pass, so the all-reduce that follows is a plain sum. */
+int mcgvc_unpack_grads_live(int model, const float* grad_blob, float* grad_live, float scale, void* stream);
 
 /* Generator.forward(x, mask), model.py:239-280.  x, mask: [B][80][T] fp32; out: [B][80][T'] fp32. */
 int mcgvc_generator_forward(const void* packed, const float* x, const float* mask, int batch,
@@ -134,8 +143,8 @@ int mcgvc_debug_plan_ksplit(int oB, int oY, int oX, int C, int N, int nSplit, in
 /* split-K factor used by the following mcgvc_debug_conv calls on the tensor-core backends: every tile's
  * k-blocks run as `k` work items that are added into `out` (which the caller zero-fills); 1 = off. */
 int mcgvc_debug_set_conv_ksplit(int k);
-/* Kernel-level entry of the "16-bit main pass + two e4m3 correction passes" convolution (conv_c8.cu;
- * not on the network path yet): out = out_scale * (sum a16*w16 + corr_scale * sum (a8h*w8l + a8l*w8h))
+/* Kernel-level entry of the "16-bit main pass + two e4m3 correction passes" convolution (conv_c8.cu; the
+ * network path reaches the same kernel under MCGVC_PRECISION_C8): out = out_scale * (sum a16*w16 + corr_scale * sum (a8h*w8l + a8l*w8h))
  * + bias + addsrc.  backend 1 = SIMT checker, 2 = tcgen05 CTA-pair kernel (blockN 128 / 256). */
 int mcgvc_debug_conv_c8(const void* a16, const void* a8h, const void* a8l, int aC, int aX, int aY, int aP,
                         int aB, const void* w16, const void* w8h, const void* w8l, int wK, int wN, int wT,

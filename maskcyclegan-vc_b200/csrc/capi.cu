@@ -190,6 +190,11 @@ static int run_graphed(GraphKey key, void* stream, F body) {
   return 0;
 }
 
+static void drop_graphs_locked() {
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  drop_graphs();
+}
+
 extern "C" {
 
 int mcgvc_set_device(int device) {
@@ -199,6 +204,7 @@ int mcgvc_set_device(int device) {
 }
 int mcgvc_set_backend(int backend) {
   if (backend != 0 && backend != 1) { set_error("backend must be 0 or 1"); return 1; }
+  if (backend != g_backend) drop_graphs_locked();   // recorded launch topology depends on it
   g_backend = backend;
   return 0;
 }
@@ -212,7 +218,11 @@ int mcgvc_set_precision(int mode) {
   return 0;
 }
 int mcgvc_get_precision(void) { return g_precision; }
-int mcgvc_set_overlap(int on) { g_overlap = on ? 1 : 0; return 0; }
+int mcgvc_set_overlap(int on) {
+  if ((on ? 1 : 0) != g_overlap) drop_graphs_locked();   // engine streams vs caller stream is baked into a graph
+  g_overlap = on ? 1 : 0;
+  return 0;
+}
 
 long long mcgvc_param_count(int model) { const ModelDesc* d = desc(model); return d ? d->paramCount : -1; }
 long long mcgvc_packed_bytes(int model) { const ModelDesc* d = desc(model); return d ? d->packed_bytes() : -1; }
@@ -243,6 +253,20 @@ int mcgvc_unpack_grads(int model, const float* gblob, float* grad_flat, void* st
   if (!d) return 1;
   if (!gblob || !grad_flat) { set_error("unpack_grads: null pointer"); return 1; }
   return unpack_grads(*d, gblob, grad_flat, cfg(stream));
+}
+
+int mcgvc_dead_param_range(int model, long long* begin, long long* len) {
+  const ModelDesc* d = desc(model);
+  if (!d) return 1;
+  if (begin) *begin = d->deadBegin;
+  if (len) *len = d->deadLen;
+  return 0;
+}
+int mcgvc_unpack_grads_live(int model, const float* gblob, float* grad_live, float scale, void* stream) {
+  const ModelDesc* d = desc(model);
+  if (!d) return 1;
+  if (!gblob || !grad_live) { set_error("unpack_grads_live: null pointer"); return 1; }
+  return unpack_grads(*d, gblob, grad_live, cfg(stream), 1, scale);
 }
 
 int mcgvc_generator_forward(const void* packed, const float* x, const float* mask, int B, int T,
@@ -305,6 +329,7 @@ int mcgvc_set_graphs(int on) {
   return 0;
 }
 int mcgvc_graph_stats(long long* captures, long long* replays) {
+  std::lock_guard<std::mutex> lk(g_graph_mu);
   if (captures) *captures = g_graph_captures;
   if (replays) *replays = g_graph_replays;
   return 0;

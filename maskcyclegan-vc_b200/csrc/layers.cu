@@ -1180,7 +1180,7 @@ __global__ void __launch_bounds__(256) unpack_wgrads_table_kernel(const __grid_c
       __syncthreads();
       for (int rr = warp; rr < kPackTile; rr += 8) {
         float* dst = dref + ((long long)ref_row(np0 + rr) * e.C + c0) * T;
-        for (int i = lane; i < rowLen; i += 32) dst[i] += tile[rr * pitch + i];
+        for (int i = lane; i < rowLen; i += 32) dst[i] += t.scale * tile[rr * pitch + i];
       }
     }
     return;
@@ -1193,7 +1193,7 @@ __global__ void __launch_bounds__(256) unpack_wgrads_table_kernel(const __grid_c
     const int n = (int)(idx / ((long long)e.T * e.C));
     int tp, np, cp;
     pack_map(a, n, c, tt, &tp, &np, &cp);
-    dref[idx] += dw[((long long)tp * e.Np + np) * e.Cp + cp];
+    dref[idx] += t.scale * dw[((long long)tp * e.Np + np) * e.Cp + cp];
   }
 }
 cudaError_t launch_unpack_wgrads_table(const PackTable& t, const float* gblob, float* gradFlat,
@@ -1212,7 +1212,7 @@ __global__ void unpack_vecs_table_kernel(const __grid_constant__ VecTable t,
                                          const float* __restrict__ eng, float* __restrict__ gradFlat) {
   const VecEntry& e = t.e[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += gridDim.x * blockDim.x)
-    gradFlat[e.refOff + i] += eng[e.engOff + vec_map(e.kind, i, e.n)];
+    gradFlat[e.refOff + i] += t.scale * eng[e.engOff + vec_map(e.kind, i, e.n)];
 }
 cudaError_t launch_pack_vecs_table(const VecTable& t, const float* params, float* eng, cudaStream_t s) {
   dim3 grid(4, t.count);

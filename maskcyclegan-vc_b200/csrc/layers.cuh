@@ -151,6 +151,7 @@ struct PackEntry {
 struct PackTable {
   int count;
   int actRec;             // float offset of the static activation record {1, 1/2} (c8 mode), or -1
+  float scale;            // unpack only: gradFlat += scale * blob (1/world folds the data-parallel average)
   PackEntry e[32];
 };
 struct VecEntry {
@@ -158,6 +159,7 @@ struct VecEntry {
 };
 struct VecTable {
   int count;
+  float scale;            // unpack only, see PackTable
   VecEntry e[96];
 };
 cudaError_t launch_pack_weights_table(const PackTable& t, const float* params, __nv_bfloat16* packed,

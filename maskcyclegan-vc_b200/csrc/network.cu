@@ -40,6 +40,7 @@ struct DescBuilder {
     d.packedBf16 = d.gradFloats = 0;
     d.actRec = 0; d.packedF32 = 64;   // first slot of the fp32 area: static activation record
     d.paramCount = p.total;
+    d.deadBegin = d.deadLen = 0;
   }
   void conv(const std::string& name, std::vector<std::string> parts, int refN, int refC, int refT,
             int kind, int biasKind, int Np, int Cp, int Tp, int Cd) {
@@ -192,6 +193,8 @@ ModelDesc build_discriminator() {
   b.norm("ds1", {"downSample1.1"}, 256, kVecIdent);
   b.norm("ds2", {"downSample2.1"}, 512, kVecIdent);
   b.norm("ds3", {"downSample3.1"}, 1024, kVecIdent);
+  b.d.deadBegin = pt.at("downSample4.0.weight");
+  b.d.deadLen = pt.at("outputConvLayer.0.weight") - b.d.deadBegin;
   return b.d;
 }
 
@@ -733,11 +736,16 @@ int pack_model(const ModelDesc& d, const float* params, void* packed, const RunC
   return r.ok ? 0 : 1;
 }
 
-int unpack_grads(const ModelDesc& d, const float* gblob, float* gradFlat, const RunCfg& rc) {
+int unpack_grads(const ModelDesc& d, const float* gblob, float* gradFlat, const RunCfg& rc, int live, float scale) {
   Run r{rc};
-  const PackTable pt = make_pack_table(d);
-  const VecTable vt = make_vec_table(d, true);
+  PackTable pt = make_pack_table(d);
+  VecTable vt = make_vec_table(d, true);
   if (pt.count > 32 || vt.count > 96) { set_error("pack tables too small"); return 1; }
+  pt.scale = vt.scale = scale;
+  if (live && d.deadLen > 0) {   // offsets behind the dead range move down by its length
+    for (int i = 0; i < pt.count; ++i) if (pt.e[i].refOff >= d.deadBegin) pt.e[i].refOff -= (int)d.deadLen;
+    for (int i = 0; i < vt.count; ++i) if (vt.e[i].refOff >= d.deadBegin) vt.e[i].refOff -= (int)d.deadLen;
+  }
   r.check(launch_unpack_wgrads_table(pt, gblob, gradFlat, rc.stream), "unpack: weights");
   r.check(launch_unpack_vecs_table(vt, gblob, gradFlat, rc.stream), "unpack: vectors");
   return r.ok ? 0 : 1;

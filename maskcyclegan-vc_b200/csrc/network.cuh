@@ -50,6 +50,10 @@ struct ModelDesc {
   long long packedF32;        // floats in the packed blob (small vectors), placed after the bf16 area
   long long gradFloats;       // floats in the engine-layout gradient blob
   long long actRec;           // float offset (packed fp32 area) of the static activation record {1, 1/2}
+  // parameters that never receive a gradient (the Discriminator's downSample4, model.py:316-320 vs
+  // :340-349): float range [deadBegin, deadBegin + deadLen) of the reference-order flat buffer.  The
+  // "live" gradient layout is the flat layout with this range cut out.
+  long long deadBegin, deadLen;
   long long packed_bytes() const { return packedBf16 * 2 + packedF32 * 4; }
 };
 
@@ -74,7 +78,9 @@ long long discriminator_fwd_ws_bytes(int B, int T);
 long long discriminator_bwd_ws_bytes(int B, int T);
 
 int pack_model(const ModelDesc& d, const float* params, void* packed, const RunCfg& rc);
-int unpack_grads(const ModelDesc& d, const float* gblob, float* gradFlat, const RunCfg& rc);
+// live = 0: gradFlat has the full reference-order layout; live = 1: the dead range is cut out
+int unpack_grads(const ModelDesc& d, const float* gblob, float* gradFlat, const RunCfg& rc, int live = 0,
+                 float scale = 1.f);
 
 int generator_forward(const void* packed, const float* x, const float* mask, int B, int T,
                       float* out, void* saved, void* ws, const RunCfg& rc);

@@ -48,6 +48,8 @@ def lib():
         getattr(l, name).argtypes = [_c_int, _c_int, _c_int]
     l.mcgvc_pack_weights.argtypes = [_c_int, _c_vp, _c_vp, _c_vp]
     l.mcgvc_unpack_grads.argtypes = [_c_int, _c_vp, _c_vp, _c_vp]
+    l.mcgvc_unpack_grads_live.argtypes = [_c_int, _c_vp, _c_vp, ctypes.c_float, _c_vp]
+    l.mcgvc_dead_param_range.argtypes = [_c_int, ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]
     l.mcgvc_generator_forward.argtypes = [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]
     l.mcgvc_generator_backward.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp,
                                            _c_int, _c_vp, _c_vp]
@@ -142,9 +144,29 @@ def pack_weights(model, flat_params):
 
 
 def unpack_grads(model, grad_blob, flat_grad):
+    """flat_grad (full reference-order layout) += engine-layout gradient blob."""
     l = lib()
     l.mcgvc_set_device(flat_grad.device.index)
     _check(l.mcgvc_unpack_grads(model, _ptr(grad_blob), _ptr(flat_grad), _stream()), "unpack_grads")
+
+
+def dead_param_range(model):
+    """(begin, len) in floats of the parameters that never receive a gradient (D: downSample4)."""
+    b, n = _c_ll(0), _c_ll(0)
+    _check(lib().mcgvc_dead_param_range(model, ctypes.byref(b), ctypes.byref(n)), "dead_param_range")
+    return b.value, n.value
+
+
+def live_grad_count(model):
+    return param_count(model) - dead_param_range(model)[1]
+
+
+def unpack_grads_live(model, grad_blob, live_grad, scale=1.0):
+    """live_grad (flat layout minus the dead range) += scale * engine-layout gradient blob."""
+    l = lib()
+    l.mcgvc_set_device(live_grad.device.index)
+    _check(l.mcgvc_unpack_grads_live(model, _ptr(grad_blob), _ptr(live_grad), ctypes.c_float(scale), _stream()),
+           "unpack_grads_live")
 
 
 def generator_forward(packed, x, mask):

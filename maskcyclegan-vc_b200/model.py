@@ -67,12 +67,27 @@ class _EngineModule(nn.Module):
         self._cb_queued = False
         self._touched = False
         self._live = None          # parameters that receive gradients (excludes dead tensors)
+        self._param_list = None    # cached list(self.parameters()) (walked on every forward)
         self._grad_sync = None     # set by parallel.GradSync
         self._weights_epoch = 0    # bumped by optim.FusedAdam (in-place update of the flat buffer)
 
     # ------------------------------------------------------------------ parameter storage
     def _unique_params(self):
-        return list(self.parameters())
+        if self._param_list is None:
+            self._param_list = list(self.parameters())
+        return self._param_list
+
+    def _reset_backward_state(self):
+        self._cb_queued = False
+        self._touched = False
+
+    def invalidate_packed(self):
+        """Force a re-pack of the engine-layout weights at the next forward.  Needed only after
+        in-place edits that bypass the Parameters' version counters (`p.data.copy_()`,
+        `m.weight.data.normal_()`, raw writes into `_flat`); optimizers, `load_state_dict` and
+        `.to()` are tracked automatically."""
+        self._packed = None
+        self._packed_version = None
 
     def _flatten(self):
         """Re-home all parameters into one flat buffer (reference parameters() order)."""
@@ -92,11 +107,23 @@ class _EngineModule(nn.Module):
                     p.grad = None
                 off += k
         self._flat = flat
-        self._flat_grad = None
+        # The flat gradient buffer survives a re-flatten when it still fits (same size, and on the
+        # device the parameters live on or will come back to): ModelSaver.save() bounces every
+        # model through .to('cpu') / .to(device) (model_saver.py:64,74), and a GradSync arena slice
+        # dropped here would silently stop gradient synchronisation after the first checkpoint.
+        fg = self._flat_grad
+        if fg is not None and dev.type == "cuda" and fg.device != dev:
+            if self._grad_sync is not None and dev.type == "cuda":
+                raise engine.EngineError(
+                    "%s moved from %s to %s while registered with GradSync: build the GradSync after "
+                    "the final .to(device)" % (type(self).__name__, fg.device, dev))
+            self._flat_grad = None
         self._gblob = None
         self._packed = None
         self._packed_version = None
         self._anchor = None
+        self._param_list = None
+        self._reset_backward_state()
 
     def _apply(self, fn, recurse=True):
         # .to()/.cuda()/.cpu() (train.py:103-110, model_saver.py:64,74) replace p.data: re-flatten
@@ -116,9 +143,18 @@ class _EngineModule(nn.Module):
             raise engine.EngineError("parameter count mismatch with the engine's model table")
         if self._gblob is None:
             self._gblob = torch.zeros(engine.grad_blob_floats(self.MODEL), dtype=torch.float32, device=dev)
-            if self._flat_grad is None:
-                self._flat_grad = torch.zeros_like(self._flat)
+            if self._flat_grad is None or self._flat_grad.device != dev:
+                # live layout: the flat layout minus parameters that never get a gradient
+                self._flat_grad = torch.zeros(engine.live_grad_count(self.MODEL), dtype=torch.float32, device=dev)
             self._anchor = torch.zeros(1, device=dev, requires_grad=True)
+        if self._cb_queued:
+            # (only forward calls come through here, and the engine never runs a forward inside a
+            # backward pass.)  A previous backward pass raised before autograd ran the
+            # end-of-backward callback (OOM, EngineError, precision-mode guard): its flag would
+            # otherwise stop every later pass from publishing gradients, and its partial sums would
+            # leak into the next publish
+            self._reset_backward_state()
+            self._gblob.zero_()
 
     def _version(self):
         # the packed layout depends on the precision mode (C8 keeps fp16 + e4m3 planes)
@@ -153,17 +189,17 @@ class _EngineModule(nn.Module):
         fresh = live[0].grad is None
         if fresh:
             self._flat_grad.zero_()
-        engine.unpack_grads(self.MODEL, self._gblob, self._flat_grad)
+        # with GradSync the data-parallel average is folded into this pass (the all-reduce is a sum)
+        scale = self._grad_sync.unpack_scale() if self._grad_sync is not None else 1.0
+        engine.unpack_grads_live(self.MODEL, self._gblob, self._flat_grad, scale)
         self._gblob.zero_()
         if self._grad_sync is not None:
             self._grad_sync.module_ready(self)
         if fresh:
             off = 0
-            live_ids = {id(p) for p in live}
-            for p in self._unique_params():
+            for p in live:          # live parameters in parameters() order == live gradient layout
                 k = p.numel()
-                if id(p) in live_ids:
-                    p.grad = self._flat_grad[off:off + k].view(p.shape)
+                p.grad = self._flat_grad[off:off + k].view(p.shape)
                 off += k
 
     def _live_params(self):
@@ -184,6 +220,14 @@ def _check_mode(ctx):
     if engine.get_precision() != ctx.precision:
         raise engine.EngineError("precision mode changed between forward (%d) and backward (%d) of one graph"
                                  % (ctx.precision, engine.get_precision()))
+
+
+def _check_saved(ctx, what):
+    if ctx.saved is None:
+        raise engine.EngineError(
+            "%s: the saved-activation blob of this forward call was already consumed; "
+            "backward(retain_graph=True) followed by a second backward (and double backward) are "
+            "not supported by the engine" % what)
 
 
 class _GeneratorFn(Function):
@@ -207,6 +251,7 @@ class _GeneratorFn(Function):
         B, T = ctx.dims
         (mask,) = ctx.saved_tensors
         _check_mode(ctx)
+        _check_saved(ctx, "Generator")
         need_w = module._need_wgrad()
         dx = engine.generator_backward(ctx.packed, ctx.saved, mask, dout.contiguous(), B, T,
                                        ctx.needs_input_grad[0], module._gblob if need_w else None, need_w)
@@ -236,6 +281,7 @@ class _DiscriminatorFn(Function):
         B, T = ctx.dims
         (out,) = ctx.saved_tensors
         _check_mode(ctx)
+        _check_saved(ctx, "Discriminator")
         need_w = module._need_wgrad()
         dx = engine.discriminator_backward(ctx.packed, ctx.saved, out, dout.contiguous(), B, T,
                                            ctx.needs_input_grad[0], module._gblob if need_w else None, need_w)
@@ -338,4 +384,8 @@ class Discriminator(_EngineModule):
         if x.device != self._flat.device:
             raise engine.EngineError("input is on %s but the model is on %s" % (x.device, self._flat.device))
         x = x.float()
+        track = torch.is_grad_enabled() and not (_LEAN and not self.training and not x.requires_grad)
+        if not track:
+            with torch.no_grad():
+                return _DiscriminatorFn.apply(x, self._anchor, self)
         return _DiscriminatorFn.apply(x, self._anchor, self)

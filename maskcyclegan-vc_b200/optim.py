@@ -48,15 +48,24 @@ class FusedAdam:
                 self.state[id(m)] = st
             st["step"] += 1
             lib.mcgvc_set_device(flat.device.index)
-            rc = lib.mcgvc_adam_step(ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(grad.data_ptr()),
-                                     ctypes.c_void_p(st["exp_avg"].data_ptr()),
-                                     ctypes.c_void_p(st["exp_avg_sq"].data_ptr()),
-                                     ctypes.c_longlong(flat.numel()), ctypes.c_float(lr),
-                                     ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]),
-                                     ctypes.c_float(self.eps), ctypes.c_int(st["step"]),
-                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-            if rc != 0:
-                raise engine.EngineError("adam_step failed: " + lib.mcgvc_last_error().decode())
+            # the gradient buffer uses the live layout (flat layout minus the never-used downSample4
+            # range): one launch per live range; the dead range sees no update, as with torch's skip
+            dead_b, dead_n = engine.dead_param_range(m.MODEL)
+            ranges = [(0, 0, flat.numel())] if dead_n == 0 else \
+                [(0, 0, dead_b), (dead_b + dead_n, dead_b, flat.numel() - dead_b - dead_n)]
+            for p_off, g_off, n in ranges:
+                if n <= 0:
+                    continue
+                rc = lib.mcgvc_adam_step(ctypes.c_void_p(flat.data_ptr() + 4 * p_off),
+                                         ctypes.c_void_p(grad.data_ptr() + 4 * g_off),
+                                         ctypes.c_void_p(st["exp_avg"].data_ptr() + 4 * p_off),
+                                         ctypes.c_void_p(st["exp_avg_sq"].data_ptr() + 4 * p_off),
+                                         ctypes.c_longlong(n), ctypes.c_float(lr),
+                                         ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]),
+                                         ctypes.c_float(self.eps), ctypes.c_int(st["step"]),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                if rc != 0:
+                    raise engine.EngineError("adam_step failed: " + lib.mcgvc_last_error().decode())
             m._weights_epoch += 1           # the flat buffer changed behind the Parameters' version counters
 
     def state_dict(self):

@@ -5,12 +5,15 @@ The path shards over the batch (every op is per-sample: InstanceNorm, not BatchN
 batch means, train.py:219-232,276-288), so with equal per-rank batches the global-batch gradient is
 the average of per-rank gradients.  The only exchange step is therefore ONE all-reduce per
 optimizer step on the packed gradient buffer of the modules that optimizer owns:
-49 075 458 floats (196.3 MB) for the two generators, 24 811 524 live floats for the four
-discriminators (their unused downSample4 tensors are never reduced).
+49 075 458 floats (196.3 MB) for the two generators, 24 811 524 live floats (99.2 MB) for the four
+discriminators -- the modules' gradient buffers use the "live" layout, i.e. the unused downSample4
+tensors (10 488 832 floats per discriminator, model.py:316-320 vs :340-349) have no slot in them.
 
-GradSync re-homes the modules' flat gradient buffers into one contiguous arena per group; each
+GradSync re-homes the modules' live gradient buffers into one contiguous arena per group; each
 module reports in from its end-of-backward callback and the arena is all-reduced once, when the
-last training-mode module of the group that took part in this backward pass has reported.
+last training-mode module of the group that took part in this backward pass has reported.  The
+1/world average is folded into the modules' unpack pass (`unpack_scale`), so the collective is a
+plain sum and no extra pass over the arena follows it.
 """
 import torch
 import torch.distributed as dist
@@ -24,22 +27,28 @@ class GradSync:
         self.groups = []
         for mods in groups:
             mods = list(mods)
-            total = sum(m._flat.numel() for m in mods)
+            # every module's slice starts 256-byte aligned (FusedAdam and the unpack kernels use 16-byte accesses)
+            sizes = [_live_count(m) for m in mods]
+            offs, total = [], 0
+            for n in sizes:
+                offs.append(total)
+                total += (n + 63) // 64 * 64
             arena = torch.zeros(total, dtype=torch.float32, device=mods[0]._flat.device)
-            off = 0
-            for m in mods:
-                n = m._flat.numel()
+            for m, off, n in zip(mods, offs, sizes):
                 m._flat_grad = arena[off:off + n]
                 m._grad_sync = self
                 for p in m.parameters():
                     p.grad = None
-                off += n
             self.groups.append({"mods": mods, "arena": arena, "pending": set()})
         self.reductions = 0
         self.reduced_bytes = 0
 
     def world(self):
         return dist.get_world_size(self.pg) if dist.is_available() and dist.is_initialized() else 1
+
+    def unpack_scale(self):
+        """Factor the modules apply while writing their gradient into the arena."""
+        return 1.0 / self.world() if self.average else 1.0
 
     def module_ready(self, module):
         """Called by a module at the end of a backward pass, after its flat gradient is final."""
@@ -72,11 +81,18 @@ class GradSync:
                 self._allreduce(m._flat_grad)
 
     def _allreduce(self, buf):
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
-        if self.average:
-            buf.mul_(1.0 / self.world())
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)   # average: see unpack_scale()
         self.reductions += 1
         self.reduced_bytes += buf.numel() * 4
+
+
+def _live_count(m):
+    """Floats in a module's live gradient layout (engine modules), or all of them (anything else)."""
+    model = getattr(m, "MODEL", None)
+    if model is None:
+        return m._flat.numel()
+    from . import engine
+    return engine.live_grad_count(model)
 
 
 def shard_batch(batch, rank, world):
