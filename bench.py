@@ -5,8 +5,9 @@ world > 1) on synthetic 80x64 mel batches.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
-`--impl reference` times the reference's algorithm on the host CPU (the oracle port of model.py +
-train.py step; the reference itself is Python and does not travel to the GPU box).
+`--impl reference` times the reference's own modules (oracle/_ref, staged by oracle/build_ref.sh) on
+the host CPU through the same train-step composition; the oracle port stands in only if oracle/_ref
+did not travel with the snapshot.
 """
 import argparse
 import json
@@ -113,61 +114,107 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# CPU arm.  The reference's own Generator / Discriminator modules (oracle/_ref, staged by
+# oracle/build_ref.sh; kind "reference") when they travelled with the snapshot, else the oracle port
+# (kind "port").  The loop body is trainstep.train_step, the restatement of train.py:186-299 that
+# also drives the engine (loaded straight from its file: the engine package is NOT imported here).
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _load_trainstep():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "mcgvc_trainstep_only", os.path.join(ROOT, "maskcyclegan-vc_b200", "trainstep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _cpu_models():
+    """(kind, models, step_fn(models, g_opt, d_opt, batch)) on the host CPU."""
+    ts = _load_trainstep()
+    if os.path.exists(os.path.join(REF_DIR, "mask_cyclegan_vc", "model.py")):
+        sys.path.insert(0, REF_DIR)
+        from mask_cyclegan_vc.model import Discriminator, Generator   # the UNMODIFIED reference modules
+        kind = "reference"
+        what = "reference mask_cyclegan_vc/model.py modules (oracle/_ref) + torch.optim.Adam"
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import maskcyclegan_oracle as O
+        Generator, Discriminator = O.OracleGenerator, O.OracleDiscriminator
+        kind = "port"
+        what = "oracle port of model.py (oracle/_ref not staged) + torch.optim.Adam"
+    models = ts.build_models(Generator, Discriminator, torch.device("cpu"), seed=0)
+    g_opt, d_opt = ts.build_optimizers(models)
+    return kind, what, models, g_opt, d_opt, ts.train_step
+
+
+def _cpu_step_timer(B, seed=1234):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, what, models, g_opt, d_opt, step = _cpu_models()
+    batch = list(synthetic_batch_host(B, T_FRAMES, seed=seed))
+
+    def one():
+        t0 = time.perf_counter()
+        g, d = step(models, g_opt, d_opt, batch)
+        float(g), float(d)                       # train.py:302-304 reads both losses every step
+        return time.perf_counter() - t0
+    return kind, what, cores, one
+
+
 def run_reference(args):
-    """CPU arm: the oracle port of the reference Generator/Discriminator + train step on all host
-    threads, on a bounded sample of the same workload (batch 2 per step instead of 64)."""
+    """`--impl reference`: the reference's CPU implementation of the full train step on all host
+    threads.  Same metric / config line as the engine arm; each step is a bounded SAMPLE of the
+    batch-64 workload -- batch 16 (BASELINE configs[2]), or batch 4 if the first step shows that
+    W + K steps at batch 16 would not finish within ~5 minutes on this box."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import maskcyclegan_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    K, W = max(args.steps, 1), max(args.warmup, 1)
     B = args.ref_batch
-    torch.manual_seed(0)
-    mods = [O.OracleGenerator(), O.OracleGenerator(), O.OracleDiscriminator(), O.OracleDiscriminator(),
-            O.OracleDiscriminator(), O.OracleDiscriminator()]
-    g_opt = torch.optim.Adam(list(mods[0].parameters()) + list(mods[1].parameters()), lr=2e-4, betas=(0.5, 0.999))
-    d_opt = torch.optim.Adam([p for m in mods[2:] for p in m.parameters()], lr=1e-4, betas=(0.5, 0.999))
-    batch = O.synthetic_batch(B, T_FRAMES, seed=1234)
-    steps = max(1, min(args.steps, args.ref_max_steps))
-    warm = max(1, min(args.warmup, 1))
-    for _ in range(warm):
-        O.train_step(*mods, g_opt, d_opt, batch)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.train_step(*mods, g_opt, d_opt, batch)
-    dt = (time.perf_counter() - t0) / steps
+    kind, what, cores, one = _cpu_step_timer(B)
+    t_first = one()
+    done_warm = 1
+    if B > 4 and t_first * (K + W) > args.ref_budget_s:
+        B = 4
+        kind, what, cores, one = _cpu_step_timer(B)
+        t_first = one()
+    for _ in range(W - done_warm):
+        one()
+    times = [one() for _ in range(K)]
+    dt = sum(times) / K
     value = B * T_FRAMES / dt
-    sample = "oracle port of model.py+train.py:186-299, fp32, batch %d per step (bounded sample of the batch-64 workload), %d timed steps" % (B, steps)
+    sample = ("%s; fp32, %d host threads; each step = the full train step (train.py:186-299) at batch %d, a bounded "
+              "sample of the batch-%d-per-GPU workload; %d warm-up + %d timed steps, %.2f s/step"
+              % (what, cores, B, args.batch, W, K, dt))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "steps": K, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "full MaskCycleGAN train step (train.py:186-299), 80x64, CPU", "batch_per_step": B, "frames": T_FRAMES},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": make_config(args.batch, max(args.gpus, 1), args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline(B, steps):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import maskcyclegan_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    mods = [O.OracleGenerator(), O.OracleGenerator(), O.OracleDiscriminator(), O.OracleDiscriminator(),
-            O.OracleDiscriminator(), O.OracleDiscriminator()]
-    g_opt = torch.optim.Adam(list(mods[0].parameters()) + list(mods[1].parameters()), lr=2e-4, betas=(0.5, 0.999))
-    d_opt = torch.optim.Adam([p for m in mods[2:] for p in m.parameters()], lr=1e-4, betas=(0.5, 0.999))
-    batch = O.synthetic_batch(B, T_FRAMES, seed=1234)
-    O.train_step(*mods, g_opt, d_opt, batch)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.train_step(*mods, g_opt, d_opt, batch)
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": B * T_FRAMES / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "oracle port, full train step at batch %d (bounded sample of batch-64 workload), 1 warm-up + %d timed steps, %.2f s/step" % (B, steps, dt)}
+    """The same CPU arm, timed beside the engine on rank 0 at N = 1: 1 warm-up + `steps` timed steps."""
+    kind, what, cores, one = _cpu_step_timer(B)
+    one()
+    dt = sum(one() for _ in range(steps)) / steps
+    return {"value": B * T_FRAMES / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%s; full train step at batch %d (bounded sample of the batch-64 workload), fp32, %d host threads, "
+                      "1 warm-up + %d timed steps, %.2f s/step" % (what, B, cores, steps, dt)}
+
+
+def make_config(B, world, args):
+    """`config` of the JSON line -- shared by the engine arm and the CPU reference arm."""
+    return {"workload": "full MaskCycleGAN train step (train.py:186-299: 10 G fwd + 12 D fwd, 2 backward, 2 Adam), "
+                        "batch %d per GPU, 80x%d mel (BASELINE configs[3])" % (B, T_FRAMES),
+            "batch_per_gpu": B, "global_batch": B * world, "frames": T_FRAMES,
+            "parallelism": "dp%d" % world,
+            "l2": "inputs larger than L2: ~%.1f GB of activations touched per step vs 126 MB L2" % (24.0 * B / 64.0)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -206,11 +253,11 @@ def main():
                     help="torch = torch.optim.Adam as in train.py:119-122; fused = one-kernel Adam on the flat buffers")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--fast-steps", type=int, default=3, help="extra steps in the other precision mode (0 = skip)")
-    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the in-line cpu_baseline sample (configs[2])")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--ref-batch", type=int, default=2)
-    ap.add_argument("--ref-max-steps", type=int, default=20)
+    ap.add_argument("--ref-batch", type=int, default=16, help="batch of one --impl reference step (configs[2])")
+    ap.add_argument("--ref-budget-s", type=float, default=330.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -387,13 +434,10 @@ def main():
                       "c8": "fp16 + 2x e4m3 correction (fp32 accumulate, fp32 activations/stats); stems/heads bf16x3",
                       "mixed": "bf16x3 split forward / bf16 backward (fp32 accumulate)", "fast": "bf16"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "full MaskCycleGAN train step (train.py:186-299: 10 G fwd + 12 D fwd, 2 backward, 2 Adam), batch %d per GPU, 80x%d mel (BASELINE configs[3])" % (B, T_FRAMES),
-                       "batch_per_gpu": B, "global_batch": B * world, "frames": T_FRAMES,
-                       "optimizer": "torch.optim.Adam" if args.optimizer == "torch" else "engine FusedAdam",
+            "config": make_config(B, world, args),
+            "engine": {"optimizer": "torch.optim.Adam" if args.optimizer == "torch" else "engine FusedAdam",
                        "precision_mode": args.precision, "precision_note": mode_note[args.precision], "lean": bool(args.lean),
-                       "parallelism": "dp%d" % world,
-                       "l2": "inputs larger than L2: ~%.1f GB of activations touched per step vs 126 MB L2" % (24.0 * B / 64.0),
-                       "grad_allreduce": "one NCCL all-reduce per optimizer step on the packed gradient arena" if world > 1 else "none (1 GPU)"},
+                       "grad_allreduce": "one NCCL all-reduce (sum; 1/world folded into the gradient unpack) per optimizer step on the live gradient arena" if world > 1 else "none (1 GPU)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
@@ -406,7 +450,8 @@ def main():
             "losses_last_step": {"g": float(losses["gh"]), "d": float(losses["dh"])},
         }
         if sync is not None:
-            line["config"]["allreduces"] = sync.reductions
+            line["engine"]["allreduces"] = sync.reductions
+            line["engine"]["allreduce_bytes"] = sync.reduced_bytes
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

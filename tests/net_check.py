@@ -118,16 +118,30 @@ def check_forward(G, D, gs, ds, B, T, verbose=True):
     return res
 
 
+_ORACLE_BWD_CACHE = {}
+
+
+def oracle_backward(gs, ds, B, T):
+    """The oracle side of check_backward (CPU fp32 autograd), cached per (B, T): at batch 64 it is
+    ~10 s of host work and the same for every precision mode of the engine."""
+    key = (B, T, id(gs), id(ds))
+    if key not in _ORACLE_BWD_CACHE:
+        x, m, _, _ = O.synthetic_batch(B, T, seed=77 + B)
+        gso = {k: v.clone().requires_grad_(True) for k, v in gs.items()}
+        dso = {k: v.clone().requires_grad_(True) for k, v in ds.items()}
+        xo = x.clone().requires_grad_(True)
+        fake = O.generator_forward(gso, xo, m)
+        d = O.discriminator_forward(dso, fake)
+        loss = torch.mean((1 - d) ** 2)
+        loss.backward()
+        _ORACLE_BWD_CACHE.clear()          # keep one entry: the batch-64 graph outputs are large
+        _ORACLE_BWD_CACHE[key] = (x, m, gso, dso, xo, fake.detach(), loss.detach())
+    return _ORACLE_BWD_CACHE[key]
+
+
 def check_backward(G, D, gs, ds, B, T, verbose=True):
     """config 2: loss = mean((1 - D(G(x, m)))^2); compares every parameter gradient and dx."""
-    x, m, _, _ = O.synthetic_batch(B, T, seed=77 + B)
-    gso = {k: v.clone().requires_grad_(True) for k, v in gs.items()}
-    dso = {k: v.clone().requires_grad_(True) for k, v in ds.items()}
-    xo = x.clone().requires_grad_(True)
-    fake = O.generator_forward(gso, xo, m)
-    d = O.discriminator_forward(dso, fake)
-    loss = torch.mean((1 - d) ** 2)
-    loss.backward()
+    x, m, gso, dso, xo, fake, loss = oracle_backward(gs, ds, B, T)
 
     for mod in (G, D):
         mod.zero_grad(set_to_none=True)

@@ -467,3 +467,93 @@ def test_lean_mode_keeps_the_training_trajectory(env):
     # weights after the step: Adam amplifies atomics-order noise on zero-gradient biases, compare norms
     assert abs(out[0][2].norm().item() - out[1][2].norm().item()) < 1e-4 * out[0][2].norm().item()
     assert abs(out[0][3].norm().item() - out[1][3].norm().item()) < 1e-4 * out[0][3].norm().item()
+
+
+# ---------------------------------------------------------------------------------------------
+# Referees at BASELINE's headline sizes: the ORACLE (CPU fp32 autograd), not the SIMT backend and
+# not another precision mode, judges the multi-wave CTA-pair data gradients, the grouped stride-2
+# data gradients, the split-K weight-gradient GEMMs and the normalisation backward at nImg = 64.
+@pytest.mark.parametrize("mode", ["parity", "c8"])
+def test_adversarial_backward_at_batch64_vs_oracle(env, mode):
+    """BASELINE configs[3] batch: G -> D adversarial pass at B = 64, T = 64; packed Generator and
+    Discriminator gradients, the input gradient, the fake batch and the loss within 1e-3."""
+    import net_check
+    e = env["pkg"].engine
+    e.set_precision(e.PRECISION_C8 if mode == "c8" else e.PRECISION_PARITY)
+    try:
+        bwd = net_check.check_backward(env["G"], env["D"], env["gs"], env["ds"], 64, 64, verbose=False)
+    finally:
+        e.set_precision(e.PRECISION_PARITY)
+    for k, v in bwd.items():
+        assert v < TOL, (mode, k, v)
+
+
+def test_c8_backward_long_frames_vs_oracle(env):
+    """C8 at the long-frame shape of BASELINE configs[4] (T = 512: InstanceNorm planes 8x larger,
+    the 1-D trunk at L = 128), forward and backward."""
+    import net_check
+    e = env["pkg"].engine
+    e.set_precision(e.PRECISION_C8)
+    try:
+        bwd = net_check.check_backward(env["G"], env["D"], env["gs"], env["ds"], 2, 512, verbose=False)
+    finally:
+        e.set_precision(e.PRECISION_PARITY)
+    for k, v in bwd.items():
+        assert v < TOL, (k, v)
+
+
+class _CapturingOpt:
+    """Wraps an optimizer: records the concatenated gradients its modules hold when step() is called."""
+
+    def __init__(self, opt, modules):
+        self.opt, self.modules, self.grads = opt, modules, None
+
+    def zero_grad(self, *a, **k):
+        return self.opt.zero_grad(*a, **k)
+
+    @staticmethod
+    def _named(m):
+        if hasattr(m, "_names"):                      # oracle module: reference state_dict names
+            return list(zip(m._names, m.params))
+        # engine module: parameters() order registers the upSample2 block under `convLayer` (model.py:227)
+        return [(n.replace("convLayer.", "upSample2.") if n.startswith("convLayer.") else n, p)
+                for n, p in m.named_parameters()]
+
+    def step(self):
+        self.grads = [{n: p.grad.detach().flatten().cpu() for n, p in self._named(m) if p.grad is not None}
+                      for m in self.modules]
+        return self.opt.step()
+
+
+@pytest.mark.parametrize("mode", ["parity", "c8"])
+def test_full_train_step_at_batch16_vs_oracle(env, mode):
+    """BASELINE configs[2]: one full optimisation step (train.py:186-299) at batch 16 from seed 0,
+    engine vs the oracle modules on the CPU: both losses, the packed gradients of the two generators
+    at generator_optimizer.step() and of the four discriminators at discriminator_optimizer.step()."""
+    pkg = env["pkg"]
+    e = pkg.engine
+    from maskcyclegan_vc_b200 import trainstep as ts
+    batch = O.synthetic_batch(16, 64, seed=4321)
+    torch.manual_seed(0)
+    om = [O.OracleGenerator(), O.OracleGenerator(), O.OracleDiscriminator(), O.OracleDiscriminator(),
+          O.OracleDiscriminator(), O.OracleDiscriminator()]
+    og = _CapturingOpt(torch.optim.Adam(list(om[0].parameters()) + list(om[1].parameters()), lr=2e-4, betas=(0.5, 0.999)), om[:2])
+    od = _CapturingOpt(torch.optim.Adam([p for m in om[2:] for p in m.parameters()], lr=1e-4, betas=(0.5, 0.999)), om[2:])
+    gl_o, dl_o = O.train_step(*om, og, od, batch)
+    e.set_precision(e.PRECISION_C8 if mode == "c8" else e.PRECISION_PARITY)
+    try:
+        models = ts.build_models(pkg.Generator, pkg.Discriminator, torch.device("cuda"), seed=0)
+        g_opt, d_opt = ts.build_optimizers(models)
+        eg, ed = _CapturingOpt(g_opt, models[:2]), _CapturingOpt(d_opt, models[2:])
+        gl, dl = ts.train_step(models, eg, ed, [t.cuda() for t in batch])
+        torch.cuda.synchronize()
+    finally:
+        e.set_precision(e.PRECISION_PARITY)
+    assert abs(gl.item() - gl_o) < TOL * abs(gl_o), (gl.item(), gl_o)
+    assert abs(dl.item() - dl_o) < TOL * abs(dl_o), (dl.item(), dl_o)
+    for name, got, want in (("G", eg.grads, og.grads), ("D", ed.grads, od.grads)):
+        assert len(got) == len(want)
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert sorted(a.keys()) == sorted(b.keys()), (name, i)      # same tensors get a gradient (downSample4: none)
+            fa, fb = torch.cat([a[k] for k in b]), torch.cat([b[k] for k in b])
+            assert rel(fa, fb) < TOL, (mode, name, i, rel(fa, fb))
