@@ -27,6 +27,10 @@ extern "C" {
 #define MCGVC_PRECISION_C8 4      /* fp16 main pass + two e4m3 correction passes (2 MMA units per MAC instead of 3):
                                      A*W ~= Ah*Wh + 2^-s (A8h*W8l + A8l*W8h); stems and heads stay split-bf16 x3.
                                      Weights must be packed in the mode they are used in. */
+#define MCGVC_PRECISION_C8H 5     /* forward exactly as C8 (Generator output inside the 1e-3 gate); the backward GEMMs of the
+                                     C8 layers run ONE fp16 pass over the same operands' 16-bit planes (dynamic power-of-two
+                                     scale on dz): gradients are TF32-class (~1e-3 relative), i.e. the accuracy class of the
+                                     reference's own CUDA default (cudnn.allow_tf32).  Same packed layout as C8. */
 
 const char* mcgvc_last_error(void);
 int mcgvc_set_device(int device);

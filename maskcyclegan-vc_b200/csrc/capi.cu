@@ -16,6 +16,7 @@ static int initial_precision() {
   const char* e = getenv("MCGVC_PRECISION");
   if (!e) return MCGVC_PRECISION_PARITY;
   if (!strcmp(e, "c8") || !strcmp(e, "4")) return MCGVC_PRECISION_C8;
+  if (!strcmp(e, "c8h") || !strcmp(e, "5")) return MCGVC_PRECISION_C8H;
   if (!strcmp(e, "mixed") || !strcmp(e, "2")) return MCGVC_PRECISION_MIXED;
   if (!strcmp(e, "fast") || !strcmp(e, "1")) return MCGVC_PRECISION_FAST;
   return MCGVC_PRECISION_PARITY;
@@ -53,10 +54,11 @@ static DevStreams* dev_streams() {
   return &d;
 }
 static RunCfg cfg(void* stream, bool backward = false) {
-  int np = (g_precision == MCGVC_PRECISION_PARITY || g_precision == MCGVC_PRECISION_C8)
-               ? 3 : (g_precision == MCGVC_PRECISION_FAST ? 1 : (backward ? 1 : 3));
-  RunCfg rc{(cudaStream_t)stream, g_backend, np, nullptr, nullptr, 0};
-  rc.c8 = g_precision == MCGVC_PRECISION_C8;   // stems / heads stay split-bf16 x3 in this mode
+  const bool c8 = g_precision == MCGVC_PRECISION_C8 || g_precision == MCGVC_PRECISION_C8H;
+  int np = (g_precision == MCGVC_PRECISION_PARITY || c8) ? 3 : (g_precision == MCGVC_PRECISION_FAST ? 1 : (backward ? 1 : 3));
+  RunCfg rc{(cudaStream_t)stream, g_backend, np, nullptr, nullptr, 0, 0};
+  rc.c8 = c8;   // stems / heads / 1-D trunk stay split-bf16 x3 in these modes
+  rc.half16 = (g_precision == MCGVC_PRECISION_C8H && backward) ? 1 : 0;
   return rc;
 }
 // run a backward body on the engine streams, bracketed by event hand-offs with the caller's stream
@@ -210,8 +212,8 @@ int mcgvc_set_backend(int backend) {
 }
 int mcgvc_set_precision(int mode) {
   if (mode != MCGVC_PRECISION_PARITY && mode != MCGVC_PRECISION_FAST && mode != MCGVC_PRECISION_MIXED &&
-      mode != MCGVC_PRECISION_C8) {
-    set_error("precision must be MCGVC_PRECISION_PARITY (3), _MIXED (2), _FAST (1) or _C8 (4)");
+      mode != MCGVC_PRECISION_C8 && mode != MCGVC_PRECISION_C8H) {
+    set_error("precision must be MCGVC_PRECISION_PARITY (3), _MIXED (2), _FAST (1), _C8 (4) or _C8H (5)");
     return 1;
   }
   g_precision = mode;

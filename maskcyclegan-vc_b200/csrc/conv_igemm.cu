@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <vector>
 
@@ -219,6 +220,15 @@ bool choose_box(int B, int Y, int X, int boxPositions, int* oBX, int* oBY, int* 
 }
 
 
+// C8H backward: scale of a single fp16 pass over C8 operand planes (1 for every other call)
+template <int NPASS>
+__device__ __forceinline__ float half16_scale(const ConvGeom& g) {
+  if (NPASS != 1 || !g.half16) return 1.f;
+  float s = g.c8OutScale;
+  if (g.c8RecA && g.c8RecW) s *= __ldg(g.c8RecA) * __ldg(g.c8RecW);
+  return s;
+}
+
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK_N, int NPASS>
 struct ConvCfg {
@@ -331,7 +341,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+    // kind::f16 input format bits [7,10) / [10,13): 1 = bf16, 0 = fp16 (C8H backward on fp16 planes)
+    const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, BLOCK_N, 0, 0) & ~((NPASS == 1 && g.half16) ? ((1u << 7) | (1u << 10)) : 0u);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -373,6 +384,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     // ------------------------------------------------------------------ epilogue
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
+    const float osc = half16_scale<NPASS>(g);
     int it = 0;
     for (int item = blockIdx.x; item < totalItems; item += gridDim.x, ++it) {
       const int tile = item / kSplit;
@@ -406,6 +418,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         uint32_t v[32];
         ptx::tmem_ld32(taddr + j * 32, v);
         ptx::tmem_ld_wait();
+        if (NPASS == 1 && g.half16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(osc * __uint_as_float(v[i]));
+        }
         epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b,
                        kSplit > 1, ks == 0);
       }
@@ -442,6 +458,7 @@ static bool check_conv_geom(const ConvGeom& g, int blockN) {
   if (g.nTaps < 1 || g.nTaps > kMaxTaps) { set_error("conv: nTaps=%d", g.nTaps); return false; }
   if (g.cBlocks != g.a.C / kBlockK) { set_error("conv: cBlocks"); return false; }
   if (g.nPass != 1 && g.nPass != 3) { set_error("conv: nPass=%d", g.nPass); return false; }
+  if (g.half16 && g.nPass != 1) { set_error("conv: half16 needs nPass = 1"); return false; }
   if (g.nGroups < 1 || g.nGroups > 4) { set_error("conv: nGroups=%d", g.nGroups); return false; }
   for (int i = 0; i < g.nGroups; ++i)
     if (g.grpTapCount[i] < 1 || g.grpTapStart[i] + g.grpTapCount[i] > g.nTaps) { set_error("conv: group %d taps", i); return false; }
@@ -612,7 +629,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     }
   } else if (warp == 1 && lane == 0 && leader) {
     // ------------------------------------------------------------------ MMA issuer (leader only)
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kTileM, BLOCK_N, 0, 0);
+    const uint32_t idesc = ptx::umma_idesc_bf16(2 * kTileM, BLOCK_N, 0, 0) & ~((NPASS == 1 && g.half16) ? ((1u << 7) | (1u << 10)) : 0u);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -654,6 +671,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (both CTAs)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    const float osc = half16_scale<NPASS>(g);
     int it = 0;
     for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
       const int tile = item / kSplit;
@@ -690,6 +708,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         uint32_t v[32];
         ptx::tmem_ld32(taddr + j * 32, v);
         ptx::tmem_ld_wait();
+        if (NPASS == 1 && g.half16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(osc * __uint_as_float(v[i]));
+        }
         epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b,
                        kSplit > 1, ks == 0);
       }
@@ -892,8 +914,8 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvGeom g) {
     const long long aoff = ((((long long)b * g.a.P + tap.plane) * g.a.Y + yy) * g.a.X + xx) * g.a.C;
     const long long woff = ((long long)tap.w * g.w.N + n) * g.w.K;
     for (int c = 0; c < g.a.C; ++c) {
-      const float ah = bf16_bits_to_f(Ah[aoff + c]);
-      const float wh = bf16_bits_to_f(Wh[woff + c]);
+      const float ah = g.half16 ? __half2float(__ushort_as_half(Ah[aoff + c])) : bf16_bits_to_f(Ah[aoff + c]);
+      const float wh = g.half16 ? __half2float(__ushort_as_half(Wh[woff + c])) : bf16_bits_to_f(Wh[woff + c]);
       acc = fmaf(ah, wh, acc);
       if (g.nPass == 3) {
         const float al = bf16_bits_to_f(Al[aoff + c]);
@@ -905,6 +927,11 @@ __global__ void conv_simt_kernel(const __grid_constant__ ConvGeom g) {
   }
   const long long off = g.grpOutOff[grp] + (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
                         (long long)(n / g.nSplit) * g.sNhi + (n % g.nSplit);
+  if (g.half16) {
+    float sc = g.c8OutScale;
+    if (g.c8RecA && g.c8RecW) sc *= g.c8RecA[0] * g.c8RecW[0];
+    acc *= sc;
+  }
   if (g.bias) acc += g.bias[n];
   if (g.addsrc) acc += g.addsrc[off];
   g.out[off] = acc;

@@ -76,6 +76,9 @@ struct ConvGeom {
   float c8OutScale, c8CorrScale;
   const float* c8RecA;  // device-side scale records {1/S, 1/E} of the two operands (null: host multipliers only)
   const float* c8RecW;
+  // "C8H" backward (nPass = 1 on C8 operand planes): ONE fp16 MMA per MAC on the 16-bit planes only,
+  // out = c8OutScale * recA[0] * recW[0] * D; the e4m3 planes are not read.
+  int half16;
 };
 
 // Weight-gradient GEMM:  dW[w_t][n][c] += sum over positions (b,y,x) in this CTA's K-slice of
@@ -101,6 +104,7 @@ struct WgradGeom {
   float c8OutScale, c8CorrScale;
   const float* c8RecZ;   // device-side scale records {1/S, 1/E} of dz and x (null: host multipliers only)
   const float* c8RecX;
+  int half16;            // nPass = 1 on the fp16 planes of C8 operands, see ConvGeom::half16
 };
 
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);

@@ -56,6 +56,7 @@ __device__ __forceinline__ void store_planes(__nv_bfloat16* hi, __nv_bfloat16* l
   ph.x = *reinterpret_cast<const uint32_t*>(&h01);
   ph.y = *reinterpret_cast<const uint32_t*>(&h23);
   *reinterpret_cast<uint2*>(hi + off) = ph;
+  if (f.c8 == 2) return;   // C8H dz: only the fp16 plane is ever read (single-pass backward GEMMs)
   const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
   const float e = f.E, el = f.E * 2048.f;
   uint8_t* p8 = reinterpret_cast<uint8_t*>(lo);

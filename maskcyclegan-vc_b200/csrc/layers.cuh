@@ -13,7 +13,8 @@ namespace mcgvc {
 // form a stride-2 convolution consumes through TMA without element strides.
 // How a value v is written into an operand's planes.  c8 = 0: split-bf16 (hi = bf16(v), lo =
 // bf16(v - hi)).  c8 = 1 (conv_c8.cu / wgrad_c8.cu): hi = fp16(v*S); the `lo` storage (2 B/elem) holds
-// two e4m3 planes of `elems` bytes each: e4m3(hi*E) and e4m3((v*S - hi)*E*2^11).
+// two e4m3 planes of `elems` bytes each: e4m3(hi*E) and e4m3((v*S - hi)*E*2^11).  c8 = 2: the fp16 plane
+// only (dz tensors of the C8H mode, whose backward GEMMs run a single fp16 pass).
 struct PlaneFmt {
   int c8;
   float S, E;

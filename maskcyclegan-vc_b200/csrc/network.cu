@@ -397,6 +397,8 @@ ConvGeom conv_geom(Run& r, const ActOperand& a, const WgtOperand& w, const TapLi
 // C8 operands (fp16 + 2 x e4m3 planes on both sides) run on the C8 kernels; everything else on the
 // split-bf16 / bf16 kernels.
 bool is_c8(const ConvGeom& g) { return g.a.h8 != nullptr && g.w.h8 != nullptr; }
+// ... on the C8 kernels (fp16 + 2 x e4m3), unless this is a C8H backward call (single fp16 pass)
+bool on_c8_kernel(const Run& r, const ConvGeom& g) { return is_c8(g) && !r.rc.half16; }
 // C8 pair kernel tile width: 256-wide tiles when they still fill the chip, else 128-wide (two TMEM
 // buffer pairs, epilogue overlapped)
 long long c8_pair_tiles(const ConvGeom& g, int bn) {
@@ -409,6 +411,14 @@ int c8_block_n(const ConvGeom& g) {
   return wide ? 256 : 128;
 }
 cudaError_t launch_conv_any(Run& r, ConvGeom& g) {
+  if (is_c8(g) && r.rc.half16) {
+    g.nPass = 1;
+    g.half16 = 1;
+    g.c8OutScale = 1.f;
+    g.c8RecA = g.a.rec;
+    g.c8RecW = g.w.rec;
+    return r.rc.backend == 0 ? launch_conv_tc(g, r.rc.stream) : launch_conv_simt(g, r.rc.stream);
+  }
   if (is_c8(g)) {
     g.c8OutScale = 1.f;
     g.c8CorrScale = 1.f / 2048.f;   // 2^-11: pre-scale of the residual planes
@@ -432,8 +442,8 @@ void plan_split(Run& r, ConvGeom& g, long long splitFloats, double minGain, cons
   // 256-wide C8 tiles cannot overlap their epilogue with the next item's MMAs (D1 + D2 fill TMEM), so
   // the red.add epilogues of K slices land on the critical path: measured 124.9 -> 121.4 ms per step
   // with split-K off in C8 mode.  Only the 128-wide (double-buffered) C8 tiles may split.
-  if (is_c8(g) && c8_block_n(g) == 256) return;
-  const int s = is_c8(g) ? plan_ksplit_waves(c8_pair_tiles(g, 128), 74, g, minGain) : conv_plan_ksplit(g, minGain);
+  if (on_c8_kernel(r, g) && c8_block_n(g) == 256) return;
+  const int s = on_c8_kernel(r, g) ? plan_ksplit_waves(c8_pair_tiles(g, 128), 74, g, minGain) : conv_plan_ksplit(g, minGain);
   if (s <= 1) return;
   r.check(cudaMemsetAsync(g.out, 0, (size_t)splitFloats * sizeof(float), r.rc.stream), what);
   g.kSplit = s;
@@ -502,6 +512,15 @@ void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList&
   g.nPass = r.rc.nPass;
   g.algoFlops = 2.0 * pB * pY * pX * (double)g.N * g.C * xtaps.n * algoFrac;
   cudaStream_t ws = r.wgrad_stream();
+  if (dz.h8 && x.h8 && r.rc.half16) {   // C8H: one fp16 pass over the 16-bit planes
+    g.nPass = 1;
+    g.half16 = 1;
+    g.c8OutScale = 1.f;
+    g.c8RecZ = dz.rec;
+    g.c8RecX = x.rec;
+    r.check(r.rc.backend == 0 ? launch_wgrad_tc(g, ws) : launch_wgrad_simt(g, ws), what);
+    return;
+  }
   if (dz.h8 && x.h8) {
     g.cTile = x.C % 256 == 0 ? 256 : 128;
     g.c8OutScale = 1.f;
@@ -1004,7 +1023,8 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   // C8 mode: the dz of every normalised layer is written as C8 planes with its own scale record
   float* dzRecs = a.takeT<float>(2 * 32);
   int nRec = 0;
-  auto dz_pair = [&](long long elems) { return take_pair(a, elems, nullptr, rc.c8, rc.c8 ? dzRecs + 2 * nRec++ : nullptr); };
+  const int dzFmt = rc.c8 ? (rc.half16 ? 2 : 1) : 0;   // C8H: dz keeps only its fp16 plane
+  auto dz_pair = [&](long long elems) { return take_pair(a, elems, nullptr, dzFmt, rc.c8 ? dzRecs + 2 * nRec++ : nullptr); };
   const TapList one = taps_one();
 
   // ---- head                                                                    model.py:278
@@ -1318,7 +1338,7 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
   for (int l = 0; l < 3; ++l) {
     const Lvl& v = lv[l];
     const long long Mo = (long long)B * v.Yo * v.Xo;
-    BfPair dz = take_pair(a, Mo * v.Nz, nullptr, rc.c8, rc.c8 ? dzRecs + 2 * nRec++ : nullptr);
+    BfPair dz = take_pair(a, Mo * v.Nz, nullptr, rc.c8 ? (rc.half16 ? 2 : 1) : 0, rc.c8 ? dzRecs + 2 * nRec++ : nullptr);
     run_bwd(r, mk_bwd(kINSwish, v.z, v.Nz, v.Yo, v.Xo, v.st, v.Nz, W.gamma(nm[v.ni]), W.beta(nm[v.ni]), 1,
                       gbuf(dAct, B, v.Yo, v.Xo, v.Nz, dActParity), tp, gGa(v.ni), gBe(v.ni), dz, nullptr),
             "D ds bwd");

@@ -17,6 +17,7 @@
 #include "tmap.cuh"
 
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 namespace mcgvc {
 
@@ -144,7 +145,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant_
       }
     } else if (warp == 1 && lane == 0) {
       // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, CTILE, 1, 1);
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, CTILE, 1, 1) & ~((NPASS == 1 && g.half16) ? ((1u << 7) | (1u << 10)) : 0u);
       constexpr uint32_t kLbo = kChunkBytes;  // next 64-channel chunk
       constexpr uint32_t kSbo = 1024;         // next 8-position group
       int stage = 0;
@@ -177,6 +178,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant_
       const int quad = warp & 3;
       const int n = n0 + quad * 32 + lane;
       float* drow = g.dw + ((long long)tap.w * g.N + n) * g.C + c0;
+      float osc = 1.f;      // C8H: single fp16 pass over C8 operand planes, scaled by their records
+      if (NPASS == 1 && g.half16) {
+        osc = g.c8OutScale;
+        if (g.c8RecZ && g.c8RecX) osc *= __ldg(g.c8RecZ) * __ldg(g.c8RecX);
+      }
       ptx::mbar_wait(tfull, 0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -187,8 +193,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant_
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
-          red_add_v4(drow + j * 32 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                     __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          red_add_v4(drow + j * 32 + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
+                     osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
       }
     }
   }
@@ -206,6 +212,7 @@ static bool check_wgrad_geom(const WgradGeom& g) {
   if (g.C % g.cTile) { set_error("wgrad: C=%d %% cTile=%d", g.C, g.cTile); return false; }
   if (g.nTaps < 1 || g.nTaps > kMaxTaps || g.splitK < 1) { set_error("wgrad: taps/splitK"); return false; }
   if (g.nPass != 1 && g.nPass != 3) { set_error("wgrad: nPass=%d", g.nPass); return false; }
+  if (g.half16 && g.nPass != 1) { set_error("wgrad: half16 needs nPass = 1"); return false; }
   return true;
 }
 
@@ -361,7 +368,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1 && lane == 0 && leader) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, CTILE, 1, 1);
+      const uint32_t idesc = ptx::umma_idesc_bf16(256, CTILE, 1, 1) & ~((NPASS == 1 && g.half16) ? ((1u << 7) | (1u << 10)) : 0u);
       constexpr uint32_t kLbo = kChunkBytes;
       constexpr uint32_t kSbo = 1024;
       int stage = 0;
@@ -393,6 +400,11 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant
       const int quad = warp & 3;
       const int n = n0 + quad * 32 + lane;
       float* drow = g.dw + ((long long)tap.w * g.N + n) * g.C + c0;
+      float osc = 1.f;      // C8H: single fp16 pass over C8 operand planes, scaled by their records
+      if (NPASS == 1 && g.half16) {
+        osc = g.c8OutScale;
+        if (g.c8RecZ && g.c8RecX) osc *= __ldg(g.c8RecZ) * __ldg(g.c8RecX);
+      }
       ptx::mbar_wait(tfull, 0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -403,8 +415,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
-          red_add_v4(drow + j * 32 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                     __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          red_add_v4(drow + j * 32 + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
+                     osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
       }
     }
   }
@@ -508,7 +520,8 @@ __global__ void wgrad_simt_kernel(const __grid_constant__ WgradGeom g) {
         const long long zo = ((((long long)b * g.dz.P) * g.dz.Y + zy) * g.dz.X + zx) * g.dz.C + n;
         const long long xo =
             ((((long long)b * g.x.P + tap.plane) * g.x.Y + xy) * g.x.X + xx) * g.x.C + c;
-        const float zh = bf16_bits(Zh[zo]), xh = bf16_bits(Xh[xo]);
+        const float zh = g.half16 ? __half2float(__ushort_as_half(Zh[zo])) : bf16_bits(Zh[zo]);
+        const float xh = g.half16 ? __half2float(__ushort_as_half(Xh[xo])) : bf16_bits(Xh[xo]);
         acc = fmaf(zh, xh, acc);
         if (g.nPass == 3) {
           acc = fmaf(zh, bf16_bits(Xl[xo]), acc);
@@ -516,6 +529,11 @@ __global__ void wgrad_simt_kernel(const __grid_constant__ WgradGeom g) {
         }
       }
     }
+  }
+  if (g.half16) {
+    float sc = g.c8OutScale;
+    if (g.c8RecZ && g.c8RecX) sc *= g.c8RecZ[0] * g.c8RecX[0];
+    acc *= sc;
   }
   atomicAdd(g.dw + ((long long)tap.w * g.N + n) * g.C + c, acc);
 }

@@ -16,6 +16,7 @@ PRECISION_PARITY = 3   # split-bf16 x3 (default; meets the 1e-3 parity gate)
 PRECISION_MIXED = 2    # forward split-bf16 x3, backward single bf16 pass
 PRECISION_FAST = 1     # single bf16 pass
 PRECISION_C8 = 4       # fp16 main pass + two e4m3 correction passes (2 MMA units per MAC); parity-class accuracy
+PRECISION_C8H = 5      # forward as C8; backward GEMMs of the C8 layers: one fp16 pass (TF32-class gradients)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcgvc.so")
 _lib = None
@@ -108,6 +109,13 @@ def graph_stats():
 
 def get_precision():
     return lib().mcgvc_get_precision()
+
+
+def pack_class(precision=None):
+    """Modes that share one packed-weight layout: split-bf16 planes (parity / mixed / fast) or the
+    fp16 + 2 x e4m3 planes (C8 / C8H)."""
+    p = get_precision() if precision is None else precision
+    return 1 if p in (PRECISION_C8, PRECISION_C8H) else 0
 
 
 def param_count(model):

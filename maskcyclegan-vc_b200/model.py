@@ -158,7 +158,7 @@ class _EngineModule(nn.Module):
 
     def _version(self):
         # the packed layout depends on the precision mode (C8 keeps fp16 + e4m3 planes)
-        return (engine.get_precision(), self._weights_epoch * 1000003 + sum(p._version for p in self._unique_params()))
+        return (engine.pack_class(), self._weights_epoch * 1000003 + sum(p._version for p in self._unique_params()))
 
     def _packed_weights(self):
         self._ensure_device_state()
