@@ -134,7 +134,8 @@ def test_opt_in_entry_points_validate_their_arguments(pkg):
     assert lib.mcgvc_loss_term(p, null, ctypes.c_longlong(1), 7, ctypes.c_float(0), ctypes.c_float(1), p, null) == 1   # unknown kind
     assert b"loss_term" in lib.mcgvc_last_error()
     assert lib.mcgvc_set_precision(4) == 0 and lib.mcgvc_get_precision() == 4      # MCGVC_PRECISION_C8
-    assert lib.mcgvc_set_precision(5) == 1
+    assert lib.mcgvc_set_precision(5) == 0 and lib.mcgvc_get_precision() == 5      # MCGVC_PRECISION_C8H
+    assert lib.mcgvc_set_precision(6) == 1
     assert lib.mcgvc_set_precision(3) == 0
 
 
