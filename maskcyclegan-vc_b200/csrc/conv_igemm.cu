@@ -161,6 +161,21 @@ bool make_wgt_tmap(CUtensorMap* m, const void* base, const WgtOperand& w, int bo
   return true;
 }
 
+bool make_tmap16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                 const unsigned long long* stridesBytes, const unsigned int* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = stridesBytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rank %d) failed: %d", rank, (int)r); return false; }
+  return true;
+}
+
 bool make_plane8_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int boxC, int BX, int BY, int BB) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;

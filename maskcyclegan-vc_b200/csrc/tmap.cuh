@@ -14,4 +14,9 @@ bool make_plane8_tmap(CUtensorMap* m, const void* base, const ActOperand& a, int
 // e4m3 plane of the weights [T][N][K]: box (64 B, boxN, 1), 64B swizzle
 bool make_wgt8_tmap(CUtensorMap* m, const void* base, const WgtOperand& w, int boxN);
 
+// generic 16-bit tiled map (rank <= 5), 128B swizzle, zero OOB fill: dims / box innermost first,
+// stridesBytes[i] = byte stride of dimension i+1
+bool make_tmap16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                 const unsigned long long* stridesBytes, const unsigned int* box);
+
 }  // namespace mcgvc

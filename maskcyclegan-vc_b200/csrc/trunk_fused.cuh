@@ -1,0 +1,50 @@
+// Fused forward of the Generator's six gated 1-D residual blocks (reference
+// mask_cyclegan_vc/model.py:40-76 ResidualLayer, :258-263): ONE launch instead of 36.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace mcgvc {
+
+constexpr int kTrunkBlocks = 6;
+
+// Everything the kernel needs besides the tensor maps.  All activation tensors are rows (b, x) of the
+// [B][W2] position grid, channels innermost; block i reads R[i] and writes z4[i], st4[i], H[i], z5[i],
+// st5[i], R[i+1] -- exactly the tensors the layer-by-layer path saves for the backward pass.
+struct TrunkFwdArgs {
+  int B, W2;
+  int BX, BB;                  // tile = BB samples x BX positions = 128 rows (BX = pow2 >= W2)
+  int nPass;                   // 3 = split-bf16, 1 = bf16
+  float* Rf[kTrunkBlocks + 1];                 // [L][256] fp32
+  __nv_bfloat16* Rhi[kTrunkBlocks + 1];        // [L][256]
+  __nv_bfloat16* Rlo[kTrunkBlocks + 1];
+  __nv_bfloat16* Hhi[kTrunkBlocks];            // [L][512]
+  __nv_bfloat16* Hlo[kTrunkBlocks];
+  float* z4[kTrunkBlocks];                     // [L][1024] raw conv || gate output
+  float* z5[kTrunkBlocks];                     // [L][256]
+  float* mean4[kTrunkBlocks];                  // [B][1024]
+  float* rstd4[kTrunkBlocks];
+  float* mean5[kTrunkBlocks];                  // [B][256]
+  float* rstd5[kTrunkBlocks];
+  const float* biasA[kTrunkBlocks];            // [1024] engine order (conv || gate)
+  const float* gammaA[kTrunkBlocks];
+  const float* betaA[kTrunkBlocks];
+  const float* biasB[kTrunkBlocks];            // [256]
+  const float* gammaB[kTrunkBlocks];
+  const float* betaB[kTrunkBlocks];
+};
+
+// Operand planes for the tensor maps: plane base of block 0 and the (uniform) byte distance between
+// consecutive blocks' planes.
+struct TrunkFwdMaps {
+  const void* Rhi; const void* Rlo; long long RStrideBytes;       // R[i] planes, [B][W2][256]
+  const void* Hhi; const void* Hlo; long long HStrideBytes;       // H[i] planes, [B][W2][512]
+  const void* Wah; const void* Wal; long long WaStrideBytes;      // conv a weights [3][1024][256]
+  const void* Wbh; const void* Wbl; long long WbStrideBytes;      // conv b weights [3][256][512]
+};
+
+// true when the fused kernel covers this shape (else the caller runs the layer-by-layer path)
+bool trunk_fwd_supported(int B, int W2);
+cudaError_t launch_trunk_fwd(const TrunkFwdArgs& a, const TrunkFwdMaps& m, cudaStream_t stream);
+
+}  // namespace mcgvc

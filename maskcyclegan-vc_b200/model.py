@@ -156,13 +156,13 @@ class _EngineModule(nn.Module):
             self._reset_backward_state()
             self._gblob.zero_()
 
-    def _version(self):
+    def _weights_version(self):
         # the packed layout depends on the precision mode (C8 keeps fp16 + e4m3 planes)
         return (engine.pack_class(), self._weights_epoch * 1000003 + sum(p._version for p in self._unique_params()))
 
     def _packed_weights(self):
         self._ensure_device_state()
-        v = self._version()
+        v = self._weights_version()
         if self._packed is None or v != self._packed_version:
             self._packed = engine.pack_weights(self.MODEL, self._flat)
             self._packed_version = v

@@ -651,10 +651,11 @@ def test_full_train_step_at_batch16_vs_oracle(env, mode):
     """BASELINE configs[2]: one full optimisation step (train.py:186-299) at batch 16 from seed 0 through
     trainstep.train_step, engine vs the oracle modules on the CPU.  The two phases are refereed
     element-wise at 1e-3 by the two tests above (each from identical weights); here the composition is
-    checked: g_loss (before any update) within 1e-3; d_loss and the discriminators' packed gradients, which
-    are evaluated AFTER the generators' Adam update, within 5e-3 -- Adam turns the fp32 noise on the
-    gradient elements that are mathematically zero (conv biases feeding InstanceNorm, SURVEY.md section 5
-    quirk 5) and the L1 sign flips into lr-sized weight differences between ANY two fp32 implementations;
+    checked: g_loss (before any update) and d_loss within 1e-3 (measured 0 / 6e-7); the discriminators'
+    packed gradients, which are evaluated AFTER the generators' first Adam update, within 1e-2 (measured
+    2e-3 ... 6e-3 in both modes): Adam's first step is lr * sign(g) for EVERY element, so each gradient
+    element whose sign differs between two fp32 implementations (elements that are mathematically zero,
+    SURVEY.md section 5 quirk 5, and the L1 sign flips) moves its weight by 2 * lr in opposite directions;
     the generators' gradients at generator_optimizer.step() per tensor by norm within 5e-3."""
     pkg = env["pkg"]
     e = pkg.engine
@@ -690,9 +691,9 @@ def test_full_train_step_at_batch16_vs_oracle(env, mode):
     rep["G tensor norms (worst)"] = worst
     print("full step B=16 [%s]:" % mode, {k: "%.2e" % v for k, v in rep.items()})
     assert rep["g_loss"] < TOL, rep
-    assert rep["d_loss"] < 5e-3, rep
+    assert rep["d_loss"] < TOL, rep
     for i in range(4):
-        assert rep["D%d" % i] < 5e-3, rep
+        assert rep["D%d" % i] < 1e-2, rep
     assert worst < 5e-3, rep
 
 
@@ -716,8 +717,9 @@ def test_c8h_forward_is_c8_and_gradients_meet_the_stated_gate(env, B, T):
         finally:
             e.set_precision(e.PRECISION_PARITY)
     # the forward pass IS the C8 forward pass (same kernels, same planes; bitwise equality is not
-    # guaranteed by either mode: statistics and split-K partials merge with floating-point atomics)
-    assert rel(outs["c8h"], outs["c8"]) < 1e-5
+    # guaranteed by either mode: statistics and split-K partials merge with floating-point atomics, and
+    # two C8 runs of the same input differ by ~1.5e-5 after the operand re-quantisation of 9 layers)
+    assert rel(outs["c8h"], outs["c8"]) < 1e-4
     e.set_precision(e.PRECISION_C8H)
     try:
         bwd = net_check.check_backward(env["G"], env["D"], env["gs"], env["ds"], B, T, verbose=False)
