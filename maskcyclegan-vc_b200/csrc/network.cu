@@ -2,6 +2,7 @@
 // schedules of the Generator and Discriminator (reference mask_cyclegan_vc/model.py:239-280 and
 // :340-349; backward = what autograd derives for them, train.py:241,298).
 #include "network.cuh"
+#include "trunk_fused.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -919,7 +920,53 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
                                               abuf(s.R[0], s.Rf[0], B, 1, d.W2, 256, 0)), st), "G 2dto1d IN");
   // six gated 1-D residual blocks                                                model.py:258-263
   const TapList k3 = taps_s1(1, 3, 0, 1, 1);
-  for (int i = 0; i < 6; ++i) {
+  bool trunkFused = false;
+  if (r.ok && r.rc.backend == 0 && trunk_fwd_supported(B, d.W2)) {
+    // ONE launch for the whole chain (trunk_fused.cu) when the saved-blob / packed-blob layouts are
+    // uniform across the six blocks (they are: identical blocks allocated in one loop)
+    TrunkFwdArgs ta{};
+    TrunkFwdMaps tm{};
+    ta.B = B; ta.W2 = d.W2; ta.nPass = r.rc.nPass;
+    ta.BX = 4;
+    while (ta.BX < d.W2) ta.BX *= 2;
+    ta.BB = 128 / ta.BX;
+    bool uniform = true;
+    auto bytes_between = [](const void* a, const void* b) { return (long long)(reinterpret_cast<const uint8_t*>(b) - reinterpret_cast<const uint8_t*>(a)); };
+    tm.Rhi = s.R[0].hi; tm.Rlo = s.R[0].lo; tm.RStrideBytes = bytes_between(s.R[0].hi, s.R[1].hi);
+    tm.Hhi = s.H[0].hi; tm.Hlo = s.H[0].lo; tm.HStrideBytes = bytes_between(s.H[0].hi, s.H[1].hi);
+    const ConvDesc& a0 = cv[G_RES0];
+    const ConvDesc& b0c = cv[G_RES0 + 1];
+    tm.Wah = W.bf + a0.fHi; tm.Wal = W.bf + a0.fLo; tm.WaStrideBytes = (cv[G_RES0 + 2].fHi - a0.fHi) * 2;
+    tm.Wbh = W.bf + b0c.fHi; tm.Wbl = W.bf + b0c.fLo; tm.WbStrideBytes = (cv[G_RES0 + 3].fHi - b0c.fHi) * 2;
+    for (int i = 0; i < 7; ++i) {
+      ta.Rf[i] = s.Rf[i]; ta.Rhi[i] = s.R[i].hi; ta.Rlo[i] = s.R[i].lo;
+      uniform = uniform && bytes_between(s.R[0].hi, s.R[i].hi) == i * tm.RStrideBytes &&
+                bytes_between(s.R[0].lo, s.R[i].lo) == i * tm.RStrideBytes;
+    }
+    for (int i = 0; i < 6; ++i) {
+      const ConvDesc& ca = cv[G_RES0 + 2 * i];
+      const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
+      const NormDesc& na = nm[GN_RES0 + 2 * i];
+      const NormDesc& nb = nm[GN_RES0 + 2 * i + 1];
+      ta.Hhi[i] = s.H[i].hi; ta.Hlo[i] = s.H[i].lo;
+      ta.z4[i] = s.z4[i]; ta.z5[i] = s.z5[i];
+      ta.mean4[i] = s.st4[i].mean; ta.rstd4[i] = s.st4[i].rstd;
+      ta.mean5[i] = s.st5[i].mean; ta.rstd5[i] = s.st5[i].rstd;
+      ta.biasA[i] = W.bias(ca); ta.gammaA[i] = W.gamma(na); ta.betaA[i] = W.beta(na);
+      ta.biasB[i] = W.bias(cb); ta.gammaB[i] = W.gamma(nb); ta.betaB[i] = W.beta(nb);
+      uniform = uniform && bytes_between(s.H[0].hi, s.H[i].hi) == i * tm.HStrideBytes &&
+                bytes_between(s.H[0].lo, s.H[i].lo) == i * tm.HStrideBytes &&
+                (ca.fHi - a0.fHi) * 2 == i * tm.WaStrideBytes && (ca.fLo - a0.fLo) * 2 == i * tm.WaStrideBytes &&
+                (cb.fHi - b0c.fHi) * 2 == i * tm.WbStrideBytes && (cb.fLo - b0c.fLo) * 2 == i * tm.WbStrideBytes;
+    }
+    if (uniform) {
+      // the statistics-pool slices of the layer-by-layer path stay reserved (same pool layout either way)
+      for (int i = 0; i < 6; ++i) { sp.take(B, 1024); sp.take(B, 256); }
+      r.check(launch_trunk_fwd(ta, tm, st), "G fused trunk");
+      trunkFused = true;
+    }
+  }
+  for (int i = 0; i < 6 && !trunkFused; ++i) {
     const ConvDesc& ca = cv[G_RES0 + 2 * i];
     const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
     const NormDesc& na = nm[GN_RES0 + 2 * i];

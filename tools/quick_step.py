@@ -16,7 +16,8 @@ from maskcyclegan_vc_b200 import trainstep as ts  # noqa: E402
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "mixed": eng.PRECISION_MIXED, "fast": eng.PRECISION_FAST}[mode])
+eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8h": eng.PRECISION_C8H, "mixed": eng.PRECISION_MIXED,
+                   "fast": eng.PRECISION_FAST}[mode])
 dev = torch.device("cuda", 0)
 models = ts.build_models(pkg.Generator, pkg.Discriminator, dev, seed=0)
 g_opt, d_opt = ts.build_optimizers(models)
@@ -44,4 +45,10 @@ def gfb():
     G0(batch[0], batch[1]).sum().backward()
 
 
-print("%s: G fwd+bwd %.3f ms | train step %.2f ms" % (mode, timeit(gfb, 10), timeit(lambda: ts.train_step(models, g_opt, d_opt, batch), reps)), flush=True)
+def gf():
+    with torch.no_grad():
+        G0(batch[0], batch[1])
+
+
+print("%s: G fwd %.3f ms | G fwd+bwd %.3f ms | train step %.2f ms"
+      % (mode, timeit(gf, 20), timeit(gfb, 10), timeit(lambda: ts.train_step(models, g_opt, d_opt, batch), reps)), flush=True)
