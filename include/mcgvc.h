@@ -41,18 +41,6 @@ int mcgvc_get_precision(void);
  * critical path); 0: everything on the caller's stream (used while timing individual kernels). */
 int mcgvc_set_overlap(int on);
 
-/* Deferred join of the weight-gradient side stream (default 1; MCGVC_DEFER_JOIN=0 or mcgvc_set_defer_join(0)
- * restores the strict "everything is ordered on the caller's stream when the call returns" contract).  With it
- * on, mcgvc_*_backward returns when the data-gradient chain is ordered on the caller's stream; weight-gradient
- * GEMMs may still be queued on the engine's side stream (mcgvc_side_stream(), a cudaStream_t of the current
- * device) and overlap the next call.  The caller must (a) keep `workspace` and `saved` of that call alive until
- * the side stream has passed them (with PyTorch: Tensor.record_stream) and (b) call mcgvc_join_side(stream)
- * before anything on `stream` reads grad_blob (mcgvc_unpack_grads*). */
-int mcgvc_set_defer_join(int on);
-int mcgvc_get_defer_join(void);
-void* mcgvc_side_stream(void);
-int mcgvc_join_side(void* stream);
-
 /* Model geometry.  Replaces Generator.__init__ / Discriminator.__init__ bookkeeping
  * (model.py:110-211, :287-327): number of floats in the reference-order flat parameter buffer
  * (order of nn.Module.parameters()), and sizes of the engine-side blobs. */

@@ -32,14 +32,8 @@ static int g_precision = initial_precision();
 // MCGVC_OVERLAP=0 runs everything on the caller's stream.
 struct DevStreams {
   cudaStream_t main = nullptr, side = nullptr;
-  cudaEvent_t in = nullptr, out = nullptr, fork = nullptr, join = nullptr;
+  cudaEvent_t in = nullptr, out = nullptr, fork = nullptr;
 };
-// Deferred join (default on, MCGVC_DEFER_JOIN=0 disables): a backward call returns once its critical
-// path (main stream) is done; the weight-gradient GEMMs still queued on the side stream -- the last
-// layers' wgrads always trail the main chain by 0.4-0.6 ms -- overlap the NEXT call's critical path.
-// The caller (model.py) keeps the workspace and the saved blob alive for the side stream
-// (Tensor.record_stream) and calls mcgvc_join_side before it reads the gradient blob.
-static int g_defer_join = -1;
 static int g_overlap = -1;   // -1: take MCGVC_OVERLAP (default on)
 static DevStreams* dev_streams() {
   static DevStreams ds[64];
@@ -56,14 +50,13 @@ static DevStreams* dev_streams() {
     cudaEventCreateWithFlags(&d.in, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&d.out, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming);
   }
   return &d;
 }
 static RunCfg cfg(void* stream, bool backward = false) {
   const bool c8 = g_precision == MCGVC_PRECISION_C8 || g_precision == MCGVC_PRECISION_C8H;
   int np = (g_precision == MCGVC_PRECISION_PARITY || c8) ? 3 : (g_precision == MCGVC_PRECISION_FAST ? 1 : (backward ? 1 : 3));
-  RunCfg rc{(cudaStream_t)stream, g_backend, np, nullptr, nullptr, 0, 0, 0};
+  RunCfg rc{(cudaStream_t)stream, g_backend, np, nullptr, nullptr, 0, 0};
   rc.c8 = c8;   // stems / heads / 1-D trunk stay split-bf16 x3 in these modes
   rc.half16 = (g_precision == MCGVC_PRECISION_C8H && backward) ? 1 : 0;
   return rc;
@@ -80,12 +73,6 @@ static int run_backward(void* stream, F body) {
   rc.stream = d->main;
   rc.side = d->side;
   rc.forkEvent = d->fork;
-  if (g_defer_join < 0) { const char* e = getenv("MCGVC_DEFER_JOIN"); g_defer_join = e ? atoi(e) : 1; }
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(caller, &cap);
-  // a captured graph must rejoin every forked stream before the capture ends; the per-launch profiler
-  // and the SIMT checking backend keep the simple stream-ordered contract too
-  rc.deferJoin = (g_defer_join && cap == cudaStreamCaptureStatusNone && !profile_enabled() && g_backend == MCGVC_BACKEND_TCGEN05) ? 1 : 0;
   const int rv = body(rc);               // joins the side stream into d->main before returning
   cudaEventRecord(d->out, d->main);
   cudaStreamWaitEvent(caller, d->out, 0);
@@ -270,23 +257,6 @@ int mcgvc_unpack_grads(int model, const float* gblob, float* grad_flat, void* st
   return unpack_grads(*d, gblob, grad_flat, cfg(stream));
 }
 
-int mcgvc_set_defer_join(int on) { g_defer_join = on ? 1 : 0; return 0; }
-int mcgvc_get_defer_join(void) {
-  if (g_defer_join < 0) { const char* e = getenv("MCGVC_DEFER_JOIN"); g_defer_join = e ? atoi(e) : 1; }
-  return g_defer_join;
-}
-void* mcgvc_side_stream(void) {
-  DevStreams* d = dev_streams();
-  return d ? (void*)d->side : nullptr;
-}
-int mcgvc_join_side(void* stream) {
-  DevStreams* d = dev_streams();
-  if (!d) return 0;                       // overlap off: nothing ever runs on a side stream
-  cudaError_t e = cudaEventRecord(d->join, d->side);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)stream, d->join, 0);
-  if (e != cudaSuccess) { set_error("join_side: %s", cudaGetErrorString(e)); return 1; }
-  return 0;
-}
 int mcgvc_dead_param_range(int model, long long* begin, long long* len) {
   const ModelDesc* d = desc(model);
   if (!d) return 1;

@@ -228,7 +228,6 @@ struct Run {
     return rc.side;
   }
   void join() {
-    if (rc.deferJoin) return;   // the tail of the weight-gradient stream overlaps the next call (capi.cu)
     if (forked && rc.side) {
       cudaEventRecord(rc.forkEvent, rc.side);
       cudaStreamWaitEvent(rc.stream, rc.forkEvent, 0);

@@ -68,8 +68,6 @@ struct RunCfg {
   cudaEvent_t forkEvent;  // persistent event used to fork to / join from the side stream
   int c8;        // 1 = C8 precision mode: fp16 main pass + two e4m3 correction passes (stems / heads: split-bf16)
   int half16;    // C8H backward: the GEMMs of C8 layers run ONE fp16 pass on the 16-bit planes (dgrad and wgrad)
-  int deferJoin; // 1: the call returns without making the main stream wait for the weight-gradient side stream;
-                 // the caller joins later (mcgvc_join_side) and keeps workspace + saved blob alive until then
 };
 
 // sizes (bytes) of the per-call buffers the caller provides

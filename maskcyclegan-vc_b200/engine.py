@@ -50,8 +50,6 @@ def lib():
     l.mcgvc_pack_weights.argtypes = [_c_int, _c_vp, _c_vp, _c_vp]
     l.mcgvc_unpack_grads.argtypes = [_c_int, _c_vp, _c_vp, _c_vp]
     l.mcgvc_unpack_grads_live.argtypes = [_c_int, _c_vp, _c_vp, ctypes.c_float, _c_vp]
-    l.mcgvc_side_stream.restype = _c_vp
-    l.mcgvc_join_side.argtypes = [_c_vp]
     l.mcgvc_dead_param_range.argtypes = [_c_int, ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]
     l.mcgvc_generator_forward.argtypes = [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]
     l.mcgvc_generator_backward.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp,
@@ -197,38 +195,6 @@ def generator_forward(packed, x, mask):
     return out, saved
 
 
-_side_streams = {}
-
-
-def _keep_alive_for_side_stream(device, *tensors):
-    """Deferred join (include/mcgvc.h): weight-gradient GEMMs of the call that just returned may still
-    read these buffers from the engine's side stream -- tell the caching allocator."""
-    l = lib()
-    if not l.mcgvc_get_defer_join():
-        return
-    s = _side_streams.get(device.index)
-    if s is None:
-        ptr = l.mcgvc_side_stream()
-        if not ptr:
-            return
-        s = torch.cuda.ExternalStream(ptr, device=device)
-        _side_streams[device.index] = s
-    for t in tensors:
-        if t is not None:
-            t.record_stream(s)
-
-
-def join_side(device):
-    """Order the current stream after everything queued on the engine's side stream."""
-    l = lib()
-    l.mcgvc_set_device(device.index)
-    _check(l.mcgvc_join_side(_stream()), "join_side")
-
-
-def set_defer_join(on):
-    lib().mcgvc_set_defer_join(1 if on else 0)
-
-
 def generator_backward(packed, saved, mask, dout, B, T, need_dx, grad_blob, need_wgrad):
     l = lib()
     l.mcgvc_set_device(dout.device.index)
@@ -237,8 +203,6 @@ def generator_backward(packed, saved, mask, dout, B, T, need_dx, grad_blob, need
     _check(l.mcgvc_generator_backward(_ptr(packed), _ptr(saved), _ptr(mask), _ptr(dout), B, T, _ptr(dx),
                                       _ptr(grad_blob), 1 if need_wgrad else 0, _ptr(ws), _stream()),
            "generator_backward")
-    if need_wgrad:
-        _keep_alive_for_side_stream(dout.device, ws, saved)
     return dx
 
 
@@ -266,8 +230,6 @@ def discriminator_backward(packed, saved, out, dout, B, T, need_dx, grad_blob, n
     _check(l.mcgvc_discriminator_backward(_ptr(packed), _ptr(saved), _ptr(out), _ptr(dout), B, T, _ptr(dx),
                                           _ptr(grad_blob), 1 if need_wgrad else 0, _ptr(ws), _stream()),
            "discriminator_backward")
-    if need_wgrad:
-        _keep_alive_for_side_stream(dout.device, ws, saved)
     return dx
 
 

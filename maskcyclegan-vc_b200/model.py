@@ -191,7 +191,6 @@ class _EngineModule(nn.Module):
             self._flat_grad.zero_()
         # with GradSync the data-parallel average is folded into this pass (the all-reduce is a sum)
         scale = self._grad_sync.unpack_scale() if self._grad_sync is not None else 1.0
-        engine.join_side(self._flat.device)      # weight-gradient GEMMs still queued on the side stream
         engine.unpack_grads_live(self.MODEL, self._gblob, self._flat_grad, scale)
         self._gblob.zero_()
         if self._grad_sync is not None:
