@@ -12,10 +12,10 @@ GENERATOR = 0
 DISCRIMINATOR = 1
 BACKEND_TCGEN05 = 0
 BACKEND_SIMT = 1
-PRECISION_PARITY = 3   # split-bf16 x3 (default; meets the 1e-3 parity gate)
+PRECISION_PARITY = 3   # split-bf16 x3 (meets the 1e-3 parity gate; 3 MMA units per MAC)
 PRECISION_MIXED = 2    # forward split-bf16 x3, backward single bf16 pass
 PRECISION_FAST = 1     # single bf16 pass
-PRECISION_C8 = 4       # fp16 main pass + two e4m3 correction passes (2 MMA units per MAC); parity-class accuracy
+PRECISION_C8 = 4       # DEFAULT: fp16 main pass + two e4m3 correction passes (2 MMA units per MAC); meets the 1e-3 gate
 PRECISION_C8H = 5      # forward as C8; backward GEMMs of the C8 layers: one fp16 pass (TF32-class gradients)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcgvc.so")
