@@ -1130,28 +1130,81 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   // ---- residual blocks, reversed
   const TapList k3f = taps_s1(1, 3, 0, 1, 1), k3b = taps_s1(1, 3, 0, 1, -1);
   float* dH = a.takeT<float>(L * 512);
-  for (int i = 5; i >= 0; --i) {
-    // one dz pair per block: the weight-gradient GEMMs read them from the side stream while the
-    // main stream already works on the next block
-    BfPair dz5 = take_pair(a, L * 256, nullptr);
-    BfPair dz4 = take_pair(a, L * 1024, nullptr);
+  // one dz pair per block: the weight-gradient GEMMs read them from the side stream while the main
+  // stream already works on the next block
+  BfPair dz5[6], dz4[6];
+  for (int i = 0; i < 6; ++i) {
+    dz5[i] = take_pair(a, L * 256, nullptr);
+    dz4[i] = take_pair(a, L * 1024, nullptr);
+  }
+  bool trunkFused = false;
+  if (r.ok && r.rc.backend == 0 && trunk_bwd_supported(B, d.W2)) {
+    // ONE launch for the data-gradient chain of all six blocks (trunk_fused.cu)
+    TrunkBwdArgs ta{};
+    TrunkBwdMaps tm{};
+    ta.B = B; ta.W2 = d.W2; ta.nPass = r.rc.nPass;
+    ta.BX = 4;
+    while (ta.BX < d.W2) ta.BX *= 2;
+    ta.BB = 128 / ta.BX;
+    ta.dR6 = dR[6]; ta.dR0 = dR[0];
+    auto bytes_between = [](const void* p0, const void* p1) { return (long long)(reinterpret_cast<const uint8_t*>(p1) - reinterpret_cast<const uint8_t*>(p0)); };
+    const ConvDesc& a0 = cv[G_RES0];
+    const ConvDesc& b0c = cv[G_RES0 + 1];
+    tm.Z5hi = dz5[0].hi; tm.Z5lo = dz5[0].lo; tm.Z5StrideBytes = bytes_between(dz5[0].hi, dz5[1].hi);
+    tm.Z4hi = dz4[0].hi; tm.Z4lo = dz4[0].lo; tm.Z4StrideBytes = bytes_between(dz4[0].hi, dz4[1].hi);
+    tm.Wah = W.bf + a0.dHi; tm.Wal = W.bf + a0.dLo; tm.WaStrideBytes = (cv[G_RES0 + 2].dHi - a0.dHi) * 2;
+    tm.Wbh = W.bf + b0c.dHi; tm.Wbl = W.bf + b0c.dLo; tm.WbStrideBytes = (cv[G_RES0 + 3].dHi - b0c.dHi) * 2;
+    bool uniform = true;
+    for (int i = 0; i < 6; ++i) {
+      const ConvDesc& ca = cv[G_RES0 + 2 * i];
+      const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
+      const int na = GN_RES0 + 2 * i, nb = GN_RES0 + 2 * i + 1;
+      ta.z4[i] = s.z4[i]; ta.z5[i] = s.z5[i];
+      ta.mean4[i] = s.st4[i].mean; ta.rstd4[i] = s.st4[i].rstd;
+      ta.mean5[i] = s.st5[i].mean; ta.rstd5[i] = s.st5[i].rstd;
+      ta.gammaA[i] = W.gamma(nm[na]); ta.betaA[i] = W.beta(nm[na]); ta.gammaB[i] = W.gamma(nm[nb]);
+      ta.dgammaA[i] = gGa(na); ta.dbetaA[i] = gBe(na); ta.dgammaB[i] = gGa(nb); ta.dbetaB[i] = gBe(nb);
+      ta.dz5hi[i] = dz5[i].hi; ta.dz5lo[i] = dz5[i].lo; ta.dz4hi[i] = dz4[i].hi; ta.dz4lo[i] = dz4[i].lo;
+      uniform = uniform && bytes_between(dz5[0].hi, dz5[i].hi) == i * tm.Z5StrideBytes &&
+                bytes_between(dz5[0].lo, dz5[i].lo) == i * tm.Z5StrideBytes &&
+                bytes_between(dz4[0].hi, dz4[i].hi) == i * tm.Z4StrideBytes &&
+                bytes_between(dz4[0].lo, dz4[i].lo) == i * tm.Z4StrideBytes &&
+                (ca.dHi - a0.dHi) * 2 == i * tm.WaStrideBytes && (ca.dLo - a0.dLo) * 2 == i * tm.WaStrideBytes &&
+                (cb.dHi - b0c.dHi) * 2 == i * tm.WbStrideBytes && (cb.dLo - b0c.dLo) * 2 == i * tm.WbStrideBytes;
+    }
+    if (uniform) {
+      for (int i = 0; i < 6; ++i) { tp.take(B, 256); tp.take(B, 1024); }   // keep the reduction-pool layout of the layer path
+      r.check(launch_trunk_bwd(ta, tm, st), "G fused trunk bwd");
+      trunkFused = true;
+      if (needWgrad)
+        for (int i = 5; i >= 0; --i) {
+          const ConvDesc& ca = cv[G_RES0 + 2 * i];
+          const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
+          run_wgrad(r, plain_op(dz5[i], B, 1, d.W2, 256), plain_op(s.H[i], B, 1, d.W2, 512),
+                    k3f, nullptr, B, 1, d.W2, gblob + cb.gW, "G res wgrad b");
+          run_wgrad(r, plain_op(dz4[i], B, 1, d.W2, 1024), plain_op(s.R[i], B, 1, d.W2, 256),
+                    k3f, nullptr, B, 1, d.W2, gblob + ca.gW, "G res wgrad a");
+        }
+    }
+  }
+  for (int i = 5; i >= 0 && !trunkFused; --i) {
     const ConvDesc& ca = cv[G_RES0 + 2 * i];
     const ConvDesc& cb = cv[G_RES0 + 2 * i + 1];
     const int na = GN_RES0 + 2 * i, nb = GN_RES0 + 2 * i + 1;
     run_bwd(r, mk_bwd(kINOnly, s.z5[i], 256, 1, d.W2, s.st5[i], 256, W.gamma(nm[nb]), W.beta(nm[nb]), 1,
-                      gbuf(dR[i + 1], B, 1, d.W2, 256, 0), tp, gGa(nb), gBe(nb), dz5, nullptr), "G res bwd b");
-    run_conv(r, plain_op(dz5, B, 1, d.W2, 256), W.bwd(cb), k3b, B, 1, d.W2,
+                      gbuf(dR[i + 1], B, 1, d.W2, 256, 0), tp, gGa(nb), gBe(nb), dz5[i], nullptr), "G res bwd b");
+    run_conv(r, plain_op(dz5[i], B, 1, d.W2, 256), W.bwd(cb), k3b, B, 1, d.W2,
              plain_out(dH, 1, d.W2, 512), nullptr, nullptr, "G res dgrad b");
     if (needWgrad)
-      run_wgrad(r, plain_op(dz5, B, 1, d.W2, 256), plain_op(s.H[i], B, 1, d.W2, 512),
+      run_wgrad(r, plain_op(dz5[i], B, 1, d.W2, 256), plain_op(s.H[i], B, 1, d.W2, 512),
                 k3f, nullptr, B, 1, d.W2, gblob + cb.gW, "G res wgrad b");
     run_bwd(r, mk_bwd(kGatedIN, s.z4[i], 1024, 1, d.W2, s.st4[i], 1024, W.gamma(nm[na]), W.beta(nm[na]), 1,
-                      gbuf(dH, B, 1, d.W2, 512, 0), tp, gGa(na), gBe(na), dz4, nullptr), "G res bwd a");
+                      gbuf(dH, B, 1, d.W2, 512, 0), tp, gGa(na), gBe(na), dz4[i], nullptr), "G res bwd a");
     // dR[i] = dR[i+1] (skip connection) + dgrad
-    run_conv(r, plain_op(dz4, B, 1, d.W2, 1024), W.bwd(ca), k3b, B, 1, d.W2,
+    run_conv(r, plain_op(dz4[i], B, 1, d.W2, 1024), W.bwd(ca), k3b, B, 1, d.W2,
              plain_out(dR[i], 1, d.W2, 256), nullptr, dR[i + 1], "G res dgrad a");
     if (needWgrad)
-      run_wgrad(r, plain_op(dz4, B, 1, d.W2, 1024), plain_op(s.R[i], B, 1, d.W2, 256),
+      run_wgrad(r, plain_op(dz4[i], B, 1, d.W2, 1024), plain_op(s.R[i], B, 1, d.W2, 256),
                 k3f, nullptr, B, 1, d.W2, gblob + ca.gW, "G res wgrad a");
   }
   // ---- 2D -> 1D

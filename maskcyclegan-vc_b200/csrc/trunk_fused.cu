@@ -388,6 +388,439 @@ trunk_fwd_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constant
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 256);
 }
 
+// ================================================================================================
+// Backward chain.  Per block i = 5..0 (dR[i+1] lives in each CTA's shared memory as its 32-column slice):
+//   S1  InstanceNorm backward of conv b's output on the CTA's 32 columns -> dz5 slice (global hi/lo)
+//       -- cluster barrier: dz5 complete --
+//   S2  data gradient of conv b, N-split: dH[:, 64j..64j+64) = sum_taps dz5 * Wb^T      (12 k-blocks)
+//   S3  GLU + InstanceNorm backward on the SAME channels (conv and gate columns 64j.. of z4) -> dz4 slice
+//   S4  data gradient of conv a, K-SPLIT: the CTA's own 128 dz4 channels x 3 taps against all 256 output
+//       columns (12 half-k-block items of 64 KB) -> partial dR[i] (128 x 256 fp32) in shared memory
+//       -- cluster barrier: partials ready --
+//   S5  each CTA sums the 8 partials of its 32-column slice over distributed shared memory and adds the
+//       skip connection: dR[i] slice                                -- cluster barrier: partials consumed --
+// The K-split keeps conv a's data gradient (K = 3072) from streaming the whole dz4 tile into every CTA.
+constexpr int kPitchH = 68;                // dH tile pitch (floats)
+constexpr int kPitchP = 260;               // partial dR tile pitch (floats)
+constexpr int kPitchR = 36;                // dR slice pitch (floats)
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int NPASS>
+struct TrunkBwdCfg {
+  static constexpr int kSlot = NPASS == 3 ? 65536 : 32768;            // ring slot: (A 16 KB + B 16 KB) x planes
+  static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
+  static constexpr int kStages = NPASS == 3 ? 3 : 6;
+  static constexpr int kRingBytes = kStages * kSlot;                  // 192 KB
+  static constexpr int kDRBytes = kRows * kPitchR * 4;                // persistent dR slice
+  static constexpr int kSmemBytes = kRingBytes + kDRBytes + 1024 + 256;
+  // scratch of the three epilogues (aliases the idle ring)
+  static constexpr int kS3Bytes = (kRows * kPitchH + kRows * kPitchA + kMaxBB * 64 * 4) * 4;
+  static constexpr int kS5Bytes = kRows * kPitchP * 4;
+  static_assert(kS3Bytes <= kRingBytes && kS5Bytes <= kRingBytes, "epilogue scratch must fit in the ring");
+};
+
+template <int NPASS>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(256, 1)
+trunk_bwd_kernel(const __grid_constant__ CUtensorMap tmZ5h, const __grid_constant__ CUtensorMap tmZ5l,
+                 const __grid_constant__ CUtensorMap tmZ4h, const __grid_constant__ CUtensorMap tmZ4l,
+                 const __grid_constant__ CUtensorMap tmWbh, const __grid_constant__ CUtensorMap tmWbl,
+                 const __grid_constant__ CUtensorMap tmWah, const __grid_constant__ CUtensorMap tmWal,
+                 const __grid_constant__ TrunkBwdArgs p) {
+  using Cfg = TrunkBwdCfg<NPASS>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* dRloc = reinterpret_cast<float*>(smem + Cfg::kRingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes + Cfg::kDRBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();
+  const int tileIdx = blockIdx.x / kCluster;
+  const int b0 = tileIdx * p.BB;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmZ5h); ptx::prefetch_tmap(&tmZ4h); ptx::prefetch_tmap(&tmWbh); ptx::prefetch_tmap(&tmWah);
+    if (NPASS == 3) { ptx::prefetch_tmap(&tmZ5l); ptx::prefetch_tmap(&tmZ4l); ptx::prefetch_tmap(&tmWbl); ptx::prefetch_tmap(&tmWal); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(tfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();          // barriers initialised and shared memory live in every CTA before any DSMEM access
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int stage = 0;
+  uint32_t phase = 0, tphase = 0;
+  const bool producer = warp == 0 && lane == 0;
+  const bool issuer = warp == 1 && lane == 0;
+  const bool epi = warp >= 4;
+  const int et = threadIdx.x - 128;
+  const int quad = warp & 3;
+  const int row = quad * 32 + lane;
+  const float invW = 1.f / (float)p.W2;
+  float* ring = reinterpret_cast<float*>(smem);
+  const int nb0 = 32 * rank;                 // this CTA's 32 columns of the 256-wide tensors
+  const int ch0 = 64 * rank;                 // this CTA's 64 gated channels
+
+  // dR[6] slice -> shared memory (rows outside the batch / beyond W2 stay zero)
+  if (epi) {
+    const int cg = et & 3, rsub = et >> 2;
+    for (int it = 0; it < kRows / 32; ++it) {
+      const int r = it * 32 + rsub;
+      const int bb = r / p.BX, bx = r - bb * p.BX, b = b0 + bb;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (b < p.B && bx < p.W2) {
+        const float* src = p.dR6 + ((size_t)b * p.W2 + bx) * 256 + nb0 + cg * 8;
+        v0 = *reinterpret_cast<const float4*>(src);
+        v1 = *reinterpret_cast<const float4*>(src + 4);
+      }
+      *reinterpret_cast<float4*>(dRloc + r * kPitchR + cg * 8) = v0;
+      *reinterpret_cast<float4*>(dRloc + r * kPitchR + cg * 8 + 4) = v1;
+    }
+    epi_bar();
+  }
+
+  for (int blk = kTrunkBlocks - 1; blk >= 0; --blk) {
+    // ================================================================ S1: IN backward of conv b (32 columns)
+    if (epi) {
+      float* zt = ring;                              // [128][36] z5 slice
+      float* kst = ring + kRows * kPitchR;           // [BB][32][2] k1 = t1/W2, k2 = t2/W2
+      {
+        const int cg = et & 3, rsub = et >> 2;
+        for (int it = 0; it < kRows / 32; ++it) {
+          const int r = it * 32 + rsub;
+          const int bb = r / p.BX, bx = r - bb * p.BX, b = b0 + bb;
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+          if (b < p.B && bx < p.W2) {
+            const float* src = p.z5[blk] + ((size_t)b * p.W2 + bx) * 256 + nb0 + cg * 8;
+            v0 = *reinterpret_cast<const float4*>(src);
+            v1 = *reinterpret_cast<const float4*>(src + 4);
+          }
+          *reinterpret_cast<float4*>(zt + r * kPitchR + cg * 8) = v0;
+          *reinterpret_cast<float4*>(zt + r * kPitchR + cg * 8 + 4) = v1;
+        }
+      }
+      epi_bar();
+      {
+        const int col = et & 31, grp = et >> 5;
+        float gsum1 = 0.f, gsum2 = 0.f;
+        for (int bb = grp; bb < p.BB; bb += 4) {
+          if (b0 + bb >= p.B) break;
+          const float mean = p.mean5[blk][(size_t)(b0 + bb) * 256 + nb0 + col];
+          const float rstd = p.rstd5[blk][(size_t)(b0 + bb) * 256 + nb0 + col];
+          float t1 = 0.f, t2 = 0.f;
+          for (int x = 0; x < p.W2; ++x) {
+            const int r = bb * p.BX + x;
+            const float dy = dRloc[r * kPitchR + col];
+            const float xh = (zt[r * kPitchR + col] - mean) * rstd;
+            t1 += dy;
+            t2 = fmaf(dy, xh, t2);
+          }
+          kst[(bb * 32 + col) * 2 + 0] = t1 * invW;
+          kst[(bb * 32 + col) * 2 + 1] = t2 * invW;
+          gsum1 += t1;
+          gsum2 += t2;
+        }
+        atomicAdd(p.dbetaB[blk] + nb0 + col, gsum1);
+        atomicAdd(p.dgammaB[blk] + nb0 + col, gsum2);
+      }
+      epi_bar();
+      {
+        const int cg = et & 3, rsub = et >> 2;
+        const int c0 = cg * 8;
+        float gm[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gm[k] = __ldg(p.gammaB[blk] + nb0 + c0 + k);
+        for (int it = 0; it < kRows / 32; ++it) {
+          const int r = it * 32 + rsub;
+          const int bb = r / p.BX, bx = r - bb * p.BX, b = b0 + bb;
+          if (b >= p.B || bx >= p.W2) continue;
+          const float* mp = p.mean5[blk] + (size_t)b * 256 + nb0 + c0;
+          const float* rp = p.rstd5[blk] + (size_t)b * 256 + nb0 + c0;
+          float dz[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float rs = __ldg(rp + k);
+            const float xh = (zt[r * kPitchR + c0 + k] - __ldg(mp + k)) * rs;
+            const float dy = dRloc[r * kPitchR + c0 + k];
+            dz[k] = rs * gm[k] * (dy - kst[(bb * 32 + c0 + k) * 2] - xh * kst[(bb * 32 + c0 + k) * 2 + 1]);
+          }
+          const size_t grow = (size_t)b * p.W2 + bx;
+          store_split8(p.dz5hi[blk] + grow * 256 + nb0 + c0, p.dz5lo[blk] + grow * 256 + nb0 + c0, dz);
+        }
+      }
+      ptx::fence_proxy_async_all();
+    }
+    ptx::cluster_sync_relacq();                      // dz5[blk] complete in all 8 slices
+    if (producer) ptx::fence_proxy_async_all();
+
+    // ================================================================ S2: dH slice = dgrad of conv b (N = 64)
+    if (producer) {
+      constexpr uint32_t kTx = (16384 + 8192) * Cfg::kPlanes;
+      for (int kb = 0; kb < 12; ++kb) {              // 3 taps x 4 channel blocks of dz5
+        const int tap = kb >> 2, cb = kb & 3;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kSlot;
+        ptx::mbar_arrive_expect_tx(&full[stage], kTx);
+        // data gradient: dH[x] += dz5[x - (tap - 1)] * W[tap]  (the forward tap read x + tap - 1)
+        ptx::tma_load_4d(st, &tmZ5h, &full[stage], cb * 64, 1 - tap, b0, blk);
+        ptx::tma_load_4d(st + 16384, &tmWbh, &full[stage], cb * 64, ch0, tap, blk);
+        if (NPASS == 3) {
+          uint8_t* lo = st + 32768;
+          ptx::tma_load_4d(lo, &tmZ5l, &full[stage], cb * 64, 1 - tap, b0, blk);
+          ptx::tma_load_4d(lo + 16384, &tmWbl, &full[stage], cb * 64, ch0, tap, blk);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (issuer) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(kRows, 64, 0, 0);
+      for (int kb = 0; kb < 12; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sA = ptx::smem_u32(smem + stage * Cfg::kSlot);
+        const uint32_t sB = sA + 16384, sAl = sA + 32768, sBl = sAl + 16384;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t dAh = ptx::umma_smem_desc_sw128(sA + k * 32, 0, 1024);
+          const uint64_t dBh = ptx::umma_smem_desc_sw128(sB + k * 32, 0, 1024);
+          ptx::umma_bf16(tmem_base, dAh, dBh, idesc, (kb | k) != 0);
+          if (NPASS == 3) {
+            const uint64_t dAl = ptx::umma_smem_desc_sw128(sAl + k * 32, 0, 1024);
+            const uint64_t dBl = ptx::umma_smem_desc_sw128(sBl + k * 32, 0, 1024);
+            ptx::umma_bf16(tmem_base, dAh, dBl, idesc, 1);
+            ptx::umma_bf16(tmem_base, dAl, dBh, idesc, 1);
+          }
+        }
+        ptx::umma_commit(&empty[stage]);
+        if (kb == 11) ptx::umma_commit(tfull);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (epi) {
+      // ============================================================== S3: GLU + IN backward -> dz4 slice
+      float* dHt = ring;                               // [128][68]
+      float* zt = ring + kRows * kPitchH;              // [128][132]: conv cols 0..63, gate cols 64..127
+      float* kst = zt + kRows * kPitchA;               // [BB][64][4]: k1a, k2a, k1g, k2g
+      // z4 slice -> shared memory while the MMAs run (the ring slots used by the pipeline are ahead of
+      // this scratch only in time, not in space: wait for the accumulator first)
+      ptx::mbar_wait(tfull, tphase);
+      ptx::tc_fence_after();
+      {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          uint32_t v[32];
+          ptx::tmem_ld32(taddr + j * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dHt + row * kPitchH + j * 32 + i) =
+                make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        }
+        ptx::tc_fence_before();
+      }
+      {
+        const int cg = et & 7, rsub = et >> 3;
+        for (int it = 0; it < kRows / 16; ++it) {
+          const int r = it * 16 + rsub;
+          const int bb = r / p.BX, bx = r - bb * p.BX, b = b0 + bb;
+          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, g0 = a0, g1 = a0;
+          if (b < p.B && bx < p.W2) {
+            const float* src = p.z4[blk] + ((size_t)b * p.W2 + bx) * 1024 + ch0 + cg * 8;
+            a0 = *reinterpret_cast<const float4*>(src); a1 = *reinterpret_cast<const float4*>(src + 4);
+            g0 = *reinterpret_cast<const float4*>(src + 512); g1 = *reinterpret_cast<const float4*>(src + 516);
+          }
+          float* d = zt + r * kPitchA + cg * 8;
+          *reinterpret_cast<float4*>(d) = a0; *reinterpret_cast<float4*>(d + 4) = a1;
+          *reinterpret_cast<float4*>(d + 64) = g0; *reinterpret_cast<float4*>(d + 68) = g1;
+        }
+      }
+      epi_bar();
+      {
+        const int col = et & 63, grp = et >> 6;        // 64 channels x 2 sample groups
+        const float gaa = __ldg(p.gammaA[blk] + ch0 + col), baa = __ldg(p.betaA[blk] + ch0 + col);
+        const float gag = __ldg(p.gammaA[blk] + 512 + ch0 + col), bag = __ldg(p.betaA[blk] + 512 + ch0 + col);
+        float s1a = 0.f, s2a = 0.f, s1g = 0.f, s2g = 0.f;
+        for (int bb = grp; bb < p.BB; bb += 2) {
+          if (b0 + bb >= p.B) break;
+          const size_t so = (size_t)(b0 + bb) * 1024 + ch0 + col;
+          const float ma = p.mean4[blk][so], ra = p.rstd4[blk][so], mg = p.mean4[blk][so + 512], rg = p.rstd4[blk][so + 512];
+          float t1a = 0.f, t2a = 0.f, t1g = 0.f, t2g = 0.f;
+          for (int x = 0; x < p.W2; ++x) {
+            const int r = bb * p.BX + x;
+            const float d = dHt[r * kPitchH + col];
+            const float xa = (zt[r * kPitchA + col] - ma) * ra, xg = (zt[r * kPitchA + 64 + col] - mg) * rg;
+            const float ya = fmaf(xa, gaa, baa), yg = fmaf(xg, gag, bag);
+            const float sg = sigmoid_fast(yg);
+            const float dya = d * sg, dyg = d * ya * sg * (1.f - sg);
+            t1a += dya; t2a = fmaf(dya, xa, t2a);
+            t1g += dyg; t2g = fmaf(dyg, xg, t2g);
+          }
+          float* k = kst + (bb * 64 + col) * 4;
+          k[0] = t1a * invW; k[1] = t2a * invW; k[2] = t1g * invW; k[3] = t2g * invW;
+          s1a += t1a; s2a += t2a; s1g += t1g; s2g += t2g;
+        }
+        atomicAdd(p.dbetaA[blk] + ch0 + col, s1a);
+        atomicAdd(p.dgammaA[blk] + ch0 + col, s2a);
+        atomicAdd(p.dbetaA[blk] + 512 + ch0 + col, s1g);
+        atomicAdd(p.dgammaA[blk] + 512 + ch0 + col, s2g);
+      }
+      epi_bar();
+      {
+        const int cg = et & 7, rsub = et >> 3;
+        const int c0 = cg * 8;
+        float gaa[8], baa[8], gag[8], bag[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          gaa[k] = __ldg(p.gammaA[blk] + ch0 + c0 + k); baa[k] = __ldg(p.betaA[blk] + ch0 + c0 + k);
+          gag[k] = __ldg(p.gammaA[blk] + 512 + ch0 + c0 + k); bag[k] = __ldg(p.betaA[blk] + 512 + ch0 + c0 + k);
+        }
+        for (int it = 0; it < kRows / 16; ++it) {
+          const int r = it * 16 + rsub;
+          const int bb = r / p.BX, bx = r - bb * p.BX, b = b0 + bb;
+          if (b >= p.B || bx >= p.W2) continue;
+          const size_t so = (size_t)b * 1024 + ch0 + c0;
+          float dza[8], dzg[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float ma = __ldg(p.mean4[blk] + so + k), ra = __ldg(p.rstd4[blk] + so + k);
+            const float mg = __ldg(p.mean4[blk] + so + 512 + k), rg = __ldg(p.rstd4[blk] + so + 512 + k);
+            const float d = dHt[r * kPitchH + c0 + k];
+            const float xa = (zt[r * kPitchA + c0 + k] - ma) * ra, xg = (zt[r * kPitchA + 64 + c0 + k] - mg) * rg;
+            const float ya = fmaf(xa, gaa[k], baa[k]), yg = fmaf(xg, gag[k], bag[k]);
+            const float sg = sigmoid_fast(yg);
+            const float dya = d * sg, dyg = d * ya * sg * (1.f - sg);
+            const float* kk = kst + (bb * 64 + c0 + k) * 4;
+            dza[k] = ra * gaa[k] * (dya - kk[0] - xa * kk[1]);
+            dzg[k] = rg * gag[k] * (dyg - kk[2] - xg * kk[3]);
+          }
+          const size_t grow = (size_t)b * p.W2 + bx;
+          store_split8(p.dz4hi[blk] + grow * 1024 + ch0 + c0, p.dz4lo[blk] + grow * 1024 + ch0 + c0, dza);
+          store_split8(p.dz4hi[blk] + grow * 1024 + 512 + ch0 + c0, p.dz4lo[blk] + grow * 1024 + 512 + ch0 + c0, dzg);
+        }
+      }
+      ptx::fence_proxy_async_all();
+    }
+    tphase ^= 1;
+    __syncthreads();                                 // this CTA's dz4 slice is written: its own TMA may read it
+    if (producer) ptx::fence_proxy_async_all();
+
+    // ================================================================ S4: partial dR = dgrad of conv a over the CTA's K slice
+    if (producer) {
+      constexpr uint32_t kTx = (16384 + 16384) * Cfg::kPlanes;
+      for (int item = 0; item < 12; ++item) {        // (N half) x (tap) x (conv / gate channel block)
+        const int nh = item / 6, rem = item - nh * 6, tap = rem >> 1, kc = (rem & 1) ? 512 + ch0 : ch0;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kSlot;
+        ptx::mbar_arrive_expect_tx(&full[stage], kTx);
+        ptx::tma_load_4d(st, &tmZ4h, &full[stage], kc, 1 - tap, b0, blk);
+        ptx::tma_load_4d(st + 16384, &tmWah, &full[stage], kc, nh * 128, tap, blk);
+        if (NPASS == 3) {
+          uint8_t* lo = st + 32768;
+          ptx::tma_load_4d(lo, &tmZ4l, &full[stage], kc, 1 - tap, b0, blk);
+          ptx::tma_load_4d(lo + 16384, &tmWal, &full[stage], kc, nh * 128, tap, blk);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (issuer) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(kRows, 128, 0, 0);
+      for (int item = 0; item < 12; ++item) {
+        const int nh = item / 6, rem = item - nh * 6;
+        const uint32_t d_tmem = tmem_base + 128 + nh * 128;
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sA = ptx::smem_u32(smem + stage * Cfg::kSlot);
+        const uint32_t sB = sA + 16384, sAl = sA + 32768, sBl = sAl + 16384;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t dAh = ptx::umma_smem_desc_sw128(sA + k * 32, 0, 1024);
+          const uint64_t dBh = ptx::umma_smem_desc_sw128(sB + k * 32, 0, 1024);
+          ptx::umma_bf16(d_tmem, dAh, dBh, idesc, (rem | k) != 0);
+          if (NPASS == 3) {
+            const uint64_t dAl = ptx::umma_smem_desc_sw128(sAl + k * 32, 0, 1024);
+            const uint64_t dBl = ptx::umma_smem_desc_sw128(sBl + k * 32, 0, 1024);
+            ptx::umma_bf16(d_tmem, dAh, dBl, idesc, 1);
+            ptx::umma_bf16(d_tmem, dAl, dBh, idesc, 1);
+          }
+        }
+        ptx::umma_commit(&empty[stage]);
+        if (item == 11) ptx::umma_commit(tfull);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (epi) {
+      float* part = ring;                              // [128][260] this CTA's partial dR[blk]
+      ptx::mbar_wait(tfull, tphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 128;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        uint32_t v[32];
+        ptx::tmem_ld32(taddr + j * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(part + row * kPitchP + j * 32 + i) =
+              make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+      }
+      ptx::tc_fence_before();
+    }
+    tphase ^= 1;
+    ptx::cluster_sync_relacq();                      // all 8 partials are in shared memory
+
+    // ================================================================ S5: reduce the CTA's 32-column slice over the cluster
+    if (epi) {
+      const int cg = et & 7, rsub = et >> 3;           // 8 float4 per 32-column row, 16 rows per pass
+      const uint32_t partBase = ptx::smem_u32(ring);
+      for (int it = 0; it < kRows / 16; ++it) {
+        const int r = it * 16 + rsub;
+        const uint32_t off = partBase + (uint32_t)((r * kPitchP + nb0 + cg * 4) * 4);
+        float4 acc = *reinterpret_cast<const float4*>(dRloc + r * kPitchR + cg * 4);   // skip connection dR[blk + 1]
+#pragma unroll
+        for (int q = 0; q < kCluster; ++q) {
+          const float4 v = ld_dsmem_f4(mapa_u32(off, (uint32_t)((rank + q) & (kCluster - 1))));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(dRloc + r * kPitchR + cg * 4) = acc;
+        if (blk == 0) {
+          const int bb = r / p.BX, bx = r - bb * p.BX, b = b0 + bb;
+          if (b < p.B && bx < p.W2)
+            *reinterpret_cast<float4*>(p.dR0 + ((size_t)b * p.W2 + bx) * 256 + nb0 + cg * 4) = acc;
+        }
+      }
+      ptx::fence_proxy_async_all();                    // the ring is TMA territory again after the next barrier
+    }
+    ptx::cluster_sync_relacq();                      // every CTA has consumed every partial
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 int env_fused_trunk() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MCGVC_FUSED_TRUNK"); v = e ? atoi(e) : 1; }
@@ -441,7 +874,47 @@ cudaError_t launch_t(const TrunkFwdArgs& a, const TrunkFwdMaps& m, cudaStream_t 
   return launched();
 }
 
+template <int NPASS>
+cudaError_t launch_bwd_t(const TrunkBwdArgs& a, const TrunkBwdMaps& m, cudaStream_t stream) {
+  using Cfg = TrunkBwdCfg<NPASS>;
+  CUtensorMap t5h, t5l, t4h, t4l, tWbh, tWbl, tWah, tWal;
+  if (!make_plane_map(&t5h, m.Z5hi, 256, a.W2, a.B, kTrunkBlocks, m.Z5StrideBytes, a.BX, a.BB)) return cudaErrorInvalidValue;
+  if (!make_plane_map(&t4h, m.Z4hi, 1024, a.W2, a.B, kTrunkBlocks, m.Z4StrideBytes, a.BX, a.BB)) return cudaErrorInvalidValue;
+  if (!make_weight_map(&tWbh, m.Wbh, 256, 512, kTrunkBlocks, m.WbStrideBytes, 64)) return cudaErrorInvalidValue;
+  if (!make_weight_map(&tWah, m.Wah, 1024, 256, kTrunkBlocks, m.WaStrideBytes, 128)) return cudaErrorInvalidValue;
+  if (NPASS == 3) {
+    if (!make_plane_map(&t5l, m.Z5lo, 256, a.W2, a.B, kTrunkBlocks, m.Z5StrideBytes, a.BX, a.BB)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&t4l, m.Z4lo, 1024, a.W2, a.B, kTrunkBlocks, m.Z4StrideBytes, a.BX, a.BB)) return cudaErrorInvalidValue;
+    if (!make_weight_map(&tWbl, m.Wbl, 256, 512, kTrunkBlocks, m.WbStrideBytes, 64)) return cudaErrorInvalidValue;
+    if (!make_weight_map(&tWal, m.Wal, 1024, 256, kTrunkBlocks, m.WaStrideBytes, 128)) return cudaErrorInvalidValue;
+  } else {
+    t5l = t5h; t4l = t4h; tWbl = tWbh; tWal = tWah;
+  }
+  static bool attr_done[64] = {};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_done[dev_id & 63];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(trunk_bwd_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("trunk_bwd: smem attr: %s", cudaGetErrorString(e)); return e; }
+    attr_set = true;
+  }
+  const int tiles = (a.B + a.BB - 1) / a.BB;
+  profile_begin(0, 2.0 * (double)a.B * a.W2 * (1024.0 * 768.0 + 256.0 * 1536.0) * kTrunkBlocks, stream);
+  trunk_bwd_kernel<NPASS><<<tiles * kCluster, 256, Cfg::kSmemBytes, stream>>>(t5h, t5l, t4h, t4l, tWbh, tWbl, tWah, tWal, a);
+  profile_end(stream);
+  return launched();
+}
+
 }  // namespace
+
+bool trunk_bwd_supported(int B, int W2) { return trunk_fwd_supported(B, W2); }
+
+cudaError_t launch_trunk_bwd(const TrunkBwdArgs& a, const TrunkBwdMaps& m, cudaStream_t stream) {
+  if (a.BX * a.BB != kRows || a.BX < a.W2 || a.BB > kMaxBB) { set_error("trunk_bwd: tile %d x %d", a.BB, a.BX); return cudaErrorInvalidValue; }
+  if ((m.Z5StrideBytes | m.Z4StrideBytes | m.WaStrideBytes | m.WbStrideBytes) & 15) { set_error("trunk_bwd: block strides must be 16-byte multiples"); return cudaErrorInvalidValue; }
+  return a.nPass == 3 ? launch_bwd_t<3>(a, m, stream) : launch_bwd_t<1>(a, m, stream);
+}
 
 bool trunk_fwd_supported(int B, int W2) {
   return env_fused_trunk() != 0 && B >= 1 && W2 >= 4 && W2 <= kRows;

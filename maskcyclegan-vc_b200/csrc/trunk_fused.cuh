@@ -47,4 +47,40 @@ struct TrunkFwdMaps {
 bool trunk_fwd_supported(int B, int W2);
 cudaError_t launch_trunk_fwd(const TrunkFwdArgs& a, const TrunkFwdMaps& m, cudaStream_t stream);
 
+// Fused data-gradient chain of the same six blocks (autograd through model.py:71-76, six times): from
+// dR[6] (gradient w.r.t. the trunk output) to dR[0], writing on the way the dz operands (bf16 hi/lo) of
+// the twelve weight-gradient GEMMs and accumulating the InstanceNorm affine gradients.
+struct TrunkBwdArgs {
+  int B, W2;
+  int BX, BB;
+  int nPass;
+  const float* dR6;                            // [L][256] gradient w.r.t. R[6]
+  float* dR0;                                  // [L][256] gradient w.r.t. R[0]
+  const float* z4[kTrunkBlocks];               // saved by the forward pass
+  const float* z5[kTrunkBlocks];
+  const float* mean4[kTrunkBlocks];
+  const float* rstd4[kTrunkBlocks];
+  const float* mean5[kTrunkBlocks];
+  const float* rstd5[kTrunkBlocks];
+  const float* gammaA[kTrunkBlocks];
+  const float* betaA[kTrunkBlocks];
+  const float* gammaB[kTrunkBlocks];
+  float* dgammaA[kTrunkBlocks];                // [1024] accumulated (+=) over samples
+  float* dbetaA[kTrunkBlocks];
+  float* dgammaB[kTrunkBlocks];                // [256]
+  float* dbetaB[kTrunkBlocks];
+  __nv_bfloat16* dz5hi[kTrunkBlocks];          // [L][256]  d(loss)/d(z5), operand of wgrad b and dgrad b
+  __nv_bfloat16* dz5lo[kTrunkBlocks];
+  __nv_bfloat16* dz4hi[kTrunkBlocks];          // [L][1024]
+  __nv_bfloat16* dz4lo[kTrunkBlocks];
+};
+struct TrunkBwdMaps {
+  const void* Z5hi; const void* Z5lo; long long Z5StrideBytes;    // dz5[i] planes [B][W2][256]
+  const void* Z4hi; const void* Z4lo; long long Z4StrideBytes;    // dz4[i] planes [B][W2][1024]
+  const void* Wbh; const void* Wbl; long long WbStrideBytes;      // conv b data-gradient weights [3][512][256]
+  const void* Wah; const void* Wal; long long WaStrideBytes;      // conv a data-gradient weights [3][256][1024]
+};
+bool trunk_bwd_supported(int B, int W2);
+cudaError_t launch_trunk_bwd(const TrunkBwdArgs& a, const TrunkBwdMaps& m, cudaStream_t stream);
+
 }  // namespace mcgvc
