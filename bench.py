@@ -275,10 +275,15 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_out = sys.stdout
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner (and warnings) to stdout; rank 0's stdout carries ONE JSON line
+        # NCCL prints its version banner (and warnings) to fd 1; rank 0's stdout must carry ONE JSON line:
+        # everything else written to fd 1 during the run goes to stderr, the line itself to the saved fd
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
@@ -458,7 +463,8 @@ def main():
         if sync is not None:
             line["engine"]["allreduces"] = sync.reductions
             line["engine"]["allreduce_bytes"] = sync.reduced_bytes
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
