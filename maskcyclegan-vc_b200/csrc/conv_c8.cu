@@ -65,8 +65,13 @@ struct C8Cfg {
   static_assert(kAccBufs >= 1 && kStages >= 2, "config");
 };
 
+// 384 threads: warps 0-3 = TMA producer / MMA issuer / TMEM allocator / spare, warps 4-11 = EIGHT epilogue
+// warps, two per TMEM lane quadrant, each draining half of the tile's columns: with D1 + D2 filling all of
+// TMEM the 256-wide tile cannot overlap its epilogue with the next tile's MMAs, so its duration sits on the
+// critical path of every tile.
+constexpr int kC8Threads = 384;
 template <int BLOCK_N>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC8Threads, 1)
 conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmA8h,
                const __grid_constant__ CUtensorMap tmA8l, const __grid_constant__ CUtensorMap tmW16,
                const __grid_constant__ CUtensorMap tmW8h, const __grid_constant__ CUtensorMap tmW8l,
@@ -99,7 +104,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], 8);
+      ptx::mbar_init(&tempty[i], 16);   // 8 epilogue warps x 2 CTAs
     }
     ptx::fence_barrier_init();
   }
@@ -207,6 +212,8 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (both CTAs)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    const int colHalf = (warp - 4) >> 2;              // which half of the tile's columns this warp drains
+    constexpr int kChunksPerWarp = BLOCK_N / 64;
     // out = c1 * (D1 + c2 * D2): host multipliers times the operands' device-side scale records
     // {1/S, 1/E} (S scales the 16-bit plane, E the e4m3 planes; 2^-11 = residual pre-scale)
     float c1 = g.c8OutScale, c2 = g.c8CorrScale;
@@ -247,7 +254,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
       const uint32_t t1 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 2 * BLOCK_N;
       const uint32_t t2 = t1 + BLOCK_N;
 #pragma unroll 1
-      for (int j = 0; j < BLOCK_N / 32; ++j) {
+      for (int j = colHalf * kChunksPerWarp; j < (colHalf + 1) * kChunksPerWarp; ++j) {
         uint32_t v1[32], v2[32];
         ptx::tmem_ld32(t1 + j * 32, v1);
         ptx::tmem_ld32(t2 + j * 32, v2);
@@ -307,7 +314,7 @@ cudaError_t launch_c8_t(const ConvGeom& g, cudaStream_t stream) {
   const int maxPairs = num_sms_c8() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
   profile_begin(0, g.algoFlops, stream);
-  conv_c8_kernel<BLOCK_N><<<2 * pairs, 256, Cfg::kSmemBytes, stream>>>(tmA16, tmA8h, tmA8l, tmW16, tmW8h, tmW8l, g);
+  conv_c8_kernel<BLOCK_N><<<2 * pairs, kC8Threads, Cfg::kSmemBytes, stream>>>(tmA16, tmA8h, tmA8l, tmW16, tmW8h, tmW8l, g);
   profile_end(stream);
   return launched();
 }

@@ -539,8 +539,11 @@ struct Conv2Cfg {
   static_assert(kTmemCols >= 32 && kTmemCols <= 512, "TMEM columns");
 };
 
+// 384 threads: eight epilogue warps (two per TMEM lane quadrant, half of the tile's columns each) so that
+// short-K layers (the Generator stem: 5 k-blocks per tile) are not bound by draining the accumulator.
+constexpr int kConv2Threads = 384;
 template <int BLOCK_N, int NPASS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv2Threads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                 const __grid_constant__ ConvGeom g) {
@@ -576,7 +579,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], 8);
+      ptx::mbar_init(&tempty[i], 16);   // 8 epilogue warps x 2 CTAs
     }
     ptx::fence_barrier_init();
   }
@@ -686,6 +689,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (both CTAs)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    const int colHalf = (warp - 4) >> 2;              // which half of the tile's columns this warp drains
+    constexpr int kChunksPerWarp = BLOCK_N / 64;
     const float osc = half16_scale<NPASS>(g);
     int it = 0;
     for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
@@ -719,7 +724,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int j = 0; j < BLOCK_N / 32; ++j) {
+      for (int j = colHalf * kChunksPerWarp; j < (colHalf + 1) * kChunksPerWarp; ++j) {
         uint32_t v[32];
         ptx::tmem_ld32(taddr + j * 32, v);
         ptx::tmem_ld_wait();
@@ -774,7 +779,7 @@ static cudaError_t launch_conv_tc2_t(const ConvGeom& g, cudaStream_t stream) {
   const int maxPairs = num_sms() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
   profile_begin(0, g.algoFlops, stream);
-  conv_tc2_kernel<BLOCK_N, NPASS><<<2 * pairs, 256, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
+  conv_tc2_kernel<BLOCK_N, NPASS><<<2 * pairs, kConv2Threads, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
   profile_end(stream);
   return launched();
 }
