@@ -122,8 +122,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
   const int pairM = (mTiles + 1) / 2;
   const int tilesPerGroup = nTiles * pairM;
   const int totalTiles = tilesPerGroup * g.nGroups;
-  const int kSplit = g.kSplit > 1 ? g.kSplit : 1;   // split-K work items (tile, K slice), see conv_tc_kernel
-  const int totalItems = totalTiles * kSplit;
+  const int totalItems = conv_total_items(g, totalTiles);   // tiles, uniform K-slices or tail-split slices
   const int pairIdx = blockIdx.x >> 1;
   const int numPairs = gridDim.x >> 1;
 
@@ -132,8 +131,8 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     for (int item = pairIdx; item < totalItems; item += numPairs) {
-      const int tile = item / kSplit;
-      const int ks = item - tile * kSplit;
+      const ConvItem wi = conv_decode_item(g, item, totalTiles);
+      const int tile = wi.tile, ks = wi.ks, kSplit = wi.nsplit;
       const int grp = tile / tilesPerGroup;
       const int tl = tile - grp * tilesPerGroup;
       const int nt = tl % nTiles;
@@ -176,8 +175,8 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
     uint32_t phase = 0;
     int it = 0;
     for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
-      const int tile = item / kSplit;
-      const int ks = item - tile * kSplit;
+      const ConvItem wi = conv_decode_item(g, item, totalTiles);
+      const int tile = wi.tile, ks = wi.ks, kSplit = wi.nsplit;
       const int acc = it % kAccBufs;
       const uint32_t aphase = (it / kAccBufs) & 1;
       ptx::mbar_wait(&tempty[acc], aphase ^ 1);
@@ -223,8 +222,8 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
     }
     int it = 0;
     for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
-      const int tile = item / kSplit;
-      const int ks = item - tile * kSplit;
+      const ConvItem wi = conv_decode_item(g, item, totalTiles);
+      const int tile = wi.tile, ks = wi.ks, kSplit = wi.nsplit;
       const int acc = it % kAccBufs;
       const uint32_t aphase = (it / kAccBufs) & 1;
       const int grp = tile / tilesPerGroup;
@@ -262,7 +261,10 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           v1[i] = __float_as_uint(c1 * fmaf(c2, __uint_as_float(v2[i]), __uint_as_float(v1[i])));
-        epilogue_chunk(g, v1, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b, kSplit > 1, ks == 0);
+        if (wi.slot >= 0)   // tail split: raw partial -> scratch, merged by conv_tail_fixup
+          store_partial_chunk(g.tailScratch + (((size_t)wi.slot * 2 + rank) * kTileM + row) * BLOCK_N + j * 32, v1);
+        else
+          epilogue_chunk(g, v1, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b, kSplit > 1, ks == 0);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -310,13 +312,16 @@ cudaError_t launch_c8_t(const ConvGeom& g, cudaStream_t stream) {
     attr_set = true;
   }
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
-  const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups * (g.kSplit > 1 ? g.kSplit : 1);
+  const int tilesAll = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups;
+  const int total = g.tailTiles > 0 ? tilesAll - g.tailTiles + g.tailTiles * g.tailSplit : tilesAll * (g.kSplit > 1 ? g.kSplit : 1);
   const int maxPairs = num_sms_c8() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
   profile_begin(0, g.algoFlops, stream);
   conv_c8_kernel<BLOCK_N><<<2 * pairs, kC8Threads, Cfg::kSmemBytes, stream>>>(tmA16, tmA8h, tmA8l, tmW16, tmW8h, tmW8l, g);
   profile_end(stream);
-  return launched();
+  cudaError_t e = launched();
+  if (e == cudaSuccess && g.tailTiles > 0) e = launch_conv_tail_fixup(g, BLOCK_N, stream);
+  return e;
 }
 
 }  // namespace
@@ -328,6 +333,7 @@ cudaError_t launch_conv_c8(const ConvGeom& g, int blockN, cudaStream_t stream) {
   if (g.a.C % kBlockK || g.a.C != g.w.K || g.cBlocks != g.a.C / kBlockK) { set_error("conv_c8: C=%d K=%d", g.a.C, g.w.K); return cudaErrorInvalidValue; }
   if (!g.a.h8 || !g.a.l8 || !g.w.h8 || !g.w.l8) { set_error("conv_c8: 8-bit planes missing"); return cudaErrorInvalidValue; }
   if (g.nTaps < 1 || g.nTaps > kMaxTaps || g.nGroups < 1 || g.nGroups > 4) { set_error("conv_c8: taps/groups"); return cudaErrorInvalidValue; }
+  if (g.tailTiles > 0 && (g.kSplit > 1 || g.tailSplit < 2 || !g.tailScratch)) { set_error("conv_c8: bad tail split"); return cudaErrorInvalidValue; }
   if (g.kSplit > 1) {
     if (g.statSum) { set_error("conv_c8: split-K cannot feed the fused statistics"); return cudaErrorInvalidValue; }
     for (int i = 0; i < g.nGroups; ++i)

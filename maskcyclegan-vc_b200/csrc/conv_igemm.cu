@@ -477,6 +477,7 @@ static bool check_conv_geom(const ConvGeom& g, int blockN) {
   if (g.nGroups < 1 || g.nGroups > 4) { set_error("conv: nGroups=%d", g.nGroups); return false; }
   for (int i = 0; i < g.nGroups; ++i)
     if (g.grpTapCount[i] < 1 || g.grpTapStart[i] + g.grpTapCount[i] > g.nTaps) { set_error("conv: group %d taps", i); return false; }
+  if (g.tailTiles > 0 && (g.kSplit > 1 || g.tailSplit < 2 || !g.tailScratch)) { set_error("conv: bad tail split"); return false; }
   if (g.kSplit > 1) {
     if (g.statSum) { set_error("conv: split-K cannot feed the fused statistics"); return false; }
     for (int i = 0; i < g.nGroups; ++i)
@@ -597,8 +598,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const int pairM = (mTiles + 1) / 2;
   const int tilesPerGroup = nTiles * pairM;
   const int totalTiles = tilesPerGroup * g.nGroups;
-  const int kSplit = g.kSplit > 1 ? g.kSplit : 1;   // split-K work items, see conv_tc_kernel
-  const int totalItems = totalTiles * kSplit;
+  const int totalItems = conv_total_items(g, totalTiles);   // tiles, uniform K-slices or tail-split slices
   const int pairIdx = blockIdx.x >> 1;
   const int numPairs = gridDim.x >> 1;
 
@@ -607,8 +607,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     for (int item = pairIdx; item < totalItems; item += numPairs) {
-      const int tile = item / kSplit;
-      const int ks = item - tile * kSplit;
+      const ConvItem wi = conv_decode_item(g, item, totalTiles);
+      const int tile = wi.tile, ks = wi.ks, kSplit = wi.nsplit;
       const int grp = tile / tilesPerGroup;
       const int tl = tile - grp * tilesPerGroup;
       const int nt = tl % nTiles;
@@ -652,8 +652,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     uint32_t phase = 0;
     int it = 0;
     for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
-      const int tile = item / kSplit;
-      const int ks = item - tile * kSplit;
+      const ConvItem wi = conv_decode_item(g, item, totalTiles);
+      const int tile = wi.tile, ks = wi.ks, kSplit = wi.nsplit;
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       ptx::mbar_wait(&tempty[acc], aphase ^ 1);
@@ -694,8 +694,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const float osc = half16_scale<NPASS>(g);
     int it = 0;
     for (int item = pairIdx; item < totalItems; item += numPairs, ++it) {
-      const int tile = item / kSplit;
-      const int ks = item - tile * kSplit;
+      const ConvItem wi = conv_decode_item(g, item, totalTiles);
+      const int tile = wi.tile, ks = wi.ks, kSplit = wi.nsplit;
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int grp = tile / tilesPerGroup;
@@ -732,8 +732,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(osc * __uint_as_float(v[i]));
         }
-        epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b,
-                       kSplit > 1, ks == 0);
+        if (wi.slot >= 0)   // tail split: raw partial -> scratch, merged by conv_tail_fixup
+          store_partial_chunk(g.tailScratch + (((size_t)wi.slot * 2 + rank) * kTileM + row) * BLOCK_N + j * 32, v);
+        else
+          epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b,
+                         kSplit > 1, ks == 0);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -775,13 +778,16 @@ static cudaError_t launch_conv_tc2_t(const ConvGeom& g, cudaStream_t stream) {
     attr_set = true;
   }
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
-  const int total = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups * (g.kSplit > 1 ? g.kSplit : 1);
+  const int tilesAll = (g.w.N / BLOCK_N) * ((mTiles + 1) / 2) * g.nGroups;
+  const int total = g.tailTiles > 0 ? tilesAll - g.tailTiles + g.tailTiles * g.tailSplit : tilesAll * (g.kSplit > 1 ? g.kSplit : 1);
   const int maxPairs = num_sms() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
   profile_begin(0, g.algoFlops, stream);
   conv_tc2_kernel<BLOCK_N, NPASS><<<2 * pairs, kConv2Threads, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
   profile_end(stream);
-  return launched();
+  cudaError_t e = launched();
+  if (e == cudaSuccess && g.tailTiles > 0) e = launch_conv_tail_fixup(g, BLOCK_N, stream);
+  return e;
 }
 
 // CTA-pair kernel selection: on by default for layers with enough tiles to fill the chip
@@ -878,6 +884,128 @@ int conv_plan_ksplit(const ConvGeom& g, double minGain) {
   if (g_force_block_n == 0 && env_block_n() != 0) g_force_block_n = env_block_n();
   const ConvVariant v = conv_variant(g);
   return plan_ksplit_waves(v.tiles, v.slots, g, minGain);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tail split (see ConvGeom::tailTiles).  With T tiles on S = 74 CTA pairs the persistent kernels run
+// ceil(T / S) rounds; when the last round is mostly empty (up2 / up1 at batch 64: 320 tiles = 4.32 rounds)
+// its tiles are cut into K-slices so that all pairs share it: 4 + 1/3 rounds instead of 5.  Sub-wave
+// launches (small batches: 10 tiles of 100 k-blocks at batch 1) are split the same way, which turns a
+// 55 us serial K loop into ~8 us.
+int conv_pair_block_n(const ConvGeom& g) {
+  if (g_force_block_n == 0 && env_block_n() != 0) g_force_block_n = env_block_n();
+  const ConvVariant v = conv_variant(g);
+  return v.pair ? v.bn : 0;
+}
+static int env_tail_split() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MCGVC_TAIL_SPLIT"); v = e ? atoi(e) : 1; }
+  return v;
+}
+bool conv_plan_tail(ConvGeom& g, int blockN, float* scratch) {
+  g.tailTiles = 0; g.tailSplit = 0; g.tailScratch = nullptr;
+  if (!env_tail_split() || !scratch || g.kSplit > 1) return false;
+  const int bn = blockN ? blockN : conv_pair_block_n(g);
+  if (bn == 0 || g.w.N % bn || g.nSplit % bn) return false;
+  const int slots = num_sms() / 2;
+  const int mTiles = g.tilesX * g.tilesY * g.tilesB;
+  const long long T = (long long)(g.w.N / bn) * ((mTiles + 1) / 2) * g.nGroups;
+  int minK = 1 << 30;
+  for (int i = 0; i < g.nGroups; ++i) {
+    const int k = g.grpTapCount[i] * g.cBlocks;
+    if (k < minK) minK = k;
+  }
+  if (minK < 16 || g.BX * g.BY < 16) return false;   // short K loops: the fix-up pass would cost more than it saves
+  if (g.nGroups > 1) return false;                   // grouped stride-2 data gradients: the last group's short tap list
+                                                     // leaves slices of a few k-blocks (measured slower: 216 -> 262 us)
+  const long long rem = T % slots;
+  if (rem == 0) return false;
+  int s = (int)(slots / rem);
+  if (s > 8) s = 8;
+  if (s > minK / 8) s = minK / 8;                    // at least 8 k-blocks per slice
+  if (s < 2) return false;
+  g.tailTiles = (int)rem;
+  g.tailSplit = s;
+  g.tailScratch = scratch;
+  return true;
+}
+
+constexpr int kFixRows = 16;   // rows of a half tile per fix-up block (an image's BX*BY rows are a multiple of it)
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256) conv_tail_fixup_kernel(const __grid_constant__ ConvGeom g) {
+  // grid (tail tile, CTA half, 16-row chunk); thread = (4-column group, row group)
+  constexpr int kColGroups = BLOCK_N / 4;
+  constexpr int kRowsPerPass = 256 / kColGroups;
+  __shared__ float4 red[2][256];
+  const int nTiles = g.w.N / BLOCK_N;
+  const int mTiles = g.tilesX * g.tilesY * g.tilesB;
+  const int pairM = (mTiles + 1) / 2;
+  const int tilesPerGroup = nTiles * pairM;
+  const int totalTiles = tilesPerGroup * g.nGroups;
+  const int tl_ = blockIdx.x, rank = blockIdx.y;
+  const int tile = totalTiles - g.tailTiles + tl_;
+  const int grp = tile / tilesPerGroup;
+  const int tl = tile - grp * tilesPerGroup;
+  const int nt = tl % nTiles;
+  int mt = (tl / nTiles) * 2 + rank;
+  if (mt >= mTiles) return;                          // odd tile count: the peer half of the last pair is padding
+  const int tx = mt % g.tilesX;
+  mt /= g.tilesX;
+  const int ty = mt % g.tilesY;
+  const int tb = mt / g.tilesY;
+  const int n0 = nt * BLOCK_N;
+  const int cg = threadIdx.x % kColGroups, rg = threadIdx.x / kColGroups;
+  const int c = cg * 4;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g.bias) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c));
+  const int rowsPerImg = g.BX * g.BY;                // a half tile holds BB images of BX*BY (>= 16) positions each
+  const int row0 = blockIdx.z * kFixRows;
+  const int b = tb * g.BB + row0 / rowsPerImg;       // all 16 rows of this block belong to one image
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  for (int row = row0 + rg; row < row0 + kFixRows; row += kRowsPerPass) {
+    const int ri = row % rowsPerImg;
+    const int bx = ri % g.BX, by = ri / g.BX;
+    const int x = tx * g.BX + bx, y = ty * g.BY + by;
+    if (x >= g.oX || y >= g.oY || b >= g.oB) continue;
+    float4 acc = bv;
+    for (int s = 0; s < g.tailSplit; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(
+          g.tailScratch + ((((size_t)tl_ * g.tailSplit + s) * 2 + rank) * kTileM + row) * BLOCK_N + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const long long off = g.grpOutOff[grp] + (long long)b * g.sB + (long long)y * g.sY + (long long)x * g.sX +
+                          (long long)((n0 + c) / g.nSplit) * g.sNhi + ((n0 + c) % g.nSplit);
+    if (g.addsrc) {
+      const float4 av = *reinterpret_cast<const float4*>(g.addsrc + off);
+      acc.x += av.x; acc.y += av.y; acc.z += av.z; acc.w += av.w;
+    }
+    *reinterpret_cast<float4*>(g.out + off) = acc;
+    s1.x += acc.x; s1.y += acc.y; s1.z += acc.z; s1.w += acc.w;
+    s2.x = fmaf(acc.x, acc.x, s2.x); s2.y = fmaf(acc.y, acc.y, s2.y); s2.z = fmaf(acc.z, acc.z, s2.z); s2.w = fmaf(acc.w, acc.w, s2.w);
+  }
+  if (g.statSum) {                                    // uniform branch: every thread of the block takes it
+    red[0][threadIdx.x] = s1;
+    red[1][threadIdx.x] = s2;
+    __syncthreads();
+    if (rg == 0 && b < g.oB) {
+      for (int k = 1; k < kRowsPerPass; ++k) {
+        const float4 u = red[0][k * kColGroups + cg], q = red[1][k * kColGroups + cg];
+        s1.x += u.x; s1.y += u.y; s1.z += u.z; s1.w += u.w;
+        s2.x += q.x; s2.y += q.y; s2.z += q.z; s2.w += q.w;
+      }
+      float* dA = g.statSum + (long long)b * g.w.N + n0 + c;
+      float* dB = g.statSq + (long long)b * g.w.N + n0 + c;
+      atomicAdd(dA + 0, s1.x); atomicAdd(dA + 1, s1.y); atomicAdd(dA + 2, s1.z); atomicAdd(dA + 3, s1.w);
+      atomicAdd(dB + 0, s2.x); atomicAdd(dB + 1, s2.y); atomicAdd(dB + 2, s2.z); atomicAdd(dB + 3, s2.w);
+    }
+  }
+}
+cudaError_t launch_conv_tail_fixup(const ConvGeom& g, int blockN, cudaStream_t stream) {
+  dim3 grid(g.tailTiles, 2, kTileM / kFixRows);
+  if (blockN == 256) conv_tail_fixup_kernel<256><<<grid, 256, 0, stream>>>(g);
+  else if (blockN == 128) conv_tail_fixup_kernel<128><<<grid, 256, 0, stream>>>(g);
+  else { set_error("conv tail fix-up: blockN=%d", blockN); return cudaErrorInvalidValue; }
+  return launched();
 }
 
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream) {

@@ -42,6 +42,43 @@ __device__ __forceinline__ void warp_colsum_add(float (&a)[32], float (&b)[32], 
   }
 }
 
+// Work item of the persistent pair kernels: a whole tile, one of kSplit uniform K-slices of a tile, or --
+// tail split -- one of tailSplit K-slices of one of the last tailTiles tiles.
+struct ConvItem {
+  int tile, ks, nsplit;
+  int slot;       // tail split: index of the slice's scratch slab, else -1
+};
+__device__ __forceinline__ int conv_total_items(const ConvGeom& g, int totalTiles) {
+  if (g.tailTiles > 0) return totalTiles - g.tailTiles + g.tailTiles * g.tailSplit;
+  return totalTiles * (g.kSplit > 1 ? g.kSplit : 1);
+}
+__device__ __forceinline__ ConvItem conv_decode_item(const ConvGeom& g, int item, int totalTiles) {
+  ConvItem it;
+  if (g.tailTiles > 0) {
+    const int mainTiles = totalTiles - g.tailTiles;
+    if (item < mainTiles) { it.tile = item; it.ks = 0; it.nsplit = 1; it.slot = -1; return it; }
+    const int t = item - mainTiles;
+    it.tile = mainTiles + t / g.tailSplit;
+    it.ks = t - (t / g.tailSplit) * g.tailSplit;
+    it.nsplit = g.tailSplit;
+    it.slot = t;
+    return it;
+  }
+  const int kSplit = g.kSplit > 1 ? g.kSplit : 1;
+  it.tile = item / kSplit;
+  it.ks = item - it.tile * kSplit;
+  it.nsplit = kSplit;
+  it.slot = -1;
+  return it;
+}
+// raw partial accumulator chunk -> scratch slab (tail split)
+__device__ __forceinline__ void store_partial_chunk(float* dst, const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4)
+    *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                      __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+}
+
 // one 32-column chunk of this thread's output row: +bias, +residual, store, optional statistics
 __device__ __forceinline__ void red_add_f32x4(float* addr, float4 t) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(t.x), "f"(t.y), "f"(t.z),

@@ -76,6 +76,13 @@ struct ConvGeom {
   float c8OutScale, c8CorrScale;
   const float* c8RecA;  // device-side scale records {1/S, 1/E} of the two operands (null: host multipliers only)
   const float* c8RecW;
+  // Tail split (pair kernels only, kSplit <= 1): the LAST tailTiles tiles -- the partial wave that would
+  // otherwise occupy a few CTA pairs for a whole extra round -- are each cut into tailSplit K-slices that
+  // run as separate work items; a slice stores its raw partial accumulator to tailScratch
+  // ([slot][cta][128 rows][BLOCK_N] fp32) and conv_tail_fixup adds the slices, the bias / residual and the
+  // fused statistics.  0 = off.  See conv_plan_tail().
+  int tailTiles, tailSplit;
+  float* tailScratch;
   // "C8H" backward (nPass = 1 on C8 operand planes): ONE fp16 MMA per MAC on the 16-bit planes only,
   // out = c8OutScale * recA[0] * recW[0] * D; the e4m3 planes are not read.
   int half16;
@@ -114,6 +121,13 @@ cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);
 // atomic merge are not free).
 int conv_plan_ksplit(const ConvGeom& g, double minGain);
 int plan_ksplit_waves(long long tiles, int slots, const ConvGeom& g, double minGain);
+// Tail split planner + fix-up launch for the pair kernels.  blockN = the C8 kernel's tile width, or 0 for the
+// split-bf16 / fp16 pair kernel (width chosen by its own variant logic).  Returns true and fills
+// g.tailTiles / g.tailSplit when the geometry profits; scratch must hold kTailScratchFloats floats.
+constexpr long long kTailScratchFloats = 74LL * 2 * 128 * 256;
+bool conv_plan_tail(ConvGeom& g, int blockN, float* scratch);
+cudaError_t launch_conv_tail_fixup(const ConvGeom& g, int blockN, cudaStream_t stream);
+int conv_pair_block_n(const ConvGeom& g);   // 0 when the geometry runs on the single-CTA kernel
 cudaError_t launch_conv_simt(const ConvGeom& g, cudaStream_t stream);
 // 16-bit main pass + two e4m3 correction passes (CTA-pair kernel, blockN 128 or 256) and its SIMT checker
 cudaError_t launch_conv_c8(const ConvGeom& g, int blockN, cudaStream_t stream);

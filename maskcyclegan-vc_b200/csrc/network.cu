@@ -218,6 +218,7 @@ struct Run {
   RunCfg rc;
   bool ok = true;
   bool forked = false;
+  float* tailScratch = nullptr;   // kTailScratchFloats floats of workspace for the conv kernels' tail split
   // weight-gradient GEMMs go to a side stream: they only feed the gradient blob, so they overlap
   // with the bandwidth-bound layer kernels and data-gradient convs of the main chain
   cudaStream_t wgrad_stream() {
@@ -411,6 +412,12 @@ int c8_block_n(const ConvGeom& g) {
   const bool wide = g.w.N % 256 == 0 && g.nSplit % 256 == 0 && c8_pair_tiles(g, 256) >= minWide;
   return wide ? 256 : 128;
 }
+// Tail split of the partial last wave (pair kernels, gemm_types.cuh): tried before the uniform split-K
+bool try_tail(Run& r, ConvGeom& g) {
+  if (r.rc.backend != 0 || !r.tailScratch || g.kSplit > 1) return false;
+  return conv_plan_tail(g, on_c8_kernel(r, g) ? c8_block_n(g) : 0, r.tailScratch);
+}
+
 cudaError_t launch_conv_any(Run& r, ConvGeom& g) {
   if (is_c8(g) && r.rc.half16) {
     g.nPass = 1;
@@ -461,7 +468,7 @@ void run_conv(Run& r, const ActOperand& a, const WgtOperand& w, const TapList& t
   if (!r.ok) return;
   g.statSum = r.rc.backend == 0 ? statSum : nullptr;
   g.statSq = statSq;
-  if (!g.statSum) plan_split(r, g, splitFloats, 0.08, what);
+  if (!try_tail(r, g) && !g.statSum) plan_split(r, g, splitFloats, 0.08, what);
   r.check(launch_conv_any(r, g), what);
 }
 
@@ -630,7 +637,7 @@ void run_dgrad_s2(Run& r, const ActOperand& dz, const WgtOperand& w, int K, int 
   g.algoFlops = 2.0 * B * Yp * Xp * (double)w.N * nt * dz.C;
   g.statSum = nullptr; g.statSq = nullptr; g.statSeg = 32;
   g.kSplit = 1;
-  plan_split(r, g, (long long)B * 4 * Yp * Xp * Cin, 0.08, what);
+  if (!try_tail(r, g)) plan_split(r, g, (long long)B * 4 * Yp * Xp * Cin, 0.08, what);
   r.check(launch_conv_any(r, g), what);
 }
 
@@ -653,7 +660,8 @@ void run_conv_in(Run& r, const ActOperand& a, const WgtOperand& w, const TapList
     // layers a little over one SM wave (Discriminator ds3: 80 pair tiles on 74 pairs): split-K plus
     // one stand-alone statistics pass over z beats paying a second, nearly empty round
     ConvGeom g = conv_geom(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0);
-    if (r.ok && !is_c8(g) && conv_plan_ksplit(g, 0.2) > 1) fused = false;   // C8 layers keep the fused statistics
+    // C8 layers and layers whose partial last wave the tail split handles keep the fused statistics
+    if (r.ok && !is_c8(g) && !try_tail(r, g) && conv_plan_ksplit(g, 0.2) > 1) fused = false;
   }
   if (!fused && r.rc.backend == 0 && splitFloats > 0) {
     run_conv(r, a, w, taps, oB, oY, oX, o, bias, nullptr, what, 1.0, nullptr, nullptr, splitFloats);
@@ -863,7 +871,8 @@ std::vector<SavedEntry> generator_saved_layout(int B, int T) {
 }
 long long generator_fwd_ws_bytes(int B, int T) {
   GenDims d(B, T);
-  return align_up((long long)B * 80 * d.X2 * 128 * 4, 256) + align_up(gen_stat_pool_floats(B) * 4, 256) + 1024;
+  return align_up((long long)B * 80 * d.X2 * 128 * 4, 256) + align_up(gen_stat_pool_floats(B) * 4, 256) + 1024 +
+         align_up(kTailScratchFloats * 4, 256) + 256;
 }
 
 int generator_forward(const void* packed, const float* x, const float* mask, int B, int T,
@@ -879,6 +888,7 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
   Arena wa(ws);
   StatPool sp(wa.takeT<float>(gen_stat_pool_floats(B)));   // conv-epilogue statistics, one memset for all layers
   r.check(cudaMemsetAsync(sp.base, 0, (size_t)gen_stat_pool_floats(B) * sizeof(float), st), "G zero stats");
+  r.tailScratch = wa.takeT<float>(kTailScratchFloats);
   float* ssq = nullptr;
 
   // parity-split buffers have a padding column/row when the extent is odd: keep it zero
@@ -1042,6 +1052,7 @@ long long generator_bwd_ws_bytes(int B, int T) {
   add(gen_stat_pool_floats(B) * 4);              // t1 / t2 reduction pool
   add(64 * 4);                                   // dz scale records (C8 mode)
   add(2 * 5120 * 4);                             // affine-grad sink
+  add(kTailScratchFloats * 4);                   // conv tail-split partials
   return align_up(b, 256) + 4096;
 }
 
@@ -1063,6 +1074,7 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
   StatPool tp(a.takeT<float>(gen_stat_pool_floats(B)));   // IN-backward reductions, one memset for all layers
   r.check(cudaMemsetAsync(tp.base, 0, (size_t)gen_stat_pool_floats(B) * sizeof(float), st), "G zero bwd sums");
   float* junk = a.takeT<float>(2 * 5120);  // sink for affine grads when the caller wants none
+  r.tailScratch = a.takeT<float>(kTailScratchFloats);
   auto gW = [&](int ci) { return gblob + cv[ci].gW; };
   auto gB = [&](int ci) -> float* { return needWgrad ? gblob + cv[ci].gB : nullptr; };
   auto gGa = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gGamma : junk; };
@@ -1313,7 +1325,8 @@ std::vector<SavedEntry> discriminator_saved_layout(int B, int T) {
 }
 long long discriminator_fwd_ws_bytes(int B, int T) {
   DisDims d(B, T);
-  return align_up((long long)B * 10 * d.W3 * 128 * 4, 256) + align_up(dis_stat_pool_floats(B) * 4, 256) + 1024;
+  return align_up((long long)B * 10 * d.W3 * 128 * 4, 256) + align_up(dis_stat_pool_floats(B) * 4, 256) + 1024 +
+         align_up(kTailScratchFloats * 4, 256) + 256;
 }
 
 int discriminator_forward(const void* packed, const float* x, int B, int T, float* out, void* saved,
@@ -1329,6 +1342,7 @@ int discriminator_forward(const void* packed, const float* x, int B, int T, floa
   Arena wa(ws);
   StatPool sp(wa.takeT<float>(dis_stat_pool_floats(B)));
   r.check(cudaMemsetAsync(sp.base, 0, (size_t)dis_stat_pool_floats(B) * sizeof(float), st), "D zero stats");
+  r.tailScratch = wa.takeT<float>(kTailScratchFloats);
   float* ssq = nullptr;
   if (d.T & 1) {
     r.check(launch_fill_zero(s.D0.hi, parity_elems(B, 80, d.T, 128) * 2, st), "zero D0");
@@ -1380,6 +1394,7 @@ long long discriminator_bwd_ws_bytes(int B, int T) {
   add(dis_stat_pool_floats(B) * 4);                            // t1 / t2 reduction pool
   add(64 * 4);                                                 // dz scale records (C8 mode)
   add(2 * 1024 * 4);                                           // affine-grad sink
+  add(kTailScratchFloats * 4);                                 // conv tail-split partials
   add(M3 * 128 * 2); add(M3 * 128 * 2);                        // dP
   add(M3 * 1024 * 4);                                          // dD3
   add(M3 * 1024 * 2); add(M3 * 1024 * 2);                      // dz3
@@ -1409,6 +1424,7 @@ int discriminator_backward(const void* packed, const void* saved, const float* o
   StatPool tp(a.takeT<float>(dis_stat_pool_floats(B)));
   r.check(cudaMemsetAsync(tp.base, 0, (size_t)dis_stat_pool_floats(B) * sizeof(float), st), "D zero bwd sums");
   float* junk = a.takeT<float>(2 * 1024);
+  r.tailScratch = a.takeT<float>(kTailScratchFloats);
   auto gW = [&](int ci) { return gblob + cv[ci].gW; };
   auto gB = [&](int ci) -> float* { return needWgrad ? gblob + cv[ci].gB : nullptr; };
   auto gGa = [&](int ni) -> float* { return needWgrad ? gblob + nm[ni].gGamma : junk; };
