@@ -370,34 +370,47 @@ def main():
     for _ in range(max(args.profile_steps, 1)):
         step_resident()
     torch.cuda.synchronize()
-    prof = eng.profile_collect()
+    kinds = eng.profile_collect_kinds()
     eng.profile_enable(False)
     eng.set_overlap(True)
-    conv, wg = prof["conv"], prof["wgrad"]
     peak = peaks["bf16_tflops_sustained"]
-    conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
-    wg_tf = wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0
     psteps = max(args.profile_steps, 1)
+
+    def tf(k):
+        return k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0
+
+    convs = [k for k in kinds if "wgrad" not in k["kernel"] and k["launches"] > 0]
+    wgs = [k for k in kinds if "wgrad" in k["kernel"] and k["launches"] > 0]
+    dom = max(convs, key=lambda k: k["ms"])            # the DOMINANT kernel family of the step
+    conv_all = {"ms": sum(k["ms"] for k in convs), "flops": sum(k["flops"] for k in convs), "launches": sum(k["launches"] for k in convs)}
+    wg = {"ms": sum(k["ms"] for k in wgs), "flops": sum(k["flops"] for k in wgs), "launches": sum(k["launches"] for k in wgs)}
     step_flops = (ts.STEP_FLOPS_LEAN_T64 if args.lean else ts.STEP_FLOPS_STRICT_T64) * B
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    # roofline.traffic: DRAM bytes per launch of the dominant kernel's OWN launches, from this round's
+    # `ncu --set full` capture (tools/ncu_summary.py --json; ncu cannot run inside the timed bench)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_kernel_traffic_%s.json" % ("c8h" if args.precision == "c8h" else args.precision))
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        key = "parity_final" if args.precision in ("parity", "mixed") else args.precision
-        if key in tj:
-            traffic = tj[key]["conv_dram_bytes_per_launch_mean_over_G_forward"]
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (implicit-GEMM fprop+dgrad, tcgen05)",
-                "achieved": conv_tf, "peak": peak, "unit": "TFLOP/s", "frac": conv_tf / peak,
+        for name, rec in tj.get("kernels", {}).items():
+            if name.replace(" ", "").startswith(dom["kernel"].replace(" ", "")):
+                traffic = rec["dram_bytes_per_launch"]
+                traffic_src = "%s (%s, summarised at commit %s): %d launches of this kernel in one G+D forward+backward at batch 64" % (
+                    os.path.basename(tpath), tj.get("source"), tj.get("summarised_at_commit"), rec["launches"])
+    roofline = {"bound": "tensor", "kernel": dom["kernel"] + " (implicit-GEMM forward + data-gradient convolutions, tcgen05 CTA pairs)",
+                "achieved": tf(dom), "peak": peak, "unit": "TFLOP/s", "frac": tf(dom) / peak,
                 "peak_source": "bf16_tflops_sustained, " + peaks["source"] + " (kernel timed inside a long step)",
-                "traffic": traffic,
-                "traffic_note": "dram__bytes_read+write per launch, mean over the 20 conv launches of one Generator forward at batch 64 (ncu --set full, profiles/r01_ncu_full_summary.md)",
-                "algorithmic_flops_per_launch": conv["flops"] / max(conv["launches"], 1),
-                "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
-                "launches_per_step": conv["launches"] / psteps,
-                "share_of_step": (conv["ms"] / psteps) / (ms / K),
-                "traffic_note": "dram__bytes_read+write per launch, mean over the 20 conv launches of one Generator forward at batch 64 (ncu --set full, profiles/r01_ncu_full_summary.md)",
-                "wgrad_kernel": {"achieved": wg_tf, "frac": wg_tf / peak, "launches_per_step": wg["launches"] / psteps,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_flops_per_launch": dom["flops"] / max(dom["launches"], 1),
+                "avg_launch_ms": dom["ms"] / max(dom["launches"], 1),
+                "launches_per_step": dom["launches"] / psteps,
+                "share_of_step": (dom["ms"] / psteps) / (ms / K),
+                "timing": "CUDA events around every launch on its stream (mcgvc_profile_*), %d extra steps with the weight-gradient side stream folded into the caller's stream" % psteps,
+                "all_conv_kernels": {"achieved": tf(conv_all), "frac": tf(conv_all) / peak, "launches_per_step": conv_all["launches"] / psteps,
+                                     "share_of_step": (conv_all["ms"] / psteps) / (ms / K)},
+                "by_kernel": [{"kernel": k["kernel"], "achieved": tf(k), "launches_per_step": k["launches"] / psteps,
+                               "share_of_step": (k["ms"] / psteps) / (ms / K)} for k in sorted(kinds, key=lambda k: -k["ms"]) if k["launches"] > 0],
+                "wgrad_kernel": {"achieved": tf(wg), "frac": tf(wg) / peak, "launches_per_step": wg["launches"] / psteps,
                                  "share_of_step": (wg["ms"] / psteps) / (ms / K)},
                 "whole_step": {"algorithmic_tflops": step_flops / (ms / K * 1e-3) / 1e12,
                                "frac": step_flops / (ms / K * 1e-3) / 1e12 / peak},

@@ -103,6 +103,12 @@ int mcgvc_set_graphs(int on);
 int mcgvc_graph_stats(long long* captures, long long* replays);
 int mcgvc_profile_enable(int on);
 int mcgvc_profile_collect(double* out6);
+/* The same per kernel family (conv_c8_kernel<256>, conv_tc2_kernel<256>, the fused trunk kernels, ...): out
+ * receives {ms, algorithmic FLOPs, launches} per kind, the return value is the number of kinds written;
+ * mcgvc_profile_kind_name names a kind.  bench.py reports the family with the largest time share as the
+ * step's dominant kernel. */
+int mcgvc_profile_collect_kinds(double* out, int max_kinds);
+const char* mcgvc_profile_kind_name(int kind);
 
 /* Device-side data feed: replaces the crop + frame-in-fill mask work of
  * dataset/vc_dataset.py:44-56 and the host->device copies of mask_cyclegan_vc/train.py:187-190.

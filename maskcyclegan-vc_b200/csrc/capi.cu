@@ -347,6 +347,15 @@ int mcgvc_profile_collect(double* out6) {
   return 0;
 }
 
+int mcgvc_profile_collect_kinds(double* out, int max_kinds) {
+  KernelProfile k[kProfKinds];
+  profile_collect_kinds(k);
+  int n = max_kinds < kProfKinds ? max_kinds : kProfKinds;
+  for (int i = 0; i < n; ++i) { out[3 * i] = k[i].ms; out[3 * i + 1] = k[i].flops; out[3 * i + 2] = (double)k[i].launches; }
+  return n;
+}
+const char* mcgvc_profile_kind_name(int kind) { return profile_kind_name(kind); }
+
 int mcgvc_saved_layout(int model, int B, int T, int index, char* name, int name_cap,
                        long long* offset, long long* bytes) {
   if (!shape_ok(B, T)) return 1;

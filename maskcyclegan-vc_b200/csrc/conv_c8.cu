@@ -316,7 +316,7 @@ cudaError_t launch_c8_t(const ConvGeom& g, cudaStream_t stream) {
   const int total = g.tailTiles > 0 ? tilesAll - g.tailTiles + g.tailTiles * g.tailSplit : tilesAll * (g.kSplit > 1 ? g.kSplit : 1);
   const int maxPairs = num_sms_c8() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
-  profile_begin(0, g.algoFlops, stream);
+  profile_begin(BLOCK_N == 256 ? kProfConvC8w : kProfConvC8n, g.algoFlops, stream);
   conv_c8_kernel<BLOCK_N><<<2 * pairs, kC8Threads, Cfg::kSmemBytes, stream>>>(tmA16, tmA8h, tmA8l, tmW16, tmW8h, tmW8l, g);
   profile_end(stream);
   cudaError_t e = launched();

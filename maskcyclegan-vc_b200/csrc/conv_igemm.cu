@@ -80,23 +80,38 @@ void profile_end(cudaStream_t s) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, s);
 }
-void profile_collect(KernelProfile* conv, KernelProfile* wgrad) {
+const char* profile_kind_name(int kind) {
+  static const char* names[kProfKinds] = {"conv_tc_kernel", "wgrad_tc_kernel / wgrad_tc2_kernel", "conv_c8_kernel<256>",
+                                          "conv_c8_kernel<128>", "conv_tc2_kernel<256>", "conv_tc2_kernel<128>",
+                                          "trunk_fwd_kernel / trunk_bwd_kernel", "wgrad_c8_kernel"};
+  return kind >= 0 && kind < kProfKinds ? names[kind] : "?";
+}
+void profile_collect_kinds(KernelProfile* out) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  KernelProfile k[2] = {{0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < kProfKinds; ++i) out[i] = KernelProfile{0, 0, 0};
   for (ProfRec& r : g_prof) {
     cudaEventSynchronize(r.b);
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
-      k[r.kind].ms += ms;
-      k[r.kind].flops += r.flops;
-      k[r.kind].launches += 1;
+    if (r.kind >= 0 && r.kind < kProfKinds && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      out[r.kind].ms += ms;
+      out[r.kind].flops += r.flops;
+      out[r.kind].launches += 1;
     }
     g_event_pool.push_back(r.a);
     g_event_pool.push_back(r.b);
   }
   g_prof.clear();
-  if (conv) *conv = k[0];
-  if (wgrad) *wgrad = k[1];
+}
+void profile_collect(KernelProfile* conv, KernelProfile* wgrad) {
+  KernelProfile k[kProfKinds];
+  profile_collect_kinds(k);
+  KernelProfile c{0, 0, 0}, w{0, 0, 0};
+  for (int i = 0; i < kProfKinds; ++i) {
+    KernelProfile& d = (i == kProfWgrad || i == kProfWgradC8) ? w : c;
+    d.ms += k[i].ms; d.flops += k[i].flops; d.launches += k[i].launches;
+  }
+  if (conv) *conv = c;
+  if (wgrad) *wgrad = w;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -782,7 +797,7 @@ static cudaError_t launch_conv_tc2_t(const ConvGeom& g, cudaStream_t stream) {
   const int total = g.tailTiles > 0 ? tilesAll - g.tailTiles + g.tailTiles * g.tailSplit : tilesAll * (g.kSplit > 1 ? g.kSplit : 1);
   const int maxPairs = num_sms() / 2;
   const int pairs = total < maxPairs ? total : maxPairs;
-  profile_begin(0, g.algoFlops, stream);
+  profile_begin(BLOCK_N == 256 ? kProfConv2w : kProfConv2n, g.algoFlops, stream);
   conv_tc2_kernel<BLOCK_N, NPASS><<<2 * pairs, kConv2Threads, Cfg::kSmemBytes, stream>>>(tmAh, tmAl, tmWh, tmWl, g);
   profile_end(stream);
   cudaError_t e = launched();

@@ -153,9 +153,23 @@ struct KernelProfile {
 };
 void profile_enable(bool on);
 bool profile_enabled();
-void profile_begin(int kind, double flops, cudaStream_t s);  // kind 0 = conv, 1 = wgrad
+// kinds: one per tensor-core kernel family, so that bench.py can name the DOMINANT kernel of a step
+enum ProfileKind {
+  kProfConv1 = 0,      // conv_tc_kernel (single-CTA tiles: small layers)
+  kProfWgrad = 1,      // wgrad_tc_kernel / wgrad_tc2_kernel (split-bf16 / fp16)
+  kProfConvC8w = 2,    // conv_c8_kernel<256>
+  kProfConvC8n = 3,    // conv_c8_kernel<128>
+  kProfConv2w = 4,     // conv_tc2_kernel<256, *>
+  kProfConv2n = 5,     // conv_tc2_kernel<128, *>
+  kProfTrunk = 6,      // trunk_fwd_kernel / trunk_bwd_kernel
+  kProfWgradC8 = 7,    // wgrad_c8_kernel
+  kProfKinds = 8
+};
+const char* profile_kind_name(int kind);
+void profile_begin(int kind, double flops, cudaStream_t s);
 void profile_end(cudaStream_t s);
-void profile_collect(KernelProfile* conv, KernelProfile* wgrad);  // synchronises, then resets
+void profile_collect(KernelProfile* conv, KernelProfile* wgrad);  // all conv kinds / all wgrad kinds; synchronises, then resets
+void profile_collect_kinds(KernelProfile* out /* [kProfKinds] */);
 
 const char* last_error();
 void set_error(const char* fmt, ...);

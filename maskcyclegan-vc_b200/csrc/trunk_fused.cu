@@ -868,7 +868,7 @@ cudaError_t launch_t(const TrunkFwdArgs& a, const TrunkFwdMaps& m, cudaStream_t 
   }
   const int tiles = (a.B + a.BB - 1) / a.BB;
   // algorithmic FLOPs: per row 2 * (1024 * 768 + 256 * 1536) per block
-  profile_begin(0, 2.0 * (double)a.B * a.W2 * (1024.0 * 768.0 + 256.0 * 1536.0) * kTrunkBlocks, stream);
+  profile_begin(kProfTrunk, 2.0 * (double)a.B * a.W2 * (1024.0 * 768.0 + 256.0 * 1536.0) * kTrunkBlocks, stream);
   trunk_fwd_kernel<NPASS><<<tiles * kCluster, 256, Cfg::kSmemBytes, stream>>>(tRh, tRl, tHh, tHl, tWah, tWal, tWbh, tWbl, a);
   profile_end(stream);
   return launched();
@@ -900,7 +900,7 @@ cudaError_t launch_bwd_t(const TrunkBwdArgs& a, const TrunkBwdMaps& m, cudaStrea
     attr_set = true;
   }
   const int tiles = (a.B + a.BB - 1) / a.BB;
-  profile_begin(0, 2.0 * (double)a.B * a.W2 * (1024.0 * 768.0 + 256.0 * 1536.0) * kTrunkBlocks, stream);
+  profile_begin(kProfTrunk, 2.0 * (double)a.B * a.W2 * (1024.0 * 768.0 + 256.0 * 1536.0) * kTrunkBlocks, stream);
   trunk_bwd_kernel<NPASS><<<tiles * kCluster, 256, Cfg::kSmemBytes, stream>>>(t5h, t5l, t4h, t4l, tWbh, tWbl, tWah, tWal, a);
   profile_end(stream);
   return launched();

@@ -238,7 +238,7 @@ cudaError_t launch_wg_c8_t(const WgradGeom& g, cudaStream_t stream) {
     attr_set = true;
   }
   const long long pairs = (long long)g.nTaps * (g.N / 256) * (g.C / CTILE) * g.splitK;
-  profile_begin(1, g.algoFlops, stream);
+  profile_begin(kProfWgradC8, g.algoFlops, stream);
   wgrad_c8_kernel<CTILE><<<(unsigned)(2 * pairs), 256, Cfg::kSmemBytes, stream>>>(tmZ16, tmZ8h, tmZ8l, tmX16, tmX8h, tmX8l, g);
   profile_end(stream);
   return launched();

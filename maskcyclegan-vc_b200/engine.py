@@ -266,3 +266,13 @@ def profile_collect():
     lib().mcgvc_profile_collect(buf)
     return {"conv": {"ms": buf[0], "flops": buf[1], "launches": int(buf[2])},
             "wgrad": {"ms": buf[3], "flops": buf[4], "launches": int(buf[5])}}
+
+
+def profile_collect_kinds():
+    """[{'kernel', 'ms', 'flops', 'launches'}] per tensor-core kernel family since the last collect."""
+    l = lib()
+    l.mcgvc_profile_kind_name.restype = ctypes.c_char_p
+    buf = (ctypes.c_double * (3 * 16))()
+    n = l.mcgvc_profile_collect_kinds(buf, 16)
+    return [{"kernel": l.mcgvc_profile_kind_name(i).decode(), "ms": buf[3 * i], "flops": buf[3 * i + 1],
+             "launches": int(buf[3 * i + 2])} for i in range(n)]

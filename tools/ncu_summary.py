@@ -19,6 +19,11 @@ def num(s):
 
 
 def main():
+    json_out = None
+    if "--json" in sys.argv:          # also write {kernel: {launches, dram_bytes_per_launch, avg_us}} for bench.py's roofline.traffic
+        i = sys.argv.index("--json")
+        json_out = sys.argv[i + 1]
+        del sys.argv[i:i + 2]
     path = sys.argv[1]
     title = sys.argv[2] if len(sys.argv) > 2 else os.path.basename(path)
     op = gzip.open if path.endswith(".gz") else open
@@ -95,6 +100,19 @@ def main():
     print("\n## per kernel\n")
     print("| kernel | launches | total us | avg us | time-weighted tensor pipe % | time-weighted tensor busy % | avg HBM GB/s | best % of HBM peak | DRAM bytes per launch MB |")
     print("|---|---|---|---|---|---|---|---|---|")
+    if json_out:
+        import subprocess
+        try:
+            commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+        except Exception:
+            commit = ""
+        js = {"source": os.path.basename(path), "title": title, "summarised_at_commit": commit,
+              "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the kernel's own launches in the capture "
+                      "(ncu --set full, isolated cold-cache launches)",
+              "kernels": {name.replace("void ", "").replace("<unnamed>::", ""): {"launches": n, "dram_bytes_per_launch": by / n, "avg_us": t / n}
+                          for name, (n, t, by, tpw, best, tmw) in agg.items()}}
+        with open(json_out, "w") as f:
+            json.dump(js, f, indent=1)
     for name, (n, t, by, tpw, best, tmw) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("| `%s` | %d | %.1f | %.1f | %.1f | %.1f | %.0f | %.1f | %.1f |" % (name[:60], n, t, t / n, tpw / t if t else 0, tmw / t if t else 0,
                                                                         by / (t * 1e-6) / 1e9 if t else 0, best, by / n / 1e6))
