@@ -335,6 +335,17 @@ def main():
     ms_e2e = timed_steps(step_e2e, K, world)
     clocks = sampler.stop() if sampler else None
 
+    dp_attr = None
+    if sync is not None:
+        # where the data-parallel overhead goes: device time of the two all-reduces per step, measured with
+        # CUDA events over a few extra steps (the timed region above runs without them)
+        sync.enable_timing(True)
+        ms_t = timed_steps(step_resident, 3, world)
+        coll_ms, n_coll = sync.collective_ms()
+        sync.enable_timing(False)
+        dp_attr = {"steps": 3, "ms_per_step": ms_t / 3, "allreduce_ms_per_step": coll_ms / 3, "allreduces_per_step": n_coll / 3,
+                   "note": "rank 0's device time inside ncclAllReduce (includes waiting for the slowest rank to arrive)"}
+
     frames = world * B * T_FRAMES
     value = frames * K / (ms * 1e-3)
     e2e_value = frames * K / (ms_e2e * 1e-3)
@@ -476,6 +487,7 @@ def main():
         if sync is not None:
             line["engine"]["allreduces"] = sync.reductions
             line["engine"]["allreduce_bytes"] = sync.reduced_bytes
+            line["engine"]["data_parallel_attribution"] = dp_attr
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:

@@ -42,6 +42,9 @@ class GradSync:
             self.groups.append({"mods": mods, "arena": arena, "pending": set()})
         self.reductions = 0
         self.reduced_bytes = 0
+        # optional attribution of the collective's cost (bench.py): CUDA events around every all-reduce
+        self.timing = False
+        self._events = []
 
     def world(self):
         return dist.get_world_size(self.pg) if dist.is_available() and dist.is_initialized() else 1
@@ -80,8 +83,27 @@ class GradSync:
             for m in mods:
                 self._allreduce(m._flat_grad)
 
+    def enable_timing(self, on=True):
+        self.timing = bool(on)
+        self._events = []
+
+    def collective_ms(self):
+        """Summed device time of the all-reduces since enable_timing() (synchronises)."""
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._events)
+        n = len(self._events)
+        self._events = []
+        return ms, n
+
     def _allreduce(self, buf):
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)   # average: see unpack_scale()
+        if self.timing and buf.is_cuda:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
+            b.record()
+            self._events.append((a, b))
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)   # average: see unpack_scale()
         self.reductions += 1
         self.reduced_bytes += buf.numel() * 4
 
