@@ -150,6 +150,9 @@ int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY,
 /* Host-side split-K planner for a convolution geometry (output grid oB x oY x oX, C input channels, N
  * output columns, nTaps filter taps) on the split-bf16 kernels; needs no GPU (assumes 148 SMs then). */
 int mcgvc_debug_plan_ksplit(int oB, int oY, int oX, int C, int N, int nSplit, int nTaps, double minGain);
+/* Host-side tail-split planner of the CTA-pair kernels (blockN = tile width 128 / 256): number of K-slices the
+ * tiles of the partial last wave are cut into (0 = none); *tail_tiles receives how many tiles that is. */
+int mcgvc_debug_plan_tail(int oB, int oY, int oX, int C, int N, int nSplit, int nTaps, int blockN, int* tail_tiles);
 /* split-K factor used by the following mcgvc_debug_conv calls on the tensor-core backends: every tile's
  * k-blocks run as `k` work items that are added into `out` (which the caller zero-fills); 1 = off. */
 int mcgvc_debug_set_conv_ksplit(int k);

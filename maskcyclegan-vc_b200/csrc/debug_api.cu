@@ -34,6 +34,25 @@ int mcgvc_debug_plan_ksplit(int oB, int oY, int oX, int C, int N, int nSplit, in
   return conv_plan_ksplit(g, minGain);
 }
 
+/* Tail-split plan for the same kind of geometry on a pair kernel of tile width blockN (host logic only):
+ * returns the number of K-slices per tail tile (0 = no tail split) and stores the number of tail tiles. */
+int mcgvc_debug_plan_tail(int oB, int oY, int oX, int C, int N, int nSplit, int nTaps, int blockN, int* tail_tiles) {
+  ConvGeom g{};
+  g.a.C = C; g.w.K = C; g.w.N = N;
+  g.oX = oX; g.oY = oY; g.oB = oB;
+  if (!choose_box(oB, oY, oX, kTileM, &g.BX, &g.BY, &g.BB)) return -1;
+  g.tilesX = (oX + g.BX - 1) / g.BX;
+  g.tilesY = (oY + g.BY - 1) / g.BY;
+  g.tilesB = (oB + g.BB - 1) / g.BB;
+  g.nTaps = nTaps; g.cBlocks = C / kBlockK;
+  g.nGroups = 1; g.grpTapStart[0] = 0; g.grpTapCount[0] = nTaps;
+  g.nSplit = nSplit;
+  static float dummy;                       // the planner only needs a non-null scratch pointer
+  const bool on = conv_plan_tail(g, blockN, &dummy);
+  if (tail_tiles) *tail_tiles = on ? g.tailTiles : 0;
+  return on ? g.tailSplit : 0;
+}
+
 int mcgvc_debug_conv(const void* a_hi, const void* a_lo, int aC, int aX, int aY, int aP, int aB,
                      const void* w_hi, const void* w_lo, int wK, int wN, int wT, int oX, int oY,
                      int oB, int nTaps, const int8_t* taps4, float* out, long long sB,

@@ -120,6 +120,26 @@ def test_split_k_planner_fills_whole_waves(pkg):
     assert plan(64, 10, 8, 512, 1024, 1024, 9, 0.2) > 1
 
 
+def test_tail_split_planner(pkg):
+    """Host logic of the tail split (csrc/conv_igemm.cu conv_plan_tail), no GPU needed (148 SMs assumed):
+    the partial last wave of the persistent pair kernels is cut into K-slices that all 74 CTA pairs share."""
+    import ctypes
+    lib = pkg.engine.lib()
+    plan = lib.mcgvc_debug_plan_tail
+    plan.argtypes = [ctypes.c_int] * 8 + [ctypes.POINTER(ctypes.c_int)]
+    tiles = ctypes.c_int(0)
+    # up1 forward at batch 64: 20480 positions x 1024 columns = 320 pair tiles = 4.32 waves -> 24 tail tiles x 3
+    assert plan(64, 20, 16, 256, 1024, 1024, 25, 256, ctypes.byref(tiles)) == 3 and tiles.value == 24
+    # up1 data gradient: 80 tiles = 1.08 waves -> the 6 tiles of the second round split 8 ways
+    assert plan(64, 20, 16, 1024, 256, 256, 25, 256, ctypes.byref(tiles)) == 8 and tiles.value == 6
+    # up2 forward: 640 tiles = 8.65 waves, 48 tail tiles on 74 pairs: nothing to share
+    assert plan(64, 40, 32, 256, 512, 512, 25, 256, ctypes.byref(tiles)) == 0
+    # batch 1, up2: 10 tiles on 74 pairs (a 100-k-block serial loop each) -> 7 slices per tile
+    assert plan(1, 40, 32, 256, 512, 512, 25, 256, ctypes.byref(tiles)) == 7 and tiles.value == 10
+    # short K loops (the heads: 2 k-blocks) are never split
+    assert plan(64, 80, 64, 128, 128, 128, 1, 128, ctypes.byref(tiles)) == 0
+
+
 def test_opt_in_entry_points_validate_their_arguments(pkg):
     """Argument checks of the f2 / f3 entry points happen before any CUDA call: status 1 + message."""
     import ctypes
