@@ -112,6 +112,10 @@ struct WgradGeom {
   const float* c8RecZ;   // device-side scale records {1/S, 1/E} of dz and x (null: host multipliers only)
   const float* c8RecX;
   int half16;            // nPass = 1 on the fp16 planes of C8 operands, see ConvGeom::half16
+  // Tap pairing (single-pass pair kernel only, all ztaps zero): one work item stages a dz k-block ONCE and
+  // multiplies it with the x boxes of TWO filter taps (two TMEM accumulators): 48 KB instead of 64 KB of
+  // operands per 8 MMAs, which takes the single-pass kernel from ingest-bound to MMA-bound.
+  int tapPair;
 };
 
 cudaError_t launch_conv_tc(const ConvGeom& g, cudaStream_t stream);

@@ -520,12 +520,30 @@ void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList&
   g.nPass = r.rc.nPass;
   g.algoFlops = 2.0 * pB * pY * pX * (double)g.N * g.C * xtaps.n * algoFrac;
   cudaStream_t ws = r.wgrad_stream();
+  // single-pass pair kernel: two taps per work item share one staged dz k-block (wgrad_gemm.cu)
+  auto pair_taps = [&]() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MCGVC_WGRAD_TAP_PAIR"); on = e ? atoi(e) : 1; }
+    if (!on || r.rc.backend != 0 || ztaps || g.nPass != 1 || g.N % 256 || g.cTile < 128 || xtaps.n < 2) return;
+    g.tapPair = 1;
+    const long long unitsP = (long long)((xtaps.n + 1) / 2) * (g.N / 256) * (g.C / g.cTile);
+    int best = 1;
+    double bestC = 1e30;
+    for (long long sk = 1; sk <= maxSplit; ++sk) {
+      const double waves = (double)(unitsP * sk) / 74.0;
+      const double rounds = (double)((unitsP * sk + 73) / 74);
+      const double cost = rounds / waves * (1.0 + 0.01 * (double)sk) + (waves < 1.0 ? 1.0 / waves : 0.0);
+      if (cost < bestC - 1e-9) { bestC = cost; best = (int)sk; }
+    }
+    g.splitK = best;
+  };
   if (dz.h8 && x.h8 && r.rc.half16) {   // C8H: one fp16 pass over the 16-bit planes
     g.nPass = 1;
     g.half16 = 1;
     g.c8OutScale = 1.f;
     g.c8RecZ = dz.rec;
     g.c8RecX = x.rec;
+    pair_taps();
     r.check(r.rc.backend == 0 ? launch_wgrad_tc(g, ws) : launch_wgrad_simt(g, ws), what);
     return;
   }
@@ -552,6 +570,7 @@ void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList&
     return;
   }
   if ((dz.h8 != nullptr) != (x.h8 != nullptr)) { r.ok = false; set_error("%s: dz and x disagree on the C8 format", what); return; }
+  pair_taps();   // mixed / fast modes (nPass = 1)
   r.check(r.rc.backend == 0 ? launch_wgrad_tc(g, ws) : launch_wgrad_simt(g, ws), what);
 }
 

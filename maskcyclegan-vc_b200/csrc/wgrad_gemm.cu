@@ -213,6 +213,11 @@ static bool check_wgrad_geom(const WgradGeom& g) {
   if (g.nTaps < 1 || g.nTaps > kMaxTaps || g.splitK < 1) { set_error("wgrad: taps/splitK"); return false; }
   if (g.nPass != 1 && g.nPass != 3) { set_error("wgrad: nPass=%d", g.nPass); return false; }
   if (g.half16 && g.nPass != 1) { set_error("wgrad: half16 needs nPass = 1"); return false; }
+  if (g.tapPair) {
+    if (g.nPass != 1 || g.N % 256 || g.cTile < 128) { set_error("wgrad: tap pairing needs the single-pass pair kernel"); return false; }
+    for (int i = 0; i < g.nTaps; ++i)
+      if (g.ztaps[i].dx || g.ztaps[i].dy) { set_error("wgrad: tap pairing needs an unshifted dz operand"); return false; }
+  }
   return true;
 }
 
@@ -457,6 +462,195 @@ static cudaError_t launch_wgrad_tc2_t(const WgradGeom& g, cudaStream_t stream) {
   return launched();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tap-paired single-pass variant (WgradGeom::tapPair): same CTA-pair decomposition, but one work item
+// owns TWO filter taps of its (256 gradient rows x CTILE channels) tile.  The dz k-block is staged once
+// and multiplied with both taps' x boxes into two TMEM accumulators (2 x CTILE <= 512 columns).  A
+// single bf16 / fp16 pass needs 32 KB of operands per 4 MMAs in the unpaired kernel (116 GB/s per SM at
+// the MMA rate, more than an SM can ingest); pairing makes it 48 KB per 8 MMAs.
+template <int CTILE>
+struct WgradPCfg {
+  static constexpr int kZBytes = 2 * kChunkBytes;                   // this CTA's 128 n rows
+  static constexpr int kXBytes = (CTILE / 128) * kChunkBytes;       // this CTA's CTILE/2 channels, per tap
+  static constexpr int kStageBytes = kZBytes + 2 * kXBytes;         // 48 KB (CTILE 256) / 32 KB (CTILE 128)
+  static constexpr int kStagesRaw = (222 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * CTILE;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(CTILE == 128 || CTILE == 256, "pair tile is 128 or 256 channels wide");
+};
+
+template <int CTILE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+wgrad_tc2p_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmXh,
+                  const __grid_constant__ WgradGeom g) {
+  using Cfg = WgradPCfg<CTILE>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int cTiles = g.C / CTILE;
+  const int nTiles = g.N / 256;
+  int w = blockIdx.x >> 1;
+  const int split = w % g.splitK;
+  w /= g.splitK;
+  const int ct = w % cTiles;
+  w /= cTiles;
+  const int nt = w % nTiles;
+  const int tp = w / nTiles;                            // < ceil(nTaps / 2)
+  const int t0 = 2 * tp, t1 = 2 * tp + 1;
+  const bool two = t1 < g.nTaps;
+  const Tap tapA = g.taps[t0];
+  const Tap tapB = g.taps[two ? t1 : t0];
+  const int n0 = nt * 256 + (int)rank * 128;
+  const int c0 = ct * CTILE;
+  const int cLoad = c0 + (int)rank * (CTILE / 2);
+
+  const int posTiles = g.tilesX * g.tilesY * g.tilesB;
+  const int per = (posTiles + g.splitK - 1) / g.splitK;
+  const int kBegin = split * per;
+  const int kEnd = (kBegin + per < posTiles) ? kBegin + per : posTiles;
+  const int numK = kEnd - kBegin;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmZh);
+    ptx::prefetch_tmap(&tmXh);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 2);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(tfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (numK > 0) {
+    if (warp == 0 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      // a lone last tap still stages (and multiplies) its x box twice into the second accumulator,
+      // which the epilogue ignores: one code path, at most one wasted tap in 25
+      for (int kt = kBegin; kt < kEnd; ++kt) {
+        int m = kt;
+        const int tx = m % g.tilesX;
+        m /= g.tilesX;
+        const int ty = m % g.tilesY;
+        const int tb = m / g.tilesY;
+        const int x0 = tx * g.BX, y0 = ty * g.BY, b0 = tb * g.BB;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          ptx::tma_load_5d_2sm(st + j * kChunkBytes, &tmZh, &full[stage], n0 + j * 64, x0, y0, 0, b0);
+#pragma unroll
+        for (int j = 0; j < CTILE / 128; ++j) {
+          ptx::tma_load_5d_2sm(st + Cfg::kZBytes + j * kChunkBytes, &tmXh, &full[stage], cLoad + j * 64,
+                               x0 + tapA.dx, y0 + tapA.dy, tapA.plane, b0);
+          ptx::tma_load_5d_2sm(st + Cfg::kZBytes + Cfg::kXBytes + j * kChunkBytes, &tmXh, &full[stage], cLoad + j * 64,
+                               x0 + tapB.dx, y0 + tapB.dy, tapB.plane, b0);
+        }
+        if (!leader) ptx::mbar_arrive_remote(&full[stage], 0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1 && lane == 0 && leader) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(256, CTILE, 1, 1) & ~(g.half16 ? ((1u << 7) | (1u << 10)) : 0u);
+      constexpr uint32_t kLbo = kChunkBytes;
+      constexpr uint32_t kSbo = 1024;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < numK; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sZ = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sXa = sZ + Cfg::kZBytes;
+        const uint32_t sXb = sXa + Cfg::kXBytes;
+#pragma unroll
+        for (int k = 0; k < kWgBlockPos / 16; ++k) {
+          const uint64_t dZ = ptx::umma_smem_desc_sw128(sZ + k * 2048, kLbo, kSbo);
+          ptx::umma_bf16_2cta(tmem_base, dZ, ptx::umma_smem_desc_sw128(sXa + k * 2048, kLbo, kSbo), idesc, (kb | k) != 0);
+          ptx::umma_bf16_2cta(tmem_base + CTILE, dZ, ptx::umma_smem_desc_sw128(sXb + k * 2048, kLbo, kSbo), idesc, (kb | k) != 0);
+        }
+        ptx::umma_commit_2cta(&empty[stage], 0x3);
+        if (kb == numK - 1) ptx::umma_commit_2cta(tfull, 0x3);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp >= 4) {
+      const int quad = warp & 3;
+      const int n = n0 + quad * 32 + lane;
+      float osc = 1.f;
+      if (g.half16) {
+        osc = g.c8OutScale;
+        if (g.c8RecZ && g.c8RecX) osc *= __ldg(g.c8RecZ) * __ldg(g.c8RecX);
+      }
+      ptx::mbar_wait(tfull, 0);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+      for (int which = 0; which < (two ? 2 : 1); ++which) {
+        const Tap tap = which ? tapB : tapA;
+        float* drow = g.dw + ((long long)tap.w * g.N + n) * g.C + c0;
+#pragma unroll 1
+        for (int j = 0; j < CTILE / 32; ++j) {
+          uint32_t v[32];
+          ptx::tmem_ld32(taddr + which * CTILE + j * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            red_add_v4(drow + j * 32 + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
+                       osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 2) ptx::tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+}
+
+template <int CTILE>
+static cudaError_t launch_wgrad_tc2p_t(const WgradGeom& g, cudaStream_t stream) {
+  using Cfg = WgradPCfg<CTILE>;
+  CUtensorMap tmZh, tmXh;
+  if (!make_act_tmap(&tmZh, g.dz.hi, g.dz, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  if (!make_act_tmap(&tmXh, g.x.hi, g.x, g.BX, g.BY, g.BB)) return cudaErrorInvalidValue;
+  static bool attr_done[64] = {};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_done[dev_id & 63];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc2p_kernel<CTILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("wgrad2p: smem attr: %s", cudaGetErrorString(e)); return e; }
+    attr_set = true;
+  }
+  const long long pairs = (long long)((g.nTaps + 1) / 2) * (g.N / 256) * (g.C / CTILE) * g.splitK;
+  profile_begin(1, g.algoFlops, stream);
+  wgrad_tc2p_kernel<CTILE><<<(unsigned)(2 * pairs), 256, Cfg::kSmemBytes, stream>>>(tmZh, tmXh, g);
+  profile_end(stream);
+  return launched();
+}
+
 static int env_wg_cta2() {
   static int v = -1;
   if (v < 0) {
@@ -475,6 +669,7 @@ cudaError_t launch_wgrad_tc(const WgradGeom& g, cudaStream_t stream) {
     // pair tile: 256 gradient rows x (128 | 256) channels; cTile (64/128/256) keeps its meaning
     // of "channels per work item", so the pair kernel needs cTile >= 128
     if (want && g.N % 256 == 0 && g.cTile >= 128) {
+      if (g.tapPair && g.nPass == 1) return g.cTile == 256 ? launch_wgrad_tc2p_t<256>(g, stream) : launch_wgrad_tc2p_t<128>(g, stream);
       if (g.nPass == 3) return g.cTile == 256 ? launch_wgrad_tc2_t<256, 3>(g, stream) : launch_wgrad_tc2_t<128, 3>(g, stream);
       return g.cTile == 256 ? launch_wgrad_tc2_t<256, 1>(g, stream) : launch_wgrad_tc2_t<128, 1>(g, stream);
     }
