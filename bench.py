@@ -456,6 +456,24 @@ def main():
                           "note": "MCGVC_LEAN=1: gradients the reference loop computes and then discards are not computed -- reported for context only"})
             pkg.set_lean(False)
 
+    # SURVEY 8(f) rows f1 + f2 wired into the step behind a flag (train.py owns Adam and the loss tail, so the
+    # headline keeps torch.optim.Adam and the torch loss expressions): same models, engine FusedAdam on the flat
+    # buffers + the one-launch-per-term loss kernels
+    opt_in = None
+    if args.fast_steps > 0 and args.optimizer == "torch":
+        fg = pkg.FusedAdam(models[:2], lr=2e-4, betas=(0.5, 0.999))
+        fd = pkg.FusedAdam(models[2:], lr=1e-4, betas=(0.5, 0.999))
+
+        def step_opt_in():
+            ts.train_step(models, fg, fd, resident, fused_losses=True)
+
+        for _ in range(2):
+            step_opt_in()
+        ms_o = timed_steps(step_opt_in, args.fast_steps, world)
+        opt_in = {"what": "engine FusedAdam (f1) + fused loss tail (f2) instead of torch.optim.Adam / torch loss expressions",
+                  "precision": args.precision, "ms_per_step": ms_o / args.fast_steps,
+                  "value": frames * args.fast_steps / (ms_o * 1e-3), "unit": UNIT}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args.cpu_batch, args.cpu_steps)
@@ -479,6 +497,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "other_precision": other,
+            "opt_in_f1_f2": opt_in,
             "generator_fwd_bwd": {"note": "north_star target line: Generator forward+backward at batch %d, 80x64 "
                                           "(58.636 algorithmic GFLOP per sample; parity mode issues 3 MMAs per MAC, "
                                           "mixed = forward x3 / backward x1)" % B, **gfb},
