@@ -761,3 +761,50 @@ def test_c8h_tcgen05_kernels_agree_with_simt_checker(env):
     print("tcgen05 vs SIMT:", {k: {kk: "%.2e" % vv for kk, vv in v.items()} for k, v in devs.items()})
     for key, v in devs["c8h"].items():
         assert v < 1e-3, (key, v)
+
+
+# ---------------------------------------------------------------------------------------------
+# Robustness of the autograd coupling (round-1 advisor findings).
+def test_failed_backward_does_not_poison_later_passes(env, monkeypatch):
+    """A backward pass that raises after one module already ran its engine backward (callback queued,
+    partial sums in its gradient blob) must not stop later passes from publishing gradients, nor leak
+    the partial sums into them."""
+    pkg = env["pkg"]
+    e = pkg.engine
+    G, D = env["G"], env["D"]
+    x, m, _, _ = O.synthetic_batch(2, 64, seed=91)
+    xc, mc = x.cuda(), m.cuda()
+
+    def clean():
+        G.zero_grad(set_to_none=True)
+        D.zero_grad(set_to_none=True)
+        ((1 - D(G(xc, mc))) ** 2).mean().backward()
+        torch.cuda.synchronize()
+        return G._flat_grad.clone(), D._flat_grad.clone()
+
+    g_ref, d_ref = clean()
+    G.zero_grad(set_to_none=True)
+    D.zero_grad(set_to_none=True)
+    loss = ((1 - D(G(xc, mc))) ** 2).mean()
+
+    def boom(*a, **k):
+        raise e.EngineError("injected failure in generator_backward")
+
+    monkeypatch.setattr(e, "generator_backward", boom)
+    with pytest.raises(RuntimeError):
+        loss.backward()                      # D's backward ran and queued its callback; G's raised
+    monkeypatch.undo()
+    assert all(p.grad is None for p in D.parameters())        # nothing was published by the failed pass
+    g2, d2 = clean()
+    assert all(p.grad is not None for n, p in D.named_parameters() if not n.startswith("downSample4."))
+    assert rel(g2, g_ref) < 1e-4 and rel(d2, d_ref) < 1e-4, (rel(g2, g_ref), rel(d2, d_ref))
+
+
+def test_second_backward_through_a_consumed_graph_raises_a_clear_error(env):
+    G = env["G"]
+    x, m, _, _ = O.synthetic_batch(1, 64, seed=92)
+    y = G(x.cuda(), m.cuda())
+    y.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="already consumed"):
+        y.sum().backward()
+    G.zero_grad(set_to_none=True)
