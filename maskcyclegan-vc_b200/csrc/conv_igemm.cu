@@ -923,6 +923,7 @@ bool conv_plan_tail(ConvGeom& g, int blockN, float* scratch) {
   const int bn = blockN ? blockN : conv_pair_block_n(g);
   if (bn == 0 || g.w.N % bn || g.nSplit % bn) return false;
   const int slots = num_sms() / 2;
+  if (slots > 74) return false;                      // kTailScratchFloats is sized for 74 slice slabs (148 SMs)
   const int mTiles = g.tilesX * g.tilesY * g.tilesB;
   const long long T = (long long)(g.w.N / bn) * ((mTiles + 1) / 2) * g.nGroups;
   int minK = 1 << 30;
