@@ -18,6 +18,23 @@ static int grid_for(long long work, int threads) {
   return (int)blocks;
 }
 
+// CTAs of `kernel` the whole device keeps resident at once (occupancy x SM count) when launched with
+// `dynSmem` bytes of dynamic shared memory (opted in here), cached per kernel: the streaming layer
+// kernels size their grids as a whole number of such waves.
+template <typename K>
+static int resident_ctas(K kernel, int threads, size_t dynSmem, int* cache) {
+  if (*cache > 0) return *cache;
+  int dev = 0, sms = 148, occ = 1;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dynSmem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, dynSmem) != cudaSuccess || occ < 1) {
+    (void)cudaGetLastError();
+    occ = 1;
+  }
+  *cache = occ * (sms > 0 ? sms : 148);
+  return *cache;
+}
+
 // fast sigmoid: ex2.approx + rcp.approx (~1e-7 relative error); an IEEE division here costs more
 // instructions than the rest of an activation and made several layer kernels issue-bound
 __device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
@@ -48,13 +65,12 @@ __device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* l
 __device__ __forceinline__ void store_planes(__nv_bfloat16* hi, __nv_bfloat16* lo, const PlaneFmt& f,
                                              long long off, float4 v) {
   if (!f.c8) { split_store4(hi, lo, off, v); return; }
-  // saturate instead of overflowing to inf (fp16 tops out at 65504; activations are O(1), dz*S <= 2^14)
-  const float sx = fminf(fmaxf(v.x * f.S, -65504.f), 65504.f), sy = fminf(fmaxf(v.y * f.S, -65504.f), 65504.f),
-              sz = fminf(fmaxf(v.z * f.S, -65504.f), 65504.f), sw = fminf(fmaxf(v.w * f.S, -65504.f), 65504.f);
-  const __half2 h01 = __floats2half2_rn(sx, sy), h23 = __floats2half2_rn(sz, sw);
+  // saturating pack (fp16 tops out at 65504; activations are O(1), dz*S <= 2^14): one F2FP per pair
+  const float sx = v.x * f.S, sy = v.y * f.S, sz = v.z * f.S, sw = v.w * f.S;
   uint2 ph;
-  ph.x = *reinterpret_cast<const uint32_t*>(&h01);
-  ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ph.x) : "f"(sy), "f"(sx));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ph.y) : "f"(sw), "f"(sz));
+  const __half2 h01 = *reinterpret_cast<const __half2*>(&ph.x), h23 = *reinterpret_cast<const __half2*>(&ph.y);
   *reinterpret_cast<uint2*>(hi + off) = ph;
   if (f.c8 == 2) return;   // C8H dz: only the fp16 plane is ever read (single-pass backward GEMMs)
   const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -221,8 +237,34 @@ __device__ __forceinline__ float4 gate4(float4 a, float4 g) {
   return make_float4(a.x * sigmoidf_(g.x), a.y * sigmoidf_(g.y), a.z * sigmoidf_(g.z), a.w * sigmoidf_(g.w));
 }
 
+// Streaming position loops of the layer kernels below.  Each thread runs a private cp.async ring in
+// shared memory: the 16-byte loads of the next kRing-1 positions are in flight (LDGSTS, no
+// registers held) while it does the math and the stores of the current one, and it only ever
+// reads back the slots it filled itself, so cp.async.wait_group is the only synchronisation.
+// A plain load-use loop left these kernels latency-bound at under half of the HBM rate
+// (profiles/r02_ncu_full_c8_raw.csv.gz: 2 LDG.128 per warp in flight, no pipe above 30 %), and
+// register double-buffering traded the in-flight depth against occupancy.
+__device__ __forceinline__ void cp_async16(float4* smem, const float* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+               ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 16-byte loads per position and ring depth per mode (ring bytes per CTA = depth * loads * 4 KB)
+template <int MODE>
+constexpr int kFwdLoads = (MODE == kGatedIN || MODE == kGatedNoNorm || MODE == kINOnly) ? 2 : 1;
+template <int MODE>
+constexpr int kBwdLoads = (MODE == kGatedIN || MODE == kGatedNoNorm) ? 3 : 2;
+template <int LOADS>
+constexpr int kRingDepth = LOADS == 1 ? 8 : (LOADS == 2 ? 6 : 4);
+extern __shared__ float4 g_ring[];   // [depth][loads][256 threads]
+
 template <int MODE>
 __global__ void __launch_bounds__(256) apply_fwd_kernel(const ApplyArgs a) {
+  constexpr bool kGated = (MODE == kGatedIN || MODE == kGatedNoNorm);
+  constexpr int kL = kFwdLoads<MODE>, kD = kRingDepth<kL>;
   const int C = a.out.C, C4 = C >> 2;           // C4 in {32, 64, 128, 256}
   const int rows = 256 / C4;                    // positions handled per block iteration
   const int c = (threadIdx.x % C4) << 2;
@@ -235,54 +277,88 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const ApplyArgs a) {
     if (MODE == kGatedIN) kg = load_scale_shift(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, C + c);
   }
   const float* zimg = a.z + (long long)img * a.zY * a.zX * a.Nz;
-  const float* rimg = a.residual ? a.residual + (long long)img * P * C : nullptr;
-  for (int p = blockIdx.x * rows + r; p < P; p += gridDim.x * rows) {
-    const int y = p / X, x = p - y * X;
-    const float* zr;
-    if (MODE == kINSwishShuffle)
-      zr = zimg + ((long long)(y >> 1) * a.zX + (x >> 1)) * a.Nz + ((((y & 1) << 1) | (x & 1)) * C) + c;
-    else
-      zr = zimg + (long long)p * a.Nz + c;
-    const float4 v = ld4(zr);
+  const float* rimg = (MODE == kINOnly && a.residual) ? a.residual + (long long)img * P * C : nullptr;
+  const int step = gridDim.x * rows;
+  float4* ring = g_ring + threadIdx.x;
+  auto issue = [&](int st, int p) {
+    if (p < P) {
+      const float* zr;
+      if (MODE == kINSwishShuffle) {
+        const int y = p / X, x = p - y * X;
+        zr = zimg + ((long long)(y >> 1) * a.zX + (x >> 1)) * a.Nz + ((((y & 1) << 1) | (x & 1)) * C) + c;
+      } else {
+        zr = zimg + (long long)p * a.Nz + c;
+      }
+      cp_async16(ring + (st * kL) * 256, zr);
+      if (kGated) cp_async16(ring + (st * kL + 1) * 256, zr + C);
+      if (MODE == kINOnly && rimg) cp_async16(ring + (st * kL + 1) * 256, rimg + (long long)p * C + c);
+    }
+    cp_async_commit();
+  };
+  int p = blockIdx.x * rows + r;
+#pragma unroll
+  for (int s = 0; s < kD - 1; ++s) issue(s, p + s * step);
+  int st = 0;
+  for (; p < P; p += step) {
+    issue(st == 0 ? kD - 1 : st - 1, p + (kD - 1) * step);
+    cp_async_wait<kD - 1>();
+    const float4 v = ring[(st * kL) * 256];
+    long long off;
+    if (MODE != kINSwishShuffle && !a.out.parity) {
+      off = ((long long)img * P + p) * C + c;
+    } else {
+      const int y = p / X, x = p - y * X;
+      off = act_off(a.out, img, y, x) + c;
+    }
     float4 o;
     if (MODE == kGatedNoNorm) {
-      o = gate4(v, ld4(zr + C));
+      o = gate4(v, ring[(st * kL + 1) * 256]);
     } else if (MODE == kGatedIN) {
-      o = gate4(ss_apply(v, ka), ss_apply(ld4(zr + C), kg));
+      o = gate4(ss_apply(v, ka), ss_apply(ring[(st * kL + 1) * 256], kg));
     } else if (MODE == kINOnly) {
       o = ss_apply(v, ka);
       if (rimg) {
-        const float4 rv = ld4(rimg + (long long)p * C + c);
+        const float4 rv = ring[(st * kL + 1) * 256];
         o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
       }
     } else {  // kINSwish, kINSwishShuffle
       o = swish4(ss_apply(v, ka));
     }
-    const long long off = act_off(a.out, img, y, x) + c;
     if (a.out.hi) store_planes(a.out.hi, a.out.lo, a.out.fmt, off, o);
     if (a.out.f32) *reinterpret_cast<float4*>(a.out.f32 + off) = o;
+    if (++st == kD) st = 0;
   }
+  cp_async_wait<0>();
 }
 
-static dim3 rows_grid(int P, int rows, int nImg) {
-  int bx = (P + rows - 1) / rows;
-  int cap = (148 * 8 + nImg - 1) / nImg;
+// Grid of a streaming layer kernel: block row = image, `rows*batch` positions per trip; two resident
+// waves in total (resident = occupancy x SMs of that instantiation), never more blocks than trips.
+static dim3 rows_grid(int P, int rows, int batch, int nImg, int resident) {
+  int bx = (P + rows * batch - 1) / (rows * batch);
+  int cap = 2 * resident / nImg;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   return dim3(bx, nImg);
 }
 
+template <int MODE>
+static void run_apply_fwd(const ApplyArgs& a, cudaStream_t s) {
+  static int resident = 0;
+  constexpr size_t ring = (size_t)kRingDepth<kFwdLoads<MODE>> * kFwdLoads<MODE> * 256 * sizeof(float4);
+  const dim3 g = rows_grid(a.out.Y * a.out.X, 256 / (a.out.C >> 2), 4, a.out.nImg,
+                           resident_ctas(apply_fwd_kernel<MODE>, 256, ring, &resident));
+  apply_fwd_kernel<MODE><<<g, 256, ring, s>>>(a);
+}
 cudaError_t launch_apply_fwd(const ApplyArgs& a, cudaStream_t s) {
   const int C4 = a.out.C >> 2;
   if (C4 < 1 || C4 > 256 || 256 % C4) { set_error("apply_fwd: C=%d unsupported", a.out.C); return cudaErrorInvalidValue; }
-  const dim3 g = rows_grid(a.out.Y * a.out.X, 256 / C4, a.out.nImg);
   switch (a.mode) {
-    case kGatedNoNorm: apply_fwd_kernel<kGatedNoNorm><<<g, 256, 0, s>>>(a); break;
-    case kGatedIN: apply_fwd_kernel<kGatedIN><<<g, 256, 0, s>>>(a); break;
-    case kINOnly: apply_fwd_kernel<kINOnly><<<g, 256, 0, s>>>(a); break;
-    case kINSwish: apply_fwd_kernel<kINSwish><<<g, 256, 0, s>>>(a); break;
-    case kINSwishShuffle: apply_fwd_kernel<kINSwishShuffle><<<g, 256, 0, s>>>(a); break;
+    case kGatedNoNorm: run_apply_fwd<kGatedNoNorm>(a, s); break;
+    case kGatedIN: run_apply_fwd<kGatedIN>(a, s); break;
+    case kINOnly: run_apply_fwd<kINOnly>(a, s); break;
+    case kINSwish: run_apply_fwd<kINSwish>(a, s); break;
+    case kINSwishShuffle: run_apply_fwd<kINSwishShuffle>(a, s); break;
     default: set_error("apply_fwd: bad mode %d", a.mode); return cudaErrorInvalidValue;
   }
   return launched();
@@ -334,22 +410,47 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
     const int per = (P + gridDim.z - 1) / gridDim.z;
     const int pBeg = blockIdx.z * per;
     const int pEnd = pBeg + per < P ? pBeg + per : P;
-#pragma unroll 2
-    for (int p = pBeg + warp; p < pEnd; p += 8) {
-      const int y = p / a.dA.X, x = p - y * a.dA.X;
-      long long zrow;
-      int col = c;
-      if (MODE == kINSwishShuffle) {
-        zrow = ((long long)img * a.zY + (y >> 1)) * a.zX + (x >> 1);
-        col = ((((y & 1) << 1) | (x & 1)) * C) + c;
-      } else {
-        zrow = ((long long)img * a.zY + y) * a.zX + x;
+    constexpr int kL = kBwdLoads<MODE>, kD = kRingDepth<kL>;   // cp.async ring, see apply_fwd_kernel
+    const bool linear = (MODE != kINSwishShuffle) && !a.dA.parity && a.zY == a.dA.Y && a.zX == a.dA.X;
+    float4* ring = g_ring + threadIdx.x;
+    auto issue = [&](int st, int p) {
+      if (p < pEnd) {
+        const float* zr;
+        long long doff;
+        int col = c;
+        if (linear) {
+          const long long row = (long long)img * P + p;
+          zr = a.z + row * a.Nz;
+          doff = row * C + c;
+        } else {
+          const int y = p / a.dA.X, x = p - y * a.dA.X;
+          long long zrow;
+          if (MODE == kINSwishShuffle) {
+            zrow = ((long long)img * a.zY + (y >> 1)) * a.zX + (x >> 1);
+            col = ((((y & 1) << 1) | (x & 1)) * C) + c;
+          } else {
+            zrow = ((long long)img * a.zY + y) * a.zX + x;
+          }
+          zr = a.z + zrow * a.Nz;
+          doff = act_off(a.dA, img, y, x) + c;
+        }
+        cp_async16(ring + (st * kL) * 256, a.dA.f32 + doff);
+        cp_async16(ring + (st * kL + 1) * 256, zr + col);
+        if (MODE == kGatedIN) cp_async16(ring + (st * kL + 2) * 256, zr + C + c);
       }
-      const float* zr = a.z + zrow * a.Nz;
-      const float4 d = ld4(a.dA.f32 + act_off(a.dA, img, y, x) + c);
-      const float4 xh = xhat4(ld4(zr + col), na);
+      cp_async_commit();
+    };
+    int p = pBeg + warp;
+#pragma unroll
+    for (int s = 0; s < kD - 1; ++s) issue(s, p + 8 * s);
+    int st = 0;
+    for (; p < pEnd; p += 8) {
+      issue(st == 0 ? kD - 1 : st - 1, p + 8 * (kD - 1));
+      cp_async_wait<kD - 1>();
+      const float4 d = ring[(st * kL) * 256];
+      const float4 xh = xhat4(ring[(st * kL + 1) * 256], na);
       if (MODE == kGatedIN) {
-        const float4 xg = xhat4(ld4(zr + C + c), ng);
+        const float4 xg = xhat4(ring[(st * kL + 2) * 256], ng);
         const float4 ya = affine4(xh, na), yg = affine4(xg, ng);
         const float4 sg = make_float4(sigmoidf_(yg.x), sigmoidf_(yg.y), sigmoidf_(yg.z), sigmoidf_(yg.w));
         const float4 dya = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
@@ -370,7 +471,9 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
         mDy = fmaxf(mDy, amax4(dy));
         mXh = fmaxf(mXh, amax4(xh));
       }
+      if (++st == kD) st = 0;
     }
+    cp_async_wait<0>();
   }
   red[0][warp][lane] = s1a; red[1][warp][lane] = s2a;
   red[2][warp][lane] = s1g; red[3][warp][lane] = s2g;
@@ -418,15 +521,21 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
   }
 }
 
-cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
-  if (a.mode == kGatedNoNorm) return cudaSuccess;  // no normalisation: nothing to reduce
+template <int MODE>
+static void run_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
+  static int resident = 0;
+  constexpr size_t ring = (size_t)kRingDepth<kBwdLoads<MODE>> * kBwdLoads<MODE> * 256 * sizeof(float4);
   const int cg = (a.dA.C + 127) / 128;
   const int P = a.dA.Y * a.dA.X;
-  int splits = (4 * 148 + cg * a.dA.nImg - 1) / (cg * a.dA.nImg);
+  // position splits: two resident waves of CTAs, each warp with at least eight positions
+  int splits = 2 * resident_ctas(apply_bwd_reduce_kernel<MODE>, 256, ring, &resident) / (cg * a.dA.nImg);
   if (splits > P / 64) splits = P / 64;
   if (splits < 1) splits = 1;
   if (splits > 64) splits = 64;
-  dim3 grid(cg, a.dA.nImg, splits);
+  apply_bwd_reduce_kernel<MODE><<<dim3(cg, a.dA.nImg, splits), 256, ring, s>>>(a);
+}
+cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
+  if (a.mode == kGatedNoNorm) return cudaSuccess;  // no normalisation: nothing to reduce
   const size_t tbytes = (size_t)a.dA.nImg * a.Nstat * sizeof(float);
   cudaError_t e = cudaSuccess;
   if (a.prezeroed) {
@@ -439,10 +548,10 @@ cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
   }
   if (e != cudaSuccess) return e;
   switch (a.mode) {
-    case kGatedIN: apply_bwd_reduce_kernel<kGatedIN><<<grid, 256, 0, s>>>(a); break;
-    case kINOnly: apply_bwd_reduce_kernel<kINOnly><<<grid, 256, 0, s>>>(a); break;
-    case kINSwish: apply_bwd_reduce_kernel<kINSwish><<<grid, 256, 0, s>>>(a); break;
-    case kINSwishShuffle: apply_bwd_reduce_kernel<kINSwishShuffle><<<grid, 256, 0, s>>>(a); break;
+    case kGatedIN: run_apply_bwd_reduce<kGatedIN>(a, s); break;
+    case kINOnly: run_apply_bwd_reduce<kINOnly>(a, s); break;
+    case kINSwish: run_apply_bwd_reduce<kINSwish>(a, s); break;
+    case kINSwishShuffle: run_apply_bwd_reduce<kINSwishShuffle>(a, s); break;
     default: set_error("apply_bwd_reduce: bad mode %d", a.mode); return cudaErrorInvalidValue;
   }
   return launched();
@@ -526,15 +635,40 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
   }
   const float* zimg = a.z + (long long)img * zP * a.Nz;
   float4 bsa = make_float4(0.f, 0.f, 0.f, 0.f), bsg = bsa;
-  for (int p = blockIdx.x * rows + r; p < zP; p += gridDim.x * rows) {
-    const int zy = p / a.zX, zx = p - zy * a.zX;
-    int y = zy, x = zx;
-    if (MODE == kINSwishShuffle) { y = (zy << 1) | (q >> 1); x = (zx << 1) | (q & 1); }
-    const float* zr = zimg + (long long)p * a.Nz;
-    const float4 d = ld4(a.dA.f32 + act_off(a.dA, img, y, x) + c);
+  constexpr int kL = kBwdLoads<MODE>, kD = kRingDepth<kL>;   // cp.async ring, see apply_fwd_kernel
+  const bool linear = (MODE != kINSwishShuffle) && !a.dA.parity;
+  const int step = gridDim.x * rows;
+  float4* ring = g_ring + threadIdx.x;
+  auto issue = [&](int st, int p) {
+    if (p < zP) {
+      long long doff;
+      if (linear) {
+        doff = ((long long)img * zP + p) * C + c;
+      } else {
+        const int zy = p / a.zX, zx = p - zy * a.zX;
+        int y = zy, x = zx;
+        if (MODE == kINSwishShuffle) { y = (zy << 1) | (q >> 1); x = (zx << 1) | (q & 1); }
+        doff = act_off(a.dA, img, y, x) + c;
+      }
+      const float* zr = zimg + (long long)p * a.Nz;
+      cp_async16(ring + (st * kL) * 256, a.dA.f32 + doff);
+      cp_async16(ring + (st * kL + 1) * 256, zr + col);
+      if (kGated) cp_async16(ring + (st * kL + 2) * 256, zr + C + col);
+    }
+    cp_async_commit();
+  };
+  int p = blockIdx.x * rows + r;
+#pragma unroll
+  for (int s = 0; s < kD - 1; ++s) issue(s, p + s * step);
+  int st = 0;
+  for (; p < zP; p += step) {
+    issue(st == 0 ? kD - 1 : st - 1, p + (kD - 1) * step);
+    cp_async_wait<kD - 1>();
+    const float4 d = ring[(st * kL) * 256];
+    const float4 zv = ring[(st * kL + 1) * 256];
     const long long orow = ((long long)img * zP + p) * a.Nz;
     if (MODE == kGatedNoNorm) {
-      const float4 va = ld4(zr + col), vg = ld4(zr + C + col);
+      const float4 va = zv, vg = ring[(st * kL + 2) * 256];
       const float4 sg = make_float4(sigmoidf_(vg.x), sigmoidf_(vg.y), sigmoidf_(vg.z), sigmoidf_(vg.w));
       const float4 dza = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
       const float4 dzg = make_float4(d.x * va.x * sg.x * (1.f - sg.x), d.y * va.y * sg.y * (1.f - sg.y),
@@ -543,7 +677,7 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
       store_planes(a.dz_hi, a.dz_lo, dzf, orow + C + col, dzg);
       acc4(bsa, dza); acc4(bsg, dzg);
     } else if (MODE == kGatedIN) {
-      const float4 xa = xhat_b(ld4(zr + col), ka), xg = xhat_b(ld4(zr + C + col), kg);
+      const float4 xa = xhat_b(zv, ka), xg = xhat_b(ring[(st * kL + 2) * 256], kg);
       const float4 ya = affine_b(xa, ka), yg = affine_b(xg, kg);
       const float4 sg = make_float4(sigmoidf_(yg.x), sigmoidf_(yg.y), sigmoidf_(yg.z), sigmoidf_(yg.w));
       const float4 dya = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
@@ -554,7 +688,7 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
       store_planes(a.dz_hi, a.dz_lo, dzf, orow + C + col, dzg);
       acc4(bsa, dza); acc4(bsg, dzg);
     } else {
-      const float4 xh = xhat_b(ld4(zr + col), ka);
+      const float4 xh = xhat_b(zv, ka);
       float4 dy = d;
       if (MODE != kINOnly) {
         const float4 g = swish_grad4(affine_b(xh, ka));
@@ -564,13 +698,23 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
       store_planes(a.dz_hi, a.dz_lo, dzf, orow + col, dz);
       acc4(bsa, dz);
     }
+    if (++st == kD) st = 0;
   }
+  cp_async_wait<0>();
   if (a.dbias) {
     bias_reduce(bsa, G4, a.dbias + col);
     if (kGated) bias_reduce(bsg, G4, a.dbias + C + col);
   }
 }
 
+template <int MODE>
+static void run_apply_bwd(const ApplyBwdArgs& a, int G4, cudaStream_t s) {
+  static int resident = 0;
+  constexpr size_t ring = (size_t)kRingDepth<kBwdLoads<MODE>> * kBwdLoads<MODE> * 256 * sizeof(float4);
+  const dim3 g = rows_grid(a.zY * a.zX, 256 / G4, 4, a.dA.nImg,
+                           resident_ctas(apply_bwd_kernel<MODE>, 256, ring, &resident));
+  apply_bwd_kernel<MODE><<<g, 256, ring, s>>>(a);
+}
 cudaError_t launch_apply_bwd(const ApplyBwdArgs& a, cudaStream_t s) {
   const bool gated = a.mode == kGatedIN || a.mode == kGatedNoNorm;
   const int G4 = (gated ? a.dA.C : a.Nz) >> 2;
@@ -580,13 +724,12 @@ cudaError_t launch_apply_bwd(const ApplyBwdArgs& a, cudaStream_t s) {
     set_error("apply_bwd: Nz=%d too wide; pass it as more images of <= 1024 columns", a.Nz);
     return cudaErrorInvalidValue;
   }
-  const dim3 g = rows_grid(a.zY * a.zX, 256 / G4, a.dA.nImg);
   switch (a.mode) {
-    case kGatedNoNorm: apply_bwd_kernel<kGatedNoNorm><<<g, 256, 0, s>>>(a); break;
-    case kGatedIN: apply_bwd_kernel<kGatedIN><<<g, 256, 0, s>>>(a); break;
-    case kINOnly: apply_bwd_kernel<kINOnly><<<g, 256, 0, s>>>(a); break;
-    case kINSwish: apply_bwd_kernel<kINSwish><<<g, 256, 0, s>>>(a); break;
-    case kINSwishShuffle: apply_bwd_kernel<kINSwishShuffle><<<g, 256, 0, s>>>(a); break;
+    case kGatedNoNorm: run_apply_bwd<kGatedNoNorm>(a, G4, s); break;
+    case kGatedIN: run_apply_bwd<kGatedIN>(a, G4, s); break;
+    case kINOnly: run_apply_bwd<kINOnly>(a, G4, s); break;
+    case kINSwish: run_apply_bwd<kINSwish>(a, G4, s); break;
+    case kINSwishShuffle: run_apply_bwd<kINSwishShuffle>(a, G4, s); break;
     default: set_error("apply_bwd: bad mode %d", a.mode); return cudaErrorInvalidValue;
   }
   return launched();
@@ -812,67 +955,127 @@ cudaError_t launch_d_stem_bwd(const float* x, int B, int T, const __nv_bfloat16*
 // Heads.  The 128->1 5x15 conv (model.py:207-211) runs as a 1-tap GEMM P[pos, t] = sum_c u[pos,c] *
 // W[t][c] over the 75 taps t (padded to 128 columns) followed by this shifted sum:
 //   out[b,h,w] = bias + sum_{kh,kw} P[(b, h+kh-2, w+kw-7), kh*15+kw]
-__global__ void head_g_fwd_kernel(const float* __restrict__ P, const float* __restrict__ bias,
-                                  int B, int Y, int X, float* __restrict__ out) {
-  const int total = B * Y * X;               // launcher guarantees < 2^31
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int x = idx % X;
-    const int by = idx / X;
-    const int y = by % Y;
-    const long long b = by / Y;
-    float acc = bias[0];
-    for (int kh = 0; kh < 5; ++kh) {
-      const int ys = y + kh - 2;
-      if (ys < 0 || ys >= Y) continue;
-      for (int kw = 0; kw < 15; ++kw) {
-        const int xs = x + kw - 7;
-        if (xs < 0 || xs >= X) continue;
-        acc += P[((b * Y + ys) * X + xs) * 128 + kh * 15 + kw];
+// One CTA per (image, band of Yt output rows, 64-column segment).  It walks the source lines
+// ys = y0-2 .. y0+Yt+1 once: a line's 78 x 76 partial products are staged in shared memory with
+// coalesced 16-byte loads (the next line is prefetched into registers meanwhile), four threads per
+// output column add up its 15 horizontal taps for each of the 5 vertical taps, and a five-register
+// rolling window per column collects the rows ys+2 .. ys-2 those belong to; row ys-2 is complete
+// after line ys.  (The first version gathered 75 scalars per output straight from HBM rows: a
+// quarter of the HBM rate.)
+constexpr int kHeadSeg = 64, kHeadRows = kHeadSeg + 14, kHeadLd = 77, kHeadVec = 19;   // 19 float4 = 76 columns
+__global__ void __launch_bounds__(256) head_g_fwd_kernel(const float* __restrict__ P, const float* __restrict__ bias,
+                                                         int Y, int X, int Yt, float* __restrict__ out) {
+  __shared__ float S[kHeadRows * kHeadLd];
+  const int x0 = blockIdx.x * kHeadSeg, y0 = blockIdx.y * Yt;
+  const long long b = blockIdx.z;
+  const int tid = threadIdx.x, xl = tid >> 2, j = tid & 3;   // column x0+xl; horizontal taps j, j+4, j+8, j+12
+  constexpr int kFetch = (kHeadRows * kHeadVec + 255) / 256;
+  float4 pre[kFetch];
+  auto fetch = [&](int ys) {
+#pragma unroll
+    for (int i = 0; i < kFetch; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx / kHeadVec, q = idx - r * kHeadVec, xs = x0 - 7 + r;
+      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < kHeadRows && ys >= 0 && ys < Y && xs >= 0 && xs < X)
+        pre[i] = ld4(P + ((b * Y + ys) * X + xs) * 128 + q * 4);
+    }
+  };
+  const int yEnd = (y0 + Yt < Y) ? y0 + Yt : Y;   // band = rows [y0, yEnd)
+  const float bv = bias[0];
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;   // wk: running sum of output row ys - k + 2
+  fetch(y0 - 2);
+  for (int ys = y0 - 2; ys < yEnd + 2; ++ys) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kFetch; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx / kHeadVec, q = idx - r * kHeadVec;
+      if (r < kHeadRows) {
+        float* d = S + r * kHeadLd + q * 4;
+        d[0] = pre[i].x; d[1] = pre[i].y; d[2] = pre[i].z; d[3] = pre[i].w;
       }
     }
-    out[idx] = acc;
+    __syncthreads();
+    if (ys + 1 < yEnd + 2) fetch(ys + 1);
+    float part[5];
+#pragma unroll
+    for (int kh = 0; kh < 5; ++kh) {
+      float s = 0.f;
+#pragma unroll
+      for (int kw = j; kw < 15; kw += 4) s += S[(xl + kw) * kHeadLd + kh * 15 + kw];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      part[kh] = s;
+    }
+    w0 += part[0]; w1 += part[1]; w2 += part[2]; w3 += part[3]; w4 += part[4];
+    const int y = ys - 2;                          // complete after this line
+    if (j == 0 && y >= y0 && y < yEnd && x0 + xl < X) out[(b * Y + y) * X + x0 + xl] = w4 + bv;
+    w4 = w3; w3 = w2; w2 = w1; w1 = w0; w0 = 0.f;
   }
 }
 cudaError_t launch_head_g_fwd(const float* P, const float* bias, int B, int Y, int X, float* out,
                               cudaStream_t s) {
-  head_g_fwd_kernel<<<grid_for((long long)B * Y * X, 128), 128, 0, s>>>(P, bias, B, Y, X, out);
+  const int segs = (X + kHeadSeg - 1) / kHeadSeg;
+  int Yt = 16;                                     // halo re-reads (Yt+4)/Yt vs enough CTAs for two per SM
+  while (Yt > 4 && (long long)B * segs * ((Y + Yt - 1) / Yt) < 296) Yt >>= 1;
+  if (B > 65535) { set_error("head_g_fwd: batch %d too large", B); return cudaErrorInvalidValue; }
+  head_g_fwd_kernel<<<dim3(segs, (Y + Yt - 1) / Yt, B), 256, 0, s>>>(P, bias, Y, X, Yt, out);
   return launched();
 }
 
 // dP[(b,y',x'), t=(kh,kw)] = dout[b, y'-kh+2, x'-kw+7]; columns >= 75 are zero.  dbias += sum dout.
-__global__ void head_g_bwd_kernel(const float* __restrict__ dout, int B, int Y, int X,
-                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                  float* __restrict__ dbias) {
-  const long long total = (long long)B * Y * X * 32;
+// A warp walks a 32-position segment of one row: the lane's four taps (fixed for the whole kernel)
+// and the row's source rows are resolved once per segment, so the inner loop is four predicated
+// loads and one split store per position (the per-element tap/row divisions made the first version
+// issue-bound: 80 % issue-slot utilisation at a third of the HBM store rate).
+__global__ void __launch_bounds__(256) head_g_bwd_kernel(const float* __restrict__ dout, int B, int Y, int X,
+                                                         __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo,
+                                                         float* __restrict__ dbias) {
+  const int lane = threadIdx.x & 31, t4 = lane << 2;
+  int oy[4], ox[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t4 + i, kh = t / 15;
+    oy[i] = (t < 75) ? 2 - kh : -(1 << 20);     // padded columns: never a valid source row
+    ox[i] = 7 - (t - kh * 15);
+  }
+  const int segs = (X + 31) >> 5;
+  const int items = B * Y * segs;                // launcher guarantees B*Y*X < 2^31
   float bacc = 0.f;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int t4 = (int)(idx & 31) << 2;
-    const int pos = (int)(idx >> 5);           // launcher guarantees B*Y*X < 2^31
-    const int x = pos % X;
-    const int by = pos / X;
-    const int y = by % Y;
-    const long long b = by / Y;
-    float v[4];
+  for (int it = blockIdx.x * 8 + (threadIdx.x >> 5); it < items; it += gridDim.x * 8) {
+    const int seg = it % segs, by = it / segs, y = by % Y;
+    const float* dimg = dout + (long long)(by - y) * X;
+    const float* rp[4];
+    bool rv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int t = t4 + i;
-      const int kh = t / 15, kw = t - kh * 15;
-      const int ys = y - kh + 2, xs = x - kw + 7;
-      v[i] = (t < 75 && ys >= 0 && ys < Y && xs >= 0 && xs < X) ? dout[(b * Y + ys) * X + xs] : 0.f;
+      const int ys = y + oy[i];
+      rv[i] = ys >= 0 && ys < Y;
+      rp[i] = dimg + (long long)(rv[i] ? ys : 0) * X + ox[i];
     }
-    split_store4(hi, lo, (long long)pos * 128 + t4, make_float4(v[0], v[1], v[2], v[3]));
-    if (t4 == 0) bacc += dout[pos];
+    const int x0 = seg << 5, x1 = (x0 + 32 < X) ? x0 + 32 : X;
+    long long off = ((long long)by * X + x0) * 128 + t4;
+#pragma unroll 4
+    for (int x = x0; x < x1; ++x, off += 128) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        v[i] = (rv[i] && (unsigned)(x + ox[i]) < (unsigned)X) ? rp[i][x] : 0.f;
+      split_store4(hi, lo, off, make_float4(v[0], v[1], v[2], v[3]));
+    }
+    if (x0 + lane < x1) bacc += dimg[y * X + x0 + lane];
   }
   if (dbias) {
     for (int o = 16; o > 0; o >>= 1) bacc += __shfl_xor_sync(0xffffffffu, bacc, o);
-    if ((threadIdx.x & 31) == 0 && bacc != 0.f) atomicAdd(dbias, bacc);
+    if (lane == 0 && bacc != 0.f) atomicAdd(dbias, bacc);
   }
 }
 cudaError_t launch_head_g_bwd(const float* dout, int B, int Y, int X, __nv_bfloat16* hi,
                               __nv_bfloat16* lo, float* dbias, cudaStream_t s) {
-  head_g_bwd_kernel<<<grid_for((long long)B * Y * X * 32, 256), 256, 0, s>>>(dout, B, Y, X, hi, lo,
-                                                                           dbias);
+  const long long items = (long long)B * Y * ((X + 31) >> 5);
+  head_g_bwd_kernel<<<grid_for(items * 32, 256), 256, 0, s>>>(dout, B, Y, X, hi, lo, dbias);
   return launched();
 }
 

@@ -18,7 +18,8 @@ PRECISION_FAST = 1     # single bf16 pass
 PRECISION_C8 = 4       # DEFAULT: fp16 main pass + two e4m3 correction passes (2 MMA units per MAC); meets the 1e-3 gate
 PRECISION_C8H = 5      # forward as C8; backward GEMMs of the C8 layers: one fp16 pass (TF32-class gradients)
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcgvc.so")
+# MCGVC_LIBRARY: another build of the same library (A/B timing of two builds in one gpurun call)
+_LIB_PATH = os.environ.get("MCGVC_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcgvc.so")
 _lib = None
 
 _c_ll = ctypes.c_longlong
