@@ -794,36 +794,57 @@ __device__ __forceinline__ StemW load_stem_w(const __nv_bfloat16* __restrict__ w
   }
   return r;
 }
-// One warp walks one (b, h) row left to right with a sliding 3x3 window (3 new loads per step, no
-// per-position index divisions); the parity-split store alternates between the row's two planes.
-struct RowWindow {
-  const float* r[3];   // rows h-1, h, h+1 of the input (null when outside the 80 mel bins)
-  float v[9];
-  int T;
-  __device__ __forceinline__ void init(const float* x, int b, int h, int T_) {
-    T = T_;
+// Work item of the stem kernels: a 32-column segment of one (b, h) row, walked left to right by one
+// warp with a sliding 3x3 window.  Lane l holds column w0+l of the three input rows (plus the two
+// halo columns), so the window advances with three shuffles per step -- no load sits on the
+// per-step dependency chain (the first version re-loaded x every step and ran at a quarter of its
+// issue rate).  Warps stride over the items of a resident-sized grid.
+struct StemItem {
+  int w0, n;                // first column, columns in this segment
+  long long base;           // element offset of (b, h, x = 0, c = lane*4) in the parity-split buffer
+  float cur[3], hl[3], hr[3];
+  __device__ __forceinline__ void locate(const ActBuf& a, int it, int segs, int T, int lane) {
+    const int row = it / segs;
+    w0 = (it - row * segs) << 5;
+    n = (T - w0 < 32) ? T - w0 : 32;
+    const int b = row / 80, h = row - b * 80;
+    base = act_off(a, b, h, 0) + lane * 4;
+  }
+  __device__ __forceinline__ void load_rows(const float* __restrict__ x, int it, int segs, int T, int lane) {
+    const int row = it / segs, b = row / 80, h = row - b * 80;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int hs = h + k - 1;
-      r[k] = (hs >= 0 && hs < 80) ? x + ((long long)b * 80 + hs) * T : nullptr;
-      v[k * 3 + 0] = 0.f;                                   // column w-1 = -1
-      v[k * 3 + 1] = 0.f;                                   // filled by the first advance()
-      v[k * 3 + 2] = r[k] ? __ldg(r[k]) : 0.f;              // column 0
+      cur[k] = hl[k] = hr[k] = 0.f;
+      if (hs >= 0 && hs < 80) {
+        const float* r = x + ((long long)b * 80 + hs) * T;
+        if (w0 + lane < T) cur[k] = __ldg(r + w0 + lane);
+        if (w0 > 0) hl[k] = __ldg(r + w0 - 1);
+        if (w0 + 32 < T) hr[k] = __ldg(r + w0 + 32);
+      }
     }
   }
-  // move the window so that its centre column is w (call with w = 0, 1, 2, ...)
-  __device__ __forceinline__ void advance(int w) {
+  // window columns (w-1, w, w+1) for step j = w - w0, given the previous step's window
+  __device__ __forceinline__ void start(float* v) const {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
+      v[k * 3 + 1] = hl[k];
+      v[k * 3 + 2] = __shfl_sync(0xffffffffu, cur[k], 0);
+    }
+  }
+  __device__ __forceinline__ void advance(float* v, int j) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float nx = __shfl_sync(0xffffffffu, cur[k], (j + 1) & 31);
       v[k * 3 + 0] = v[k * 3 + 1];
       v[k * 3 + 1] = v[k * 3 + 2];
-      v[k * 3 + 2] = (r[k] && w + 1 < T) ? __ldg(r[k] + w + 1) : 0.f;
+      v[k * 3 + 2] = (j + 1 < 32) ? nx : hr[k];
     }
   }
 };
-__device__ __forceinline__ long long row_plane_base(const ActBuf& a, int b, int h, int pw) {
-  // offset of element (b, h, x = pw, c = 0); consecutive same-parity x are a.C apart
-  return act_off(a, b, h, pw);
+// offset between the x-even and x-odd planes of one row of a parity-split buffer
+__device__ __forceinline__ long long odd_plane_offset(const ActBuf& a) {
+  return (long long)((a.Y + 1) >> 1) * ((a.X + 1) >> 1) * a.C;
 }
 
 __global__ void __launch_bounds__(256) d_stem_fwd_kernel(const float* __restrict__ x, int B, int T,
@@ -834,24 +855,26 @@ __global__ void __launch_bounds__(256) d_stem_fwd_kernel(const float* __restrict
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const StemW sw = load_stem_w(wh, wl, bias, lane);
-  const int rows = B * 80;
-  for (int row = warp; row < rows; row += nwarps) {
-    const int b = row / 80, h = row - b * 80;
-    RowWindow win;
-    win.init(x, b, h, T);
-    const long long base0 = row_plane_base(out, b, h, 0) + lane * 4;
-    const long long base1 = T > 1 ? row_plane_base(out, b, h, 1) + lane * 4 : base0;
-    for (int w = 0; w < T; ++w) {
-      win.advance(w);
+  const int segs = (T + 31) >> 5, items = B * 80 * segs;
+  const long long odd = odd_plane_offset(out);
+  for (int it = warp; it < items; it += nwarps) {
+    StemItem m;
+    m.locate(out, it, segs, T, lane);
+    m.load_rows(x, it, segs, T, lane);
+    float v[9];
+    m.start(v);
+    for (int j = 0; j < m.n; ++j) {
+      m.advance(v, j);
       float z[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float acc = sw.b[c];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], win.v[t], acc);
+        for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], v[t], acc);
         z[c] = acc * sigmoidf_(acc);
       }
-      const long long off = ((w & 1) ? base1 : base0) + (long long)(w >> 1) * out.C;
+      const int w = m.w0 + j;
+      const long long off = m.base + ((w & 1) ? odd : 0) + (long long)(w >> 1) * out.C;
       store_planes(out.hi, out.lo, out.fmt, off, make_float4(z[0], z[1], z[2], z[3]));
     }
   }
@@ -859,18 +882,27 @@ __global__ void __launch_bounds__(256) d_stem_fwd_kernel(const float* __restrict
 cudaError_t launch_d_stem_fwd(const float* x, int B, int T, const __nv_bfloat16* wh,
                               const __nv_bfloat16* wl, const float* bias, ActBuf out, cudaStream_t s) {
   if (!out.parity) { set_error("d_stem_fwd: expects a parity-split output"); return cudaErrorInvalidValue; }
-  const int rows = B * 80;
-  int blocks = (rows + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  d_stem_fwd_kernel<<<blocks, 256, 0, s>>>(x, B, T, wh, wl, bias, out);
+  static int resident = 0;
+  const long long items = (long long)B * 80 * ((T + 31) >> 5);
+  long long blocks = (items + 7) / 8;
+  const int cap = resident_ctas(d_stem_fwd_kernel, 256, 0, &resident);
+  if (blocks > cap) blocks = cap;
+  d_stem_fwd_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, B, T, wh, wl, bias, out);
   return launched();
 }
 
 // Backward of the stem: recompute z from x (9 MACs), dz = dA * swish'(z); weight / bias gradients
 // accumulate per lane, merge in shared memory and go to the engine-layout gradient blob
 // (dW[n][tap] at n*64 + tap); when the input needs a gradient, q[pos][tap] = sum_n dz[n] * w[n][tap]
-// is written for the 3x3 fold below.
-__global__ void __launch_bounds__(256) d_stem_bwd_kernel(const float* __restrict__ x, int B, int T,
+// is written for the 3x3 fold below.  The dA loads run kStemRing-1 steps ahead of the math through
+// a per-lane cp.async ring (see apply_fwd_kernel) whose cursor crosses item boundaries.
+constexpr int kStemRing = 8;
+struct StemCursor {   // (item, step) iterator of one warp, used once for the loads and once for the math
+  int it, j;
+  StemItem m;
+};
+template <bool kQ>
+__global__ void __launch_bounds__(256, 2) d_stem_bwd_kernel(const float* __restrict__ x, int B, int T,
                                                          const __nv_bfloat16* __restrict__ wh,
                                                          const __nv_bfloat16* __restrict__ wl,
                                                          const float* __restrict__ bias, ActBuf dA,
@@ -890,40 +922,96 @@ __global__ void __launch_bounds__(256) d_stem_bwd_kernel(const float* __restrict
 #pragma unroll
     for (int t = 0; t < 9; ++t) gw[c][t] = 0.f;
   }
-  const int rows = B * 80;
-  for (int row = warp; row < rows; row += nwarps) {
-    const int b = row / 80, h = row - b * 80;
-    RowWindow win;
-    win.init(x, b, h, T);
-    const long long base0 = row_plane_base(dA, b, h, 0) + lane * 4;
-    const long long base1 = T > 1 ? row_plane_base(dA, b, h, 1) + lane * 4 : base0;
-    for (int w = 0; w < T; ++w) {
-      win.advance(w);
-      const float4 d4 = ld4(dA.f32 + ((w & 1) ? base1 : base0) + (long long)(w >> 1) * dA.C);
+  const int segs = (T + 31) >> 5, items = B * 80 * segs;
+  const long long odd = odd_plane_offset(dA);
+  float4* ring = g_ring + threadIdx.x;
+  // load cursor: issues one step's 16 bytes per call, walking items ahead of the math
+  int lit = warp, lj = 0, ln = 0, lw0 = 0;
+  long long lbase = 0;
+  auto load_locate = [&]() {
+    if (lit < items) {
+      const int row = lit / segs;
+      lw0 = (lit - row * segs) << 5;
+      ln = (T - lw0 < 32) ? T - lw0 : 32;
+      const int b = row / 80, h = row - b * 80;
+      lbase = act_off(dA, b, h, 0) + lane * 4;
+    }
+  };
+  auto issue = [&](int st) {
+    if (lit < items) {
+      const int w = lw0 + lj;
+      cp_async16(ring + st * 256, dA.f32 + lbase + ((w & 1) ? odd : 0) + (long long)(w >> 1) * dA.C);
+      if (++lj == ln) { lit += nwarps; lj = 0; load_locate(); }
+    }
+    cp_async_commit();
+  };
+  load_locate();
+#pragma unroll
+  for (int s = 0; s < kStemRing - 1; ++s) issue(s);
+  int st = 0;
+  for (int it = warp; it < items; it += nwarps) {
+    StemItem m;
+    m.locate(dA, it, segs, T, lane);
+    m.load_rows(x, it, segs, T, lane);
+    float v[9];
+    m.start(v);
+    for (int j = 0; j < m.n; ++j) {
+      issue(st == 0 ? kStemRing - 1 : st - 1);
+      cp_async_wait<kStemRing - 1>();
+      const float4 d4 = ring[st * 256];
+      if (++st == kStemRing) st = 0;
+      m.advance(v, j);
       const float d[4] = {d4.x, d4.y, d4.z, d4.w};
       float dz[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float acc = sw.b[c];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], win.v[t], acc);
+        for (int t = 0; t < 9; ++t) acc = fmaf(sw.w[c][t], v[t], acc);
         dz[c] = d[c] * swish_grad(acc);
         gb[c] += dz[c];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) gw[c][t] = fmaf(dz[c], win.v[t], gw[c][t]);
+        for (int t = 0; t < 9; ++t) gw[c][t] = fmaf(dz[c], v[t], gw[c][t]);
       }
-      if (q) {
-        const long long pos = (long long)row * T + w;
+      if (kQ) {
+        // q[pos][t] = sum over the warp's 128 channels: 9 per-lane partials, recursive-halving
+        // reduction (taps 0..7: 4+2+1 exchanges leave tap (lane>>2)&7 in each lane, two more sum the
+        // lane quad; tap 8: plain butterfly) -- 14 shuffles instead of 45
+        float p[9];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          float p = dz[0] * sw.w[0][t] + dz[1] * sw.w[1][t] + dz[2] * sw.w[2][t] + dz[3] * sw.w[3][t];
+        for (int t = 0; t < 9; ++t)
+          p[t] = dz[0] * sw.w[0][t] + dz[1] * sw.w[1][t] + dz[2] * sw.w[2][t] + dz[3] * sw.w[3][t];
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        float r4[4], r2[2], r1;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-          if (lane == t) q[pos * 12 + t] = p;
+        for (int i = 0; i < 4; ++i) {           // keep taps {0..3} (bit4 = 0) or {4..7} (bit4 = 1)
+          const float give = b4 ? p[i] : p[i + 4];
+          const float got = __shfl_xor_sync(0xffffffffu, give, 16);
+          r4[i] = (b4 ? p[i + 4] : p[i]) + got;
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float give = b3 ? r4[i] : r4[i + 2];
+          const float got = __shfl_xor_sync(0xffffffffu, give, 8);
+          r2[i] = (b3 ? r4[i + 2] : r4[i]) + got;
+        }
+        {
+          const float give = b2 ? r2[0] : r2[1];
+          const float got = __shfl_xor_sync(0xffffffffu, give, 4);
+          r1 = (b2 ? r2[1] : r2[0]) + got;
+        }
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+        float p8 = p[8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p8 += __shfl_xor_sync(0xffffffffu, p8, o);
+        const long long pos = ((long long)(it / segs)) * T + m.w0 + j;
+        if ((lane & 3) == 0) q[pos * 12 + (lane >> 2)] = r1;   // tap = bit4*4 + bit3*2 + bit2
+        if (lane == 1) q[pos * 12 + 8] = p8;
       }
     }
   }
+  cp_async_wait<0>();
   if (dW) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -944,10 +1032,15 @@ cudaError_t launch_d_stem_bwd(const float* x, int B, int T, const __nv_bfloat16*
                               const __nv_bfloat16* wl, const float* bias, ActBuf dA, float* dW,
                               float* dB, float* q, cudaStream_t s) {
   if (!dA.parity) { set_error("d_stem_bwd: expects a parity-split gradient"); return cudaErrorInvalidValue; }
-  const int rows = B * 80;
-  int blocks = (rows + 7) / 8;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  d_stem_bwd_kernel<<<blocks, 256, 0, s>>>(x, B, T, wh, wl, bias, dA, dW, dB, q);
+  static int residentQ = 0, residentW = 0;
+  constexpr size_t ring = (size_t)kStemRing * 256 * sizeof(float4);
+  const long long items = (long long)B * 80 * ((T + 31) >> 5);
+  long long blocks = (items + 7) / 8;
+  const int cap = q ? resident_ctas(d_stem_bwd_kernel<true>, 256, ring, &residentQ)
+                    : resident_ctas(d_stem_bwd_kernel<false>, 256, ring, &residentW);
+  if (blocks > cap) blocks = cap;
+  if (q) d_stem_bwd_kernel<true><<<(unsigned)blocks, 256, ring, s>>>(x, B, T, wh, wl, bias, dA, dW, dB, q);
+  else d_stem_bwd_kernel<false><<<(unsigned)blocks, 256, ring, s>>>(x, B, T, wh, wl, bias, dA, dW, dB, q);
   return launched();
 }
 
