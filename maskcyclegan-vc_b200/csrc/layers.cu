@@ -252,6 +252,38 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Index helpers of the position loops.  After the rings removed the load latency these kernels
+// became issue-bound (75-80 % issue-slot utilisation, profiles/r02_ncu_layers_summary.md), most of it
+// integer work: a division per position for (y, x) and 64-bit offset chains.  PosWalk steps
+// (p, y, x) by a constant stride with one compare, ActIdx keeps the image base in the pointer and
+// the in-image offset in 32 bits (launchers check that one image stays below 2^31 elements).
+struct PosWalk {
+  int p, y, x;
+  __device__ __forceinline__ void init(int p0, int X) { p = p0; y = p0 / X; x = p0 - y * X; }
+  __device__ __forceinline__ void next(int step, int dy, int dx, int X) {
+    p += step; y += dy; x += dx;
+    if (x >= X) { x -= X; ++y; }
+  }
+};
+struct ActIdx {
+  int X, C, Yp, Xp, parity;
+  __device__ __forceinline__ ActIdx(const ActBuf& a)
+      : X(a.X), C(a.C), Yp((a.Y + 1) >> 1), Xp((a.X + 1) >> 1), parity(a.parity) {}
+  __device__ __forceinline__ long long image(const ActBuf& a, int img) const {
+    return parity ? (long long)img * 4 * Yp * Xp * C : (long long)img * a.Y * X * C;
+  }
+  __device__ __forceinline__ unsigned at(int y, int x) const {
+    if (!parity) return (unsigned)(y * X + x) * C;
+    const int pl = ((y & 1) << 1) | (x & 1);
+    return (unsigned)((pl * Yp + (y >> 1)) * Xp + (x >> 1)) * C;
+  }
+};
+
+static bool image_fits_32bit(long long elems) { return elems > 0 && elems < (1LL << 31); }
+static long long act_image_elems(const ActBuf& a) {
+  return a.parity ? 4LL * ((a.Y + 1) >> 1) * ((a.X + 1) >> 1) * a.C : (long long)a.Y * a.X * a.C;
+}
+
 // 16-byte loads per position and ring depth per mode (ring bytes per CTA = depth * loads * 4 KB)
 template <int MODE>
 constexpr int kFwdLoads = (MODE == kGatedIN || MODE == kGatedNoNorm || MODE == kINOnly) ? 2 : 1;
@@ -276,40 +308,36 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const ApplyArgs a) {
     ka = load_scale_shift(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, c);
     if (MODE == kGatedIN) kg = load_scale_shift(a.mean, a.rstd, a.gamma, a.beta, img, a.Nstat, a.affPeriod, C + c);
   }
-  const float* zimg = a.z + (long long)img * a.zY * a.zX * a.Nz;
-  const float* rimg = (MODE == kINOnly && a.residual) ? a.residual + (long long)img * P * C : nullptr;
-  const int step = gridDim.x * rows;
+  const float* zimg = a.z + (long long)img * a.zY * a.zX * a.Nz + c;
+  const float* rimg = (MODE == kINOnly && a.residual) ? a.residual + (long long)img * P * C + c : nullptr;
+  const ActIdx oi(a.out);
+  const long long obase = oi.image(a.out, img) + c;
+  const int step = gridDim.x * rows, dy = step / X, dx = step - dy * X;
   float4* ring = g_ring + threadIdx.x;
-  auto issue = [&](int st, int p) {
-    if (p < P) {
-      const float* zr;
-      if (MODE == kINSwishShuffle) {
-        const int y = p / X, x = p - y * X;
-        zr = zimg + ((long long)(y >> 1) * a.zX + (x >> 1)) * a.Nz + ((((y & 1) << 1) | (x & 1)) * C) + c;
-      } else {
-        zr = zimg + (long long)p * a.Nz + c;
-      }
-      cp_async16(ring + (st * kL) * 256, zr);
-      if (kGated) cp_async16(ring + (st * kL + 1) * 256, zr + C);
-      if (MODE == kINOnly && rimg) cp_async16(ring + (st * kL + 1) * 256, rimg + (long long)p * C + c);
+  auto issue = [&](int st, const PosWalk& w) {
+    if (w.p < P) {
+      unsigned zo;
+      if (MODE == kINSwishShuffle)
+        zo = (unsigned)((w.y >> 1) * a.zX + (w.x >> 1)) * a.Nz + ((((w.y & 1) << 1) | (w.x & 1)) * C);
+      else
+        zo = (unsigned)w.p * a.Nz;
+      cp_async16(ring + (st * kL) * 256, zimg + zo);
+      if (kGated) cp_async16(ring + (st * kL + 1) * 256, zimg + zo + C);
+      if (MODE == kINOnly && rimg) cp_async16(ring + (st * kL + 1) * 256, rimg + (unsigned)w.p * C);
     }
     cp_async_commit();
   };
-  int p = blockIdx.x * rows + r;
+  PosWalk ld, cs;                                // load walker (kD-1 positions ahead) and consumer
+  cs.init(blockIdx.x * rows + r, X);
+  ld = cs;
 #pragma unroll
-  for (int s = 0; s < kD - 1; ++s) issue(s, p + s * step);
+  for (int s = 0; s < kD - 1; ++s) { issue(s, ld); ld.next(step, dy, dx, X); }
   int st = 0;
-  for (; p < P; p += step) {
-    issue(st == 0 ? kD - 1 : st - 1, p + (kD - 1) * step);
+  for (; cs.p < P; cs.next(step, dy, dx, X)) {
+    issue(st == 0 ? kD - 1 : st - 1, ld);
+    ld.next(step, dy, dx, X);
     cp_async_wait<kD - 1>();
     const float4 v = ring[(st * kL) * 256];
-    long long off;
-    if (MODE != kINSwishShuffle && !a.out.parity) {
-      off = ((long long)img * P + p) * C + c;
-    } else {
-      const int y = p / X, x = p - y * X;
-      off = act_off(a.out, img, y, x) + c;
-    }
     float4 o;
     if (MODE == kGatedNoNorm) {
       o = gate4(v, ring[(st * kL + 1) * 256]);
@@ -324,6 +352,7 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const ApplyArgs a) {
     } else {  // kINSwish, kINSwishShuffle
       o = swish4(ss_apply(v, ka));
     }
+    const long long off = obase + oi.at(cs.y, cs.x);
     if (a.out.hi) store_planes(a.out.hi, a.out.lo, a.out.fmt, off, o);
     if (a.out.f32) *reinterpret_cast<float4*>(a.out.f32 + off) = o;
     if (++st == kD) st = 0;
@@ -353,6 +382,9 @@ static void run_apply_fwd(const ApplyArgs& a, cudaStream_t s) {
 cudaError_t launch_apply_fwd(const ApplyArgs& a, cudaStream_t s) {
   const int C4 = a.out.C >> 2;
   if (C4 < 1 || C4 > 256 || 256 % C4) { set_error("apply_fwd: C=%d unsupported", a.out.C); return cudaErrorInvalidValue; }
+  if (!image_fits_32bit((long long)a.zY * a.zX * a.Nz) || !image_fits_32bit(act_image_elems(a.out))) {
+    set_error("apply_fwd: one image exceeds 2^31 elements"); return cudaErrorInvalidValue;
+  }
   switch (a.mode) {
     case kGatedNoNorm: run_apply_fwd<kGatedNoNorm>(a, s); break;
     case kGatedIN: run_apply_fwd<kGatedIN>(a, s); break;
@@ -411,41 +443,33 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
     const int pBeg = blockIdx.z * per;
     const int pEnd = pBeg + per < P ? pBeg + per : P;
     constexpr int kL = kBwdLoads<MODE>, kD = kRingDepth<kL>;   // cp.async ring, see apply_fwd_kernel
-    const bool linear = (MODE != kINSwishShuffle) && !a.dA.parity && a.zY == a.dA.Y && a.zX == a.dA.X;
+    const int X = a.dA.X;
+    const ActIdx di(a.dA);
+    const float* dimg = a.dA.f32 + di.image(a.dA, img) + c;
+    const float* zimg = a.z + (long long)img * a.zY * a.zX * a.Nz + c;
+    const int dy = 8 / X, dx = 8 - dy * X;
     float4* ring = g_ring + threadIdx.x;
-    auto issue = [&](int st, int p) {
-      if (p < pEnd) {
-        const float* zr;
-        long long doff;
-        int col = c;
-        if (linear) {
-          const long long row = (long long)img * P + p;
-          zr = a.z + row * a.Nz;
-          doff = row * C + c;
-        } else {
-          const int y = p / a.dA.X, x = p - y * a.dA.X;
-          long long zrow;
-          if (MODE == kINSwishShuffle) {
-            zrow = ((long long)img * a.zY + (y >> 1)) * a.zX + (x >> 1);
-            col = ((((y & 1) << 1) | (x & 1)) * C) + c;
-          } else {
-            zrow = ((long long)img * a.zY + y) * a.zX + x;
-          }
-          zr = a.z + zrow * a.Nz;
-          doff = act_off(a.dA, img, y, x) + c;
-        }
-        cp_async16(ring + (st * kL) * 256, a.dA.f32 + doff);
-        cp_async16(ring + (st * kL + 1) * 256, zr + col);
-        if (MODE == kGatedIN) cp_async16(ring + (st * kL + 2) * 256, zr + C + c);
+    auto issue = [&](int st, const PosWalk& w) {
+      if (w.p < pEnd) {
+        unsigned zo;
+        if (MODE == kINSwishShuffle)
+          zo = (unsigned)((w.y >> 1) * a.zX + (w.x >> 1)) * a.Nz + ((((w.y & 1) << 1) | (w.x & 1)) * C);
+        else
+          zo = (unsigned)(w.y * a.zX + w.x) * a.Nz;
+        cp_async16(ring + (st * kL) * 256, dimg + di.at(w.y, w.x));
+        cp_async16(ring + (st * kL + 1) * 256, zimg + zo);
+        if (MODE == kGatedIN) cp_async16(ring + (st * kL + 2) * 256, zimg + zo + C);
       }
       cp_async_commit();
     };
-    int p = pBeg + warp;
+    PosWalk ld;
+    ld.init(pBeg + warp, X);
 #pragma unroll
-    for (int s = 0; s < kD - 1; ++s) issue(s, p + 8 * s);
+    for (int s = 0; s < kD - 1; ++s) { issue(s, ld); ld.next(8, dy, dx, X); }
     int st = 0;
-    for (; p < pEnd; p += 8) {
-      issue(st == 0 ? kD - 1 : st - 1, p + 8 * (kD - 1));
+    for (int p = pBeg + warp; p < pEnd; p += 8) {
+      issue(st == 0 ? kD - 1 : st - 1, ld);
+      ld.next(8, dy, dx, X);
       cp_async_wait<kD - 1>();
       const float4 d = ring[(st * kL) * 256];
       const float4 xh = xhat4(ring[(st * kL + 1) * 256], na);
@@ -536,6 +560,9 @@ static void run_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
 }
 cudaError_t launch_apply_bwd_reduce(const ApplyBwdArgs& a, cudaStream_t s) {
   if (a.mode == kGatedNoNorm) return cudaSuccess;  // no normalisation: nothing to reduce
+  if (!image_fits_32bit((long long)a.zY * a.zX * a.Nz) || !image_fits_32bit(act_image_elems(a.dA))) {
+    set_error("apply_bwd_reduce: one image exceeds 2^31 elements"); return cudaErrorInvalidValue;
+  }
   const size_t tbytes = (size_t)a.dA.nImg * a.Nstat * sizeof(float);
   cudaError_t e = cudaSuccess;
   if (a.prezeroed) {
@@ -636,45 +663,43 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
   const float* zimg = a.z + (long long)img * zP * a.Nz;
   float4 bsa = make_float4(0.f, 0.f, 0.f, 0.f), bsg = bsa;
   constexpr int kL = kBwdLoads<MODE>, kD = kRingDepth<kL>;   // cp.async ring, see apply_fwd_kernel
-  const bool linear = (MODE != kINSwishShuffle) && !a.dA.parity;
-  const int step = gridDim.x * rows;
+  const int step = gridDim.x * rows, dy = step / a.zX, dx = step - dy * a.zX;
+  const ActIdx di(a.dA);
+  const float* dimg = a.dA.f32 + di.image(a.dA, img) + c;
+  const float* zcol = zimg + col;
   float4* ring = g_ring + threadIdx.x;
-  auto issue = [&](int st, int p) {
-    if (p < zP) {
-      long long doff;
-      if (linear) {
-        doff = ((long long)img * zP + p) * C + c;
-      } else {
-        const int zy = p / a.zX, zx = p - zy * a.zX;
-        int y = zy, x = zx;
-        if (MODE == kINSwishShuffle) { y = (zy << 1) | (q >> 1); x = (zx << 1) | (q & 1); }
-        doff = act_off(a.dA, img, y, x) + c;
-      }
-      const float* zr = zimg + (long long)p * a.Nz;
-      cp_async16(ring + (st * kL) * 256, a.dA.f32 + doff);
-      cp_async16(ring + (st * kL + 1) * 256, zr + col);
-      if (kGated) cp_async16(ring + (st * kL + 2) * 256, zr + C + col);
+  auto issue = [&](int st, const PosWalk& w) {      // w walks the z rows (zy, zx)
+    if (w.p < zP) {
+      int y = w.y, x = w.x;
+      if (MODE == kINSwishShuffle) { y = (y << 1) | (q >> 1); x = (x << 1) | (q & 1); }
+      const unsigned zo = (unsigned)w.p * a.Nz;
+      cp_async16(ring + (st * kL) * 256, dimg + di.at(y, x));
+      cp_async16(ring + (st * kL + 1) * 256, zcol + zo);
+      if (kGated) cp_async16(ring + (st * kL + 2) * 256, zcol + zo + C);
     }
     cp_async_commit();
   };
-  int p = blockIdx.x * rows + r;
+  PosWalk ld;
+  ld.init(blockIdx.x * rows + r, a.zX);
 #pragma unroll
-  for (int s = 0; s < kD - 1; ++s) issue(s, p + s * step);
+  for (int s = 0; s < kD - 1; ++s) { issue(s, ld); ld.next(step, dy, dx, a.zX); }
   int st = 0;
-  for (; p < zP; p += step) {
-    issue(st == 0 ? kD - 1 : st - 1, p + (kD - 1) * step);
+  const long long obase = (long long)img * zP * a.Nz + col;
+  for (int p = blockIdx.x * rows + r; p < zP; p += step) {
+    issue(st == 0 ? kD - 1 : st - 1, ld);
+    ld.next(step, dy, dx, a.zX);
     cp_async_wait<kD - 1>();
     const float4 d = ring[(st * kL) * 256];
     const float4 zv = ring[(st * kL + 1) * 256];
-    const long long orow = ((long long)img * zP + p) * a.Nz;
+    const long long orow = obase + (unsigned)p * a.Nz;   // includes this thread's column
     if (MODE == kGatedNoNorm) {
       const float4 va = zv, vg = ring[(st * kL + 2) * 256];
       const float4 sg = make_float4(sigmoidf_(vg.x), sigmoidf_(vg.y), sigmoidf_(vg.z), sigmoidf_(vg.w));
       const float4 dza = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
       const float4 dzg = make_float4(d.x * va.x * sg.x * (1.f - sg.x), d.y * va.y * sg.y * (1.f - sg.y),
                                      d.z * va.z * sg.z * (1.f - sg.z), d.w * va.w * sg.w * (1.f - sg.w));
-      store_planes(a.dz_hi, a.dz_lo, dzf, orow + col, dza);
-      store_planes(a.dz_hi, a.dz_lo, dzf, orow + C + col, dzg);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow, dza);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow + C, dzg);
       acc4(bsa, dza); acc4(bsg, dzg);
     } else if (MODE == kGatedIN) {
       const float4 xa = xhat_b(zv, ka), xg = xhat_b(ring[(st * kL + 2) * 256], kg);
@@ -684,8 +709,8 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
       const float4 dyg = make_float4(d.x * ya.x * sg.x * (1.f - sg.x), d.y * ya.y * sg.y * (1.f - sg.y),
                                      d.z * ya.z * sg.z * (1.f - sg.z), d.w * ya.w * sg.w * (1.f - sg.w));
       const float4 dza = in_bwd4(dya, xa, ka), dzg = in_bwd4(dyg, xg, kg);
-      store_planes(a.dz_hi, a.dz_lo, dzf, orow + col, dza);
-      store_planes(a.dz_hi, a.dz_lo, dzf, orow + C + col, dzg);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow, dza);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow + C, dzg);
       acc4(bsa, dza); acc4(bsg, dzg);
     } else {
       const float4 xh = xhat_b(zv, ka);
@@ -695,7 +720,7 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs a) {
         dy = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
       }
       const float4 dz = in_bwd4(dy, xh, ka);
-      store_planes(a.dz_hi, a.dz_lo, dzf, orow + col, dz);
+      store_planes(a.dz_hi, a.dz_lo, dzf, orow, dz);
       acc4(bsa, dz);
     }
     if (++st == kD) st = 0;
@@ -719,6 +744,9 @@ cudaError_t launch_apply_bwd(const ApplyBwdArgs& a, cudaStream_t s) {
   const bool gated = a.mode == kGatedIN || a.mode == kGatedNoNorm;
   const int G4 = (gated ? a.dA.C : a.Nz) >> 2;
   if (G4 < 1 || (G4 <= 256 && 256 % G4)) { set_error("apply_bwd: %d column groups unsupported", G4); return cudaErrorInvalidValue; }
+  if (!image_fits_32bit((long long)a.zY * a.zX * a.Nz) || !image_fits_32bit(act_image_elems(a.dA))) {
+    set_error("apply_bwd: one image exceeds 2^31 elements"); return cudaErrorInvalidValue;
+  }
   if (G4 > 256) {
     // wide rows (the 1D->2D layer, 5120 columns viewed as [B*20][256]) are passed as narrower images
     set_error("apply_bwd: Nz=%d too wide; pass it as more images of <= 1024 columns", a.Nz);
