@@ -765,27 +765,35 @@ cudaError_t launch_apply_bwd(const ApplyBwdArgs& a, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------
 // Stem operands.  Generator (model.py:241-242): the 2-channel input stack(x*mask, mask) with its 15
-// horizontal taps folded into channels: X15[b,h,w, kw*2+c] = in_c[b,h,w+kw-7]; 30 of 64 channels
-// used, so the 5x15 conv becomes 5 vertical taps over a 64-channel operand.
+// horizontal taps and PAIRS of vertical taps folded into channels.  The operand has 81 rows per
+// image, row r holding input rows r-1 and r:
+//   X[b,r,w, dh*30 + kw*2 + c] = in_c[b, r-1+dh, w+kw-7],  dh in {0,1}, r in [0,81)
+// 60 of 64 channels used, so the 5x15 conv becomes 3 vertical taps (operand rows h-1, h+1, h+3 for
+// output row h; tap t holds kernel rows 2t and 2t+1, the sixth row's weights are zero) over a
+// 64-channel operand -- K = 192 per output instead of 320 with one kernel row per GEMM tap.
 __global__ void prep_g_kernel(const float* __restrict__ x, const float* __restrict__ mask, int B,
                               int T, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const long long total = (long long)B * 80 * T * 16;
+  const long long total = (long long)B * 81 * T * 16;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(idx & 15) << 2;
     const long long pos = idx >> 4;
     const int w = (int)(pos % T);
-    const long long bh = pos / T;
+    const long long br = pos / T;
+    const int r = (int)(br % 81);
+    const long long b = br / 81;
     float v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int ch = c4 + i;
-      const int kw = ch >> 1, c = ch & 1;
-      const int ws = w + kw - 7;
+      const int dh = ch >= 30 ? 1 : 0, rem = ch - dh * 30;
+      const int kw = rem >> 1, c = rem & 1;
+      const int ws = w + kw - 7, hs = r - 1 + dh;
       float val = 0.f;
-      if (ch < 30 && ws >= 0 && ws < T) {
-        const float m = mask[bh * T + ws];
-        val = c ? m : x[bh * T + ws] * m;
+      if (ch < 60 && hs >= 0 && hs < 80 && ws >= 0 && ws < T) {
+        const long long src = (b * 80 + hs) * T + ws;
+        const float m = mask[src];
+        val = c ? m : x[src] * m;
       }
       v[i] = val;
     }
@@ -794,7 +802,7 @@ __global__ void prep_g_kernel(const float* __restrict__ x, const float* __restri
 }
 cudaError_t launch_prep_g(const float* x, const float* mask, int B, int T, __nv_bfloat16* hi,
                           __nv_bfloat16* lo, cudaStream_t s) {
-  const long long total = (long long)B * 80 * T * 16;
+  const long long total = (long long)B * 81 * T * 16;
   prep_g_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, mask, B, T, hi, lo);
   return launched();
 }
@@ -1260,7 +1268,7 @@ cudaError_t launch_head_d_bwd(const float* dout, const float* out, int B, int Y,
 }
 
 // Stem input gradients: fold the operand gradient back onto the input grid.
-//   Generator: dx[b,h,w] = mask[b,h,w] * sum_kw dX15[(b,h,w-kw+7), kw*2]   (d(x*mask)/dx = mask)
+//   Generator: dx[b,h,w] = mask[b,h,w] * sum_{dh,kw} dX[(b,h+1-dh,w-kw+7), dh*30 + kw*2]   (d(x*mask)/dx = mask)
 __global__ void col2im_g_kernel(const float* __restrict__ dX, const float* __restrict__ mask, int B,
                                 int T, float* __restrict__ dx) {
   const long long total = (long long)B * 80 * T;
@@ -1268,10 +1276,15 @@ __global__ void col2im_g_kernel(const float* __restrict__ dX, const float* __res
        idx += (long long)gridDim.x * blockDim.x) {
     const int w = (int)(idx % T);
     const long long bh = idx / T;
+    const int h = (int)(bh % 80);
+    const long long b = bh / 80;
     float acc = 0.f;
-    for (int kw = 0; kw < 15; ++kw) {
-      const int wd = w - kw + 7;
-      if (wd >= 0 && wd < T) acc += dX[(bh * T + wd) * 64 + kw * 2];
+    for (int dh = 0; dh < 2; ++dh) {             // operand rows h+1 (dh = 0) and h (dh = 1) hold input row h
+      const long long row = (b * 81 + h + 1 - dh) * T;
+      for (int kw = 0; kw < 15; ++kw) {
+        const int wd = w - kw + 7;
+        if (wd >= 0 && wd < T) acc += dX[(row + wd) * 64 + dh * 30 + kw * 2];
+      }
     }
     dx[idx] = acc * mask[idx];
   }
@@ -1313,7 +1326,7 @@ __device__ __forceinline__ void pack_map(const PackArgs& a, int n, int c, int t,
   switch (a.kind) {
     case kPackStd: *tp = t; *np = n + a.nOffset; *cp = c; break;
     case kPackShuffle: *tp = t; *np = (n & 3) * (a.N >> 2) + (n >> 2) + a.nOffset; *cp = c; break;
-    case kPackStemG: { const int kh = t / 15, kw = t - kh * 15; *tp = kh; *np = n + a.nOffset; *cp = kw * 2 + c; break; }
+    case kPackStemG: { const int kh = t / 15, kw = t - kh * 15; *tp = kh >> 1; *np = n + a.nOffset; *cp = (kh & 1) * 30 + kw * 2 + c; break; }
     case kPack2dTo1d: *tp = c % 20; *np = n + a.nOffset; *cp = c / 20; break;
     case kPack1dTo2d: *tp = 0; *np = (n % 20) * 256 + n / 20; *cp = c; break;
     case kPackHead: *tp = 0; *np = t; *cp = c; break;

@@ -139,7 +139,9 @@ ModelDesc build_generator() {
   pt.conv("lastConvLayer", 1, 128, 75);
 
   DescBuilder b(pt);
-  b.conv("stem", {"conv1", "conv1_gates"}, 128, 2, 75, kPackStemG, kVecIdent, 256, 64, 5, 64);
+  // stem: the 15 horizontal taps AND pairs of vertical taps are folded into the operand's channels
+  // (60 of 64 used), leaving 3 vertical taps at rows h-2, h, h+2 (see prep_g_kernel)
+  b.conv("stem", {"conv1", "conv1_gates"}, 128, 2, 75, kPackStemG, kVecIdent, 256, 64, 3, 64);
   b.conv("ds1", {"downSample1.convLayer.0", "downSample1.convLayer_gates.0"}, 256, 128, 25,
          kPackStd, kVecIdent, 512, 128, 25, 128);
   b.conv("ds2", {"downSample2.convLayer.0", "downSample2.convLayer_gates.0"}, 256, 256, 25,
@@ -325,6 +327,13 @@ TapList taps_s1(int KH, int KW, int padH, int padW, int sign) {
   TapList l;
   for (int kh = 0; kh < KH; ++kh)
     for (int kw = 0; kw < KW; ++kw) l.add(sign * (kw - padW), sign * (kh - padH), 0, kh * KW + kw);
+  return l;
+}
+// Generator stem over the folded operand: 3 taps at input rows -2, 0, +2 (each holds kernel rows 2t, 2t+1)
+// (operand row r = input row + 1: the operand has 81 rows, see prep_g_kernel)
+TapList taps_stem_g(int sign) {
+  TapList l;
+  for (int t = 0; t < 3; ++t) l.add(0, sign * (2 * t - 1), 0, t);
   return l;
 }
 // stride-2 KxK forward taps over a parity-split input
@@ -838,7 +847,7 @@ GenSaved plan_gen_saved(const GenDims& d, void* base, std::vector<SavedEntry>* l
   const long long M0 = (long long)d.B * 80 * d.T, M1 = (long long)d.B * 40 * d.W1,
                   M2 = (long long)d.B * 20 * d.W2, L = (long long)d.B * d.W2,
                   M7 = (long long)d.B * 40 * d.X1, M8 = (long long)d.B * 80 * d.X2;
-  s.X15 = take_pair(a, M0 * 64, "X15");
+  s.X15 = take_pair(a, (long long)d.B * 81 * d.T * 64, "X15");   // 81 operand rows per image (prep_g_kernel)
   s.z0 = a.takeT<float>(M0 * 256, "z0");
   s.A0 = take_pair(a, parity_elems(d.B, 80, d.T, 128), "A0", c8, rec);
   s.z1 = a.takeT<float>(M1 * 512, "z1");
@@ -922,8 +931,8 @@ int generator_forward(const void* packed, const float* x, const float* mask, int
 
   // stem: stack(x*mask, mask) -> 5x15 conv || gates -> a * sigmoid(g)            model.py:241-242
   r.check(launch_prep_g(x, mask, B, T, s.X15.hi, s.X15.lo, st), "prep_g");
-  run_conv(r, plain_op(s.X15, B, 80, T, 64), W.fwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, 1),
-           B, 80, T, plain_out(s.z0, 80, T, 256), W.bias(cv[G_STEM]), nullptr, "G stem conv", 150.0 / 320.0);
+  run_conv(r, plain_op(s.X15, B, 81, T, 64), W.fwd(cv[G_STEM]), taps_stem_g(1),
+           B, 80, T, plain_out(s.z0, 80, T, 256), W.bias(cv[G_STEM]), nullptr, "G stem conv", 150.0 / 192.0);
   if (r.ok) r.check(launch_apply_fwd(mk_apply(kGatedNoNorm, s.z0, 256, 80, T, Stat{nullptr, nullptr}, 0,
                                               nullptr, nullptr, 1, nullptr,
                                               abuf(s.A0, nullptr, B, 80, T, 128, 1)), st), "G stem glu");
@@ -1067,7 +1076,7 @@ long long generator_bwd_ws_bytes(int B, int T) {
   add((long long)B * 40 * d.W1 * 512 * 2); add((long long)B * 40 * d.W1 * 512 * 2);  // dz1
   add(parity_elems(B, 80, d.T, 128) * 4);        // dA0
   add(M0 * 256 * 2); add(M0 * 256 * 2);          // dz0
-  add(M0 * 64 * 4);                              // dX15
+  add((long long)B * 81 * d.T * 64 * 4);         // dX15 (81 operand rows per image)
   add(gen_stat_pool_floats(B) * 4);              // t1 / t2 reduction pool
   add(64 * 4);                                   // dz scale records (C8 mode)
   add(2 * 5120 * 4);                             // affine-grad sink
@@ -1281,12 +1290,12 @@ int generator_backward(const void* packed, const void* saved, const float* mask,
                     gbuf(dA0, B, 80, d.T, 128, 1), tp, nullptr, nullptr, dz0, gB(G_STEM)),
           "G stem bwd");
   if (needWgrad)
-    run_wgrad(r, plain_op(dz0, B, 80, d.T, 256), plain_op(s.X15, B, 80, d.T, 64),
-              taps_s1(5, 1, 2, 0, 1), nullptr, B, 80, d.T, gW(G_STEM), "G stem wgrad", 150.0 / 320.0);
+    run_wgrad(r, plain_op(dz0, B, 80, d.T, 256), plain_op(s.X15, B, 81, d.T, 64),
+              taps_stem_g(1), nullptr, B, 80, d.T, gW(G_STEM), "G stem wgrad", 150.0 / 192.0);
   if (dx) {
-    float* dX15 = a.takeT<float>(M0 * 64);
-    run_conv(r, plain_op(dz0, B, 80, d.T, 256), W.bwd(cv[G_STEM]), taps_s1(5, 1, 2, 0, -1), B, 80,
-             d.T, plain_out(dX15, 80, d.T, 64), nullptr, nullptr, "G stem dgrad", 150.0 / 320.0);
+    float* dX15 = a.takeT<float>((long long)B * 81 * d.T * 64);
+    run_conv(r, plain_op(dz0, B, 80, d.T, 256), W.bwd(cv[G_STEM]), taps_stem_g(-1), B, 81,
+             d.T, plain_out(dX15, 81, d.T, 64), nullptr, nullptr, "G stem dgrad", 150.0 / 192.0);
     if (r.ok) r.check(launch_col2im_g(dX15, mask, B, d.T, dx, st), "G col2im");
   }
   r.join();
