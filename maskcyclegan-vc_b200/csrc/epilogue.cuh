@@ -136,4 +136,70 @@ __device__ __forceinline__ void epilogue_chunk(const ConvGeom& g, const uint32_t
 }
 
 
+// Coalesced variant of the plain-store path.  A TMEM lane is an output row, so the direct epilogue
+// writes 32 different 128-byte lines with every STG.128 (16 bytes each): short-K layers (Generator
+// stem, heads: 2-3 k-blocks per tile) then run at the rate the L2 takes those partial-sector writes,
+// ~1.7 TB/s.  Here a warp stages its chunk through a 16-row x 36-float shared buffer (two rounds of
+// 16 rows; conflict-free 16-byte accesses both ways) so that every STG.128 covers four full lines.
+// `rowp[h*4+k]` = output pointer (chunk column 0) of row h*16 + k*4 + lane/8, `vmask` = ballot of the
+// rows' validity.  Statistics are taken from the registers exactly as in epilogue_chunk.
+constexpr int kStagePitch = 36;                          // floats per staged row (32 + 4: no bank conflicts)
+constexpr int kStageFloatsPerWarp = 16 * kStagePitch;
+__device__ __forceinline__ void epilogue_chunk_staged(const ConvGeom& g, const uint32_t (&v)[32], bool valid,
+                                                      float* sbuf, float* const (&rowp)[8], unsigned vmask,
+                                                      int ncol0, int lane, int b) {
+  float o[32];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float4 t;
+    t.x = __uint_as_float(v[i + 0]);
+    t.y = __uint_as_float(v[i + 1]);
+    t.z = __uint_as_float(v[i + 2]);
+    t.w = __uint_as_float(v[i + 3]);
+    if (g.bias) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + ncol0 + i));
+      t.x += bv.x; t.y += bv.y; t.z += bv.z; t.w += bv.w;
+    }
+    o[i] = t.x; o[i + 1] = t.y; o[i + 2] = t.z; o[i + 3] = t.w;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if ((lane >> 4) == h) {
+      float* d = sbuf + (lane & 15) * kStagePitch;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(d + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = k * 4 + (lane >> 3), jj = (lane & 7) * 4;
+      const float4 t = *reinterpret_cast<const float4*>(sbuf + r * kStagePitch + jj);
+      if ((vmask >> (h * 16 + r)) & 1u) *reinterpret_cast<float4*>(rowp[h * 4 + k] + jj) = t;
+    }
+    __syncwarp();
+  }
+  if (g.statSum) {
+    float q[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      o[i] = valid ? o[i] : 0.f;
+      q[i] = o[i] * o[i];
+    }
+    const bool img_ok = b < g.oB;
+    const long long so = (long long)(img_ok ? b : 0) * g.w.N + ncol0;
+    float* dA = g.statSum + so;
+    float* dB = g.statSq + so;
+    switch (g.statSeg) {
+      case 32: warp_colsum_add<32>(o, q, lane, dA, dB, img_ok); break;
+      case 16: warp_colsum_add<16>(o, q, lane, dA, dB, img_ok); break;
+      case 8: warp_colsum_add<8>(o, q, lane, dA, dB, img_ok); break;
+      case 4: warp_colsum_add<4>(o, q, lane, dA, dB, img_ok); break;
+      case 2: warp_colsum_add<2>(o, q, lane, dA, dB, img_ok); break;
+      default: warp_colsum_add<1>(o, q, lane, dA, dB, img_ok); break;
+    }
+  }
+}
+
+
 }  // namespace mcgvc
