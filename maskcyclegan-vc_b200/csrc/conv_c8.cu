@@ -57,10 +57,11 @@ struct C8Cfg {
   static constexpr int kOffW8h = kOffA8l + kA8;
   static constexpr int kOffW8l = kOffW8h + kW8;
   static constexpr int kStageBytes = kOffW8l + kW8;           // 64 KB (N = 256) / 48 KB (N = 128)
-  static constexpr int kStages = (222 * 1024) / kStageBytes > 8 ? 8 : (222 * 1024) / kStageBytes;
+  static constexpr int kOutStageBytes = 8 * kStageFloatsPerWarp * 4;   // coalescing buffers of the 8 epilogue warps
+  static constexpr int kStages = (222 * 1024 - kOutStageBytes) / kStageBytes > 8 ? 8 : (222 * 1024 - kOutStageBytes) / kStageBytes;
   static constexpr int kAccBufs = 512 / (2 * BLOCK_N);        // D1 + D2 per buffer: 1 (N=256) or 2 (N=128)
   static constexpr int kTmemCols = 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kOutStageBytes;
   static_assert(kStageBytes % 1024 == 0 && kOffA8h % 1024 == 0 && kOffW8h % 1024 == 0 && kOffW8l % 1024 == 0, "tile alignment");
   static_assert(kAccBufs >= 1 && kStages >= 2, "config");
 };
@@ -248,6 +249,19 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
       float* orow = g.out + off;
       const float* arow = g.addsrc ? g.addsrc + off : nullptr;
 
+      // plain stores go through the warp's coalescing buffer (epilogue_chunk_staged)
+      const bool staged = !arow && wi.slot < 0 && kSplit == 1;
+      float* rowp[8];
+      unsigned vmask = 0;
+      if (staged) {
+        vmask = __ballot_sync(0xffffffffu, valid);
+        const unsigned long long mine = reinterpret_cast<unsigned long long>(orow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, mine, (i >> 2) * 16 + (i & 3) * 4 + (lane >> 3)));
+      }
+      float* sbuf = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * kStageFloatsPerWarp;
+
       ptx::mbar_wait(&tfull[acc], aphase);
       ptx::tc_fence_after();
       const uint32_t t1 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 2 * BLOCK_N;
@@ -261,10 +275,16 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           v1[i] = __float_as_uint(c1 * fmaf(c2, __uint_as_float(v2[i]), __uint_as_float(v1[i])));
-        if (wi.slot >= 0)   // tail split: raw partial -> scratch, merged by conv_tail_fixup
+        if (wi.slot >= 0) {   // tail split: raw partial -> scratch, merged by conv_tail_fixup
           store_partial_chunk(g.tailScratch + (((size_t)wi.slot * 2 + rank) * kTileM + row) * BLOCK_N + j * 32, v1);
-        else
+        } else if (staged) {
+          float* rp[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rp[i] = rowp[i] + j * 32;
+          epilogue_chunk_staged(g, v1, valid, sbuf, rp, vmask, n0 + j * 32, lane, b);
+        } else {
           epilogue_chunk(g, v1, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b, kSplit > 1, ks == 0);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();

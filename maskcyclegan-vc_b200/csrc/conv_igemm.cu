@@ -265,11 +265,12 @@ struct ConvCfg {
   static constexpr int kABytes = kTileM * kBlockK * 2;    // 16 KB
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = (kABytes + kBBytes) * (NPASS == 3 ? 2 : 1);
-  static constexpr int kBudget = 222 * 1024;
+  static constexpr int kOutStageBytes = 4 * kStageFloatsPerWarp * 4;   // coalescing buffers of the 4 epilogue warps
+  static constexpr int kBudget = 222 * 1024 - kOutStageBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * BLOCK_N;           // two accumulator buffers
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kOutStageBytes;
   static_assert(kStages >= 2, "need at least two pipeline stages");
   static_assert(kTmemCols >= 32 && kTmemCols <= 512, "TMEM columns");
 };
@@ -440,6 +441,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       float* orow = g.out + off;
       const float* arow = g.addsrc ? g.addsrc + off : nullptr;
 
+      // plain stores go through the warp's coalescing buffer (epilogue_chunk_staged)
+      const bool staged = !arow && kSplit == 1;
+      float* rowp[8];
+      unsigned vmask = 0;
+      if (staged) {
+        vmask = __ballot_sync(0xffffffffu, valid);
+        const unsigned long long mine = reinterpret_cast<unsigned long long>(orow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, mine, (i >> 2) * 16 + (i & 3) * 4 + (lane >> 3)));
+      }
+      float* sbuf = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * kStageFloatsPerWarp;
+
       ptx::mbar_wait(&tfull[acc], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
@@ -452,8 +466,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(osc * __uint_as_float(v[i]));
         }
-        epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b,
-                       kSplit > 1, ks == 0);
+        if (staged) {
+          float* rp[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rp[i] = rowp[i] + j * 32;
+          epilogue_chunk_staged(g, v, valid, sbuf, rp, vmask, n0 + j * 32, lane, b);
+        } else {
+          epilogue_chunk(g, v, valid, orow + j * 32, arow ? arow + j * 32 : nullptr, n0 + j * 32, lane, b,
+                         kSplit > 1, ks == 0);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
