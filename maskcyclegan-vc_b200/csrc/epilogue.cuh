@@ -202,4 +202,26 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvGeom& g, const u
 }
 
 
+// Coalesced red.global.add of one 32-row x 32-column chunk (weight-gradient kernels): same staging as
+// epilogue_chunk_staged; `rowp[h*4+k]` = destination (chunk column 0) of row h*16 + k*4 + lane/8.
+__device__ __forceinline__ void red_chunk_staged(const float (&o)[32], float* sbuf, float* const (&rowp)[8],
+                                                 int lane) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if ((lane >> 4) == h) {
+      float* d = sbuf + (lane & 15) * kStagePitch;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(d + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = k * 4 + (lane >> 3), jj = (lane & 7) * 4;
+      red_add_f32x4(rowp[h * 4 + k] + jj, *reinterpret_cast<const float4*>(sbuf + r * kStagePitch + jj));
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace mcgvc

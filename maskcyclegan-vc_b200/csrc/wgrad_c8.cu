@@ -13,6 +13,7 @@
 // Selected with mcgvc_set_precision(MCGVC_PRECISION_C8), see conv_c8.cu; mcgvc_debug_wgrad_c8 reaches it
 // in isolation.
 #include "gemm_types.cuh"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -42,9 +43,6 @@ __host__ __device__ constexpr uint32_t idesc16_mn(uint32_t fmt, uint32_t M, uint
 __host__ __device__ constexpr uint32_t idesc8_mn(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 template <int CTILE>
 struct WgC8Cfg {
@@ -58,9 +56,10 @@ struct WgC8Cfg {
   static constexpr int kOffX8h = kOffZ8l + kZ8;
   static constexpr int kOffX8l = kOffX8h + kX8;
   static constexpr int kStageBytes = kOffX8l + kX8;       // 64 KB / 48 KB
-  static constexpr int kStages = (222 * 1024) / kStageBytes > 8 ? 8 : (222 * 1024) / kStageBytes;
+  static constexpr int kOutStageBytes = 4 * kStageFloatsPerWarp * 4;   // coalescing buffers of the 4 epilogue warps
+  static constexpr int kStages = (222 * 1024 - kOutStageBytes) / kStageBytes > 8 ? 8 : (222 * 1024 - kOutStageBytes) / kStageBytes;
   static constexpr int kTmemCols = 2 * CTILE;             // D1 and D2
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kOutStageBytes;
   static constexpr int kXRow = CTILE / 2;                 // bytes per position row of an x e4m3 box
   static_assert(CTILE == 128 || CTILE == 256, "pair tile is 128 or 256 channels wide");
   static_assert(kStageBytes % 1024 == 0 && kOffZ8h % 1024 == 0 && kOffX8h % 1024 == 0 && kOffX8l % 1024 == 0, "tile alignment");
@@ -193,6 +192,14 @@ wgrad_c8_kernel(const __grid_constant__ CUtensorMap tmZ16, const __grid_constant
         c1 *= __ldg(g.c8RecZ) * __ldg(g.c8RecX);
         c2 *= __ldg(g.c8RecZ + 1) * __ldg(g.c8RecX + 1);
       }
+      float* rowp[8];
+      {
+        const unsigned long long mine = reinterpret_cast<unsigned long long>(drow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, mine, (i >> 2) * 16 + (i & 3) * 4 + (lane >> 3)));
+      }
+      float* sbuf = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * kStageFloatsPerWarp;
       ptx::mbar_wait(tfull, 0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -202,13 +209,15 @@ wgrad_c8_kernel(const __grid_constant__ CUtensorMap tmZ16, const __grid_constant
         ptx::tmem_ld32(taddr + j * 32, v1);
         ptx::tmem_ld32(taddr + CTILE + j * 32, v2);
         ptx::tmem_ld_wait();
+        // coalesced red.add through the warp's staging buffer (a TMEM lane is a dW row: the direct
+        // form hit 32 different lines with 16 bytes each per instruction)
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          red_add4(drow + j * 32 + i,
-                   c1 * fmaf(c2, __uint_as_float(v2[i + 0]), __uint_as_float(v1[i + 0])),
-                   c1 * fmaf(c2, __uint_as_float(v2[i + 1]), __uint_as_float(v1[i + 1])),
-                   c1 * fmaf(c2, __uint_as_float(v2[i + 2]), __uint_as_float(v1[i + 2])),
-                   c1 * fmaf(c2, __uint_as_float(v2[i + 3]), __uint_as_float(v1[i + 3])));
+        for (int i = 0; i < 32; ++i) o[i] = c1 * fmaf(c2, __uint_as_float(v2[i]), __uint_as_float(v1[i]));
+        float* rp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rp[i] = rowp[i] + j * 32;
+        red_chunk_staged(o, sbuf, rp, lane);
       }
     }
   }

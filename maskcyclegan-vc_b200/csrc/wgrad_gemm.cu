@@ -13,6 +13,7 @@
 // red.global.add.v4.f32, which also merges the K splits and the repeated uses of one module in a
 // backward pass.
 #include "gemm_types.cuh"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -30,18 +31,14 @@ struct WgradCfg {
   static constexpr int kZBytes = 2 * kChunkBytes;               // 128 rows of n
   static constexpr int kXBytes = (CTILE / 64) * kChunkBytes;
   static constexpr int kStageBytes = (kZBytes + kXBytes) * (NPASS == 3 ? 2 : 1);
-  static constexpr int kStagesRaw = (222 * 1024) / kStageBytes;
+  static constexpr int kOutStageBytes = 4 * kStageFloatsPerWarp * 4;   // coalescing buffers of the 4 epilogue warps
+  static constexpr int kStagesRaw = (222 * 1024 - kOutStageBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = CTILE < 32 ? 32 : CTILE;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kOutStageBytes;
   static_assert(kStages >= 2, "need at least two pipeline stages");
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
-               "f"(d)
-               : "memory");
-}
 
 template <int CTILE, int NPASS>
 __global__ void __launch_bounds__(256, 1)
@@ -183,6 +180,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant_
         osc = g.c8OutScale;
         if (g.c8RecZ && g.c8RecX) osc *= __ldg(g.c8RecZ) * __ldg(g.c8RecX);
       }
+      // coalesced red.add through the warp's staging buffer (epilogue.cuh red_chunk_staged)
+      float* rowp[8];
+      {
+        const unsigned long long mine = reinterpret_cast<unsigned long long>(drow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, mine, (i >> 2) * 16 + (i & 3) * 4 + (lane >> 3)));
+      }
+      float* sbuf = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * kStageFloatsPerWarp;
       ptx::mbar_wait(tfull, 0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -191,10 +197,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant_
         uint32_t v[32];
         ptx::tmem_ld32(taddr + j * 32, v);
         ptx::tmem_ld_wait();
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          red_add_v4(drow + j * 32 + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
-                     osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
+        for (int i = 0; i < 32; ++i) o[i] = osc * __uint_as_float(v[i]);
+        float* rp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rp[i] = rowp[i] + j * 32;
+        red_chunk_staged(o, sbuf, rp, lane);
       }
     }
   }
@@ -262,10 +271,11 @@ struct Wgrad2Cfg {
   static constexpr int kZBytes = 2 * kChunkBytes;                   // this CTA's 128 n rows
   static constexpr int kXBytes = (CTILE / 128) * kChunkBytes;       // this CTA's CTILE/2 channels
   static constexpr int kStageBytes = (kZBytes + kXBytes) * (NPASS == 3 ? 2 : 1);
-  static constexpr int kStagesRaw = (222 * 1024) / kStageBytes;
+  static constexpr int kOutStageBytes = 4 * kStageFloatsPerWarp * 4;   // coalescing buffers of the 4 epilogue warps
+  static constexpr int kStagesRaw = (222 * 1024 - kOutStageBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = CTILE;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kOutStageBytes;
   static_assert(CTILE == 128 || CTILE == 256, "pair tile is 128 or 256 channels wide");
 };
 
@@ -410,6 +420,15 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant
         osc = g.c8OutScale;
         if (g.c8RecZ && g.c8RecX) osc *= __ldg(g.c8RecZ) * __ldg(g.c8RecX);
       }
+      // coalesced red.add through the warp's staging buffer (epilogue.cuh red_chunk_staged)
+      float* rowp[8];
+      {
+        const unsigned long long mine = reinterpret_cast<unsigned long long>(drow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, mine, (i >> 2) * 16 + (i & 3) * 4 + (lane >> 3)));
+      }
+      float* sbuf = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * kStageFloatsPerWarp;
       ptx::mbar_wait(tfull, 0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -418,10 +437,13 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant
         uint32_t v[32];
         ptx::tmem_ld32(taddr + j * 32, v);
         ptx::tmem_ld_wait();
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          red_add_v4(drow + j * 32 + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
-                     osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
+        for (int i = 0; i < 32; ++i) o[i] = osc * __uint_as_float(v[i]);
+        float* rp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rp[i] = rowp[i] + j * 32;
+        red_chunk_staged(o, sbuf, rp, lane);
       }
     }
   }
@@ -473,10 +495,11 @@ struct WgradPCfg {
   static constexpr int kZBytes = 2 * kChunkBytes;                   // this CTA's 128 n rows
   static constexpr int kXBytes = (CTILE / 128) * kChunkBytes;       // this CTA's CTILE/2 channels, per tap
   static constexpr int kStageBytes = kZBytes + 2 * kXBytes;         // 48 KB (CTILE 256) / 32 KB (CTILE 128)
-  static constexpr int kStagesRaw = (222 * 1024) / kStageBytes;
+  static constexpr int kOutStageBytes = 4 * kStageFloatsPerWarp * 4;   // coalescing buffers of the 4 epilogue warps
+  static constexpr int kStagesRaw = (222 * 1024 - kOutStageBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * CTILE;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kOutStageBytes;
   static_assert(CTILE == 128 || CTILE == 256, "pair tile is 128 or 256 channels wide");
 };
 
@@ -610,15 +633,26 @@ wgrad_tc2p_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
       for (int which = 0; which < (two ? 2 : 1); ++which) {
         const Tap tap = which ? tapB : tapA;
         float* drow = g.dw + ((long long)tap.w * g.N + n) * g.C + c0;
+        float* rowp[8];
+        {
+          const unsigned long long mine = reinterpret_cast<unsigned long long>(drow);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, mine, (i >> 2) * 16 + (i & 3) * 4 + (lane >> 3)));
+        }
+        float* sbuf = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * kStageFloatsPerWarp;
 #pragma unroll 1
         for (int j = 0; j < CTILE / 32; ++j) {
           uint32_t v[32];
           ptx::tmem_ld32(taddr + which * CTILE + j * 32, v);
           ptx::tmem_ld_wait();
+          float o[32];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            red_add_v4(drow + j * 32 + i, osc * __uint_as_float(v[i]), osc * __uint_as_float(v[i + 1]),
-                       osc * __uint_as_float(v[i + 2]), osc * __uint_as_float(v[i + 3]));
+          for (int i = 0; i < 32; ++i) o[i] = osc * __uint_as_float(v[i]);
+          float* rp[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rp[i] = rowp[i] + j * 32;
+          red_chunk_staged(o, sbuf, rp, lane);
         }
       }
     }
