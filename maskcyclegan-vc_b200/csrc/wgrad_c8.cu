@@ -89,12 +89,16 @@ wgrad_c8_kernel(const __grid_constant__ CUtensorMap tmZ16, const __grid_constant
   const int cTiles = g.C / CTILE;
   const int nTiles = g.N / 256;
   int w = blockIdx.x >> 1;
-  const int split = w % g.splitK;
-  w /= g.splitK;
-  const int ct = w % cTiles;
-  w /= cTiles;
+  // taps fastest, position split slowest: the ~74 pairs running at a time work on the same slice of
+  // positions for every tap, so dz / x are streamed from HBM once and re-read from L2 (split-fastest
+  // order re-streamed both operands per tap: 2-3x the algorithmic DRAM bytes), and the red.adds of
+  // one dW tile are spread over the whole launch
+  const int t = w % g.nTaps;
+  w /= g.nTaps;
   const int nt = w % nTiles;
-  const int t = w / nTiles;
+  w /= nTiles;
+  const int ct = w % cTiles;
+  const int split = w / cTiles;
   const Tap tap = g.taps[t];
   const Tap ztap = g.ztaps[t];
   const int n0 = nt * 256 + (int)rank * 128;            // this CTA's gradient rows

@@ -59,16 +59,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work decode: blockIdx.x -> (split, cTile, nTile, tap)
+  // work decode: blockIdx.x -> (tap, nTile, cTile, split)
   const int cTiles = g.C / CTILE;
   const int nTiles = g.N / 128;
   int w = blockIdx.x;
-  const int split = w % g.splitK;
-  w /= g.splitK;
-  const int ct = w % cTiles;
-  w /= cTiles;
+  // taps fastest, position split slowest: the ~74 pairs running at a time work on the same slice of
+  // positions for every tap, so dz / x are streamed from HBM once and re-read from L2 (split-fastest
+  // order re-streamed both operands per tap: 2-3x the algorithmic DRAM bytes), and the red.adds of
+  // one dW tile are spread over the whole launch
+  const int t = w % g.nTaps;
+  w /= g.nTaps;
   const int nt = w % nTiles;
-  const int t = w / nTiles;
+  w /= nTiles;
+  const int ct = w % cTiles;
+  const int split = w / cTiles;
   const Tap tap = g.taps[t];
   const Tap ztap = g.ztaps[t];
   const int n0 = nt * 128, c0 = ct * CTILE;
@@ -303,12 +307,16 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant
   const int cTiles = g.C / CTILE;
   const int nTiles = g.N / 256;
   int w = blockIdx.x >> 1;
-  const int split = w % g.splitK;
-  w /= g.splitK;
-  const int ct = w % cTiles;
-  w /= cTiles;
+  // taps fastest, position split slowest: the ~74 pairs running at a time work on the same slice of
+  // positions for every tap, so dz / x are streamed from HBM once and re-read from L2 (split-fastest
+  // order re-streamed both operands per tap: 2-3x the algorithmic DRAM bytes), and the red.adds of
+  // one dW tile are spread over the whole launch
+  const int t = w % g.nTaps;
+  w /= g.nTaps;
   const int nt = w % nTiles;
-  const int t = w / nTiles;
+  w /= nTiles;
+  const int ct = w % cTiles;
+  const int split = w / cTiles;
   const Tap tap = g.taps[t];
   const Tap ztap = g.ztaps[t];
   const int n0 = nt * 256 + (int)rank * 128;            // this CTA's gradient rows
@@ -526,12 +534,13 @@ wgrad_tc2p_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
   const int cTiles = g.C / CTILE;
   const int nTiles = g.N / 256;
   int w = blockIdx.x >> 1;
-  const int split = w % g.splitK;
-  w /= g.splitK;
-  const int ct = w % cTiles;
-  w /= cTiles;
+  const int tapPairs = (g.nTaps + 1) >> 1;               // tap pairs fastest, position split slowest (see wgrad_tc2_kernel)
+  const int tp = w % tapPairs;
+  w /= tapPairs;
   const int nt = w % nTiles;
-  const int tp = w / nTiles;                            // < ceil(nTaps / 2)
+  w /= nTiles;
+  const int ct = w % cTiles;
+  const int split = w / cTiles;
   const int t0 = 2 * tp, t1 = 2 * tp + 1;
   const bool two = t1 < g.nTaps;
   const Tap tapA = g.taps[t0];
