@@ -1,6 +1,7 @@
 // Bandwidth-bound layer kernels (see layers.cuh).  All are plain CUDA: coalesced 16-byte accesses
-// along the channel dimension, warp-shuffle / shared-memory reductions for InstanceNorm, grid
-// sizes capped at a multiple of the SM count with grid-stride loops.
+// along the channel dimension, per-thread cp.async rings for the streaming position loops,
+// warp-shuffle / shared-memory reductions for InstanceNorm, grids sized as whole resident waves
+// (occupancy x SM count) with grid-stride loops.
 #include "layers.cuh"
 #include "gemm_types.cuh"
 
@@ -933,10 +934,6 @@ cudaError_t launch_d_stem_fwd(const float* x, int B, int T, const __nv_bfloat16*
 // is written for the 3x3 fold below.  The dA loads run kStemRing-1 steps ahead of the math through
 // a per-lane cp.async ring (see apply_fwd_kernel) whose cursor crosses item boundaries.
 constexpr int kStemRing = 8;
-struct StemCursor {   // (item, step) iterator of one warp, used once for the loads and once for the math
-  int it, j;
-  StemItem m;
-};
 template <bool kQ>
 __global__ void __launch_bounds__(256, 2) d_stem_bwd_kernel(const float* __restrict__ x, int B, int T,
                                                          const __nv_bfloat16* __restrict__ wh,
