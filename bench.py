@@ -247,7 +247,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
     ap.add_argument("--impl", default="engine")
-    ap.add_argument("--precision", default="c8", choices=["parity", "c8", "c8h", "mixed", "fast"])
+    ap.add_argument("--precision", default="c8", choices=["parity", "c8", "c8w", "c8h", "mixed", "fast"])
     ap.add_argument("--lean", type=int, default=0)
     ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
                     help="torch = torch.optim.Adam as in train.py:119-122; fused = one-kernel Adam on the flat buffers")
@@ -290,11 +290,14 @@ def main():
     B = args.batch
     eng.lib()
     eng.set_backend(eng.BACKEND_TCGEN05)
-    modes = {"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8h": eng.PRECISION_C8H, "mixed": eng.PRECISION_MIXED,
-             "fast": eng.PRECISION_FAST}
+    modes = {"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8w": eng.PRECISION_C8W, "c8h": eng.PRECISION_C8H,
+             "mixed": eng.PRECISION_MIXED, "fast": eng.PRECISION_FAST}
     mode_note = {"parity": "split-bf16 x3 in every GEMM (fwd, dgrad, wgrad): outputs and gradients within 1e-3 of the fp32 reference",
                  "c8": "fp16 main pass + two e4m3 correction passes in every GEMM but the stems/heads (those: split-bf16 x3), "
                        "2 MMA units per MAC: outputs and gradients within 1e-3 of the fp32 reference",
+                 "c8w": "forward and data-gradient GEMMs exactly as c8; the weight-gradient GEMMs of the c8 layers (leaves of the backward "
+                        "graph: their rounding is not propagated) run ONE fp16 pass over the same operands' 16-bit planes, 5/3 MMA units "
+                        "per MAC of a train step: outputs and gradients within 1e-3 of the fp32 reference (same referees as c8)",
                  "c8h": "forward exactly as c8 (G output within 1e-3 of the reference); the backward GEMMs of the c8 layers run ONE fp16 "
                         "pass with a dynamic power-of-two scale on dz: gradients TF32-class (gate 5e-3 on the packed gradient, "
                         "tests/test_gpu_network.py), the accuracy class of the reference's own CUDA default (cudnn.allow_tf32)",
@@ -362,7 +365,7 @@ def main():
 
     gfb = {}
     G0.train()
-    for gmode in ("parity", "c8", "c8h", "mixed", "fast"):
+    for gmode in ("parity", "c8", "c8w", "c8h", "mixed", "fast"):
         eng.set_precision(modes[gmode])
         for _ in range(3):
             g_fwd_bwd()
@@ -399,7 +402,8 @@ def main():
     # roofline.traffic: DRAM bytes per launch of the dominant kernel's OWN launches, from this round's
     # `ncu --set full` capture (tools/ncu_summary.py --json; ncu cannot run inside the timed bench)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r02_kernel_traffic_%s.json" % ("c8h" if args.precision == "c8h" else args.precision))
+    # (c8w runs c8's forward / data-gradient kernels: same launches of the dominant kernel)
+    tpath = os.path.join(ROOT, "profiles", "r02_kernel_traffic_%s.json" % ("c8" if args.precision == "c8w" else args.precision))
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
@@ -429,12 +433,13 @@ def main():
                          "mixed": "forward: 3 bf16 MMAs per algorithmic MAC, backward: 1; achieved counts algorithmic FLOPs once",
                          "c8h": "forward: one fp16 MMA + two e4m3 MMAs (2x rate) per MAC = 2 units, backward: 1 fp16 MMA per MAC; achieved counts algorithmic FLOPs once",
                          "c8": "one fp16 MMA + two e4m3 MMAs (2x rate) per algorithmic MAC = 2 bf16-MMA time units (ceiling 1/2 of bf16 peak); achieved counts algorithmic FLOPs once",
+                         "c8w": "forward and data-gradient convolutions (this kernel): one fp16 MMA + two e4m3 MMAs (2x rate) per algorithmic MAC = 2 units (ceiling 1/2 of bf16 peak); weight gradients: 1 fp16 MMA per MAC; achieved counts algorithmic FLOPs once",
                          "fast": "single bf16 pass"}[args.precision]}
 
     other = None
     if args.fast_steps > 0:
         other = []
-        for other_mode in ("parity", "c8", "c8h", "mixed", "fast"):
+        for other_mode in ("parity", "c8", "c8w", "c8h", "mixed", "fast"):
             if other_mode == args.precision:
                 continue
             eng.set_precision(modes[other_mode])
@@ -484,6 +489,7 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"parity": "bf16x3 split (fp32 accumulate, fp32 activations/stats)",
                       "c8": "fp16 + 2x e4m3 correction (fp32 accumulate, fp32 activations/stats); stems/heads bf16x3",
+                      "c8w": "fp16 + 2x e4m3 correction in forward and data-gradient GEMMs, fp16 weight-gradient GEMMs (fp32 accumulate, fp32 activations/stats); stems/heads/trunk bf16x3",
                       "c8h": "forward fp16 + 2x e4m3 correction / backward fp16 (fp32 accumulate, fp32 activations/stats); stems/heads/trunk bf16x3",
                       "mixed": "bf16x3 split forward / bf16 backward (fp32 accumulate)", "fast": "bf16"}[args.precision],
             "data": "synthetic",

@@ -31,6 +31,13 @@ extern "C" {
                                      C8 layers run ONE fp16 pass over the same operands' 16-bit planes (dynamic power-of-two
                                      scale on dz): gradients are TF32-class (~1e-3 relative), i.e. the accuracy class of the
                                      reference's own CUDA default (cudnn.allow_tf32).  Same packed layout as C8. */
+#define MCGVC_PRECISION_C8W 6     /* forward AND data-gradient GEMMs exactly as C8; only the weight-gradient GEMMs of the C8
+                                     layers run ONE fp16 pass over the operands' 16-bit planes (the C8H weight-gradient
+                                     kernels).  A weight gradient is a leaf of the backward graph -- its rounding error is
+                                     not propagated through further layers -- so outputs, input gradients and packed
+                                     parameter gradients stay inside the same 1e-3 gate as C8 (tests/test_gpu_network.py,
+                                     every C8 referee also runs in this mode) at 5/3 instead of 2 MMA units per MAC of
+                                     a training step.  Same packed layout as C8. */
 
 const char* mcgvc_last_error(void);
 int mcgvc_set_device(int device);

@@ -10,7 +10,7 @@
 using namespace mcgvc;
 
 static int g_backend = MCGVC_BACKEND_TCGEN05;
-// default precision mode: MCGVC_PRECISION=parity|c8|c8h|mixed|fast in the environment (the unchanged reference
+// default precision mode: MCGVC_PRECISION=parity|c8|c8w|c8h|mixed|fast in the environment (the unchanged reference
 // train.py has no other way to choose), else C8 -- the fastest mode that holds the 1e-3 parity gate on
 // outputs AND gradients (refereed against the oracle at batch 64 / 16, tests/test_gpu_network.py)
 static int initial_precision() {
@@ -18,6 +18,7 @@ static int initial_precision() {
   if (!e) return MCGVC_PRECISION_C8;
   if (!strcmp(e, "c8") || !strcmp(e, "4")) return MCGVC_PRECISION_C8;
   if (!strcmp(e, "c8h") || !strcmp(e, "5")) return MCGVC_PRECISION_C8H;
+  if (!strcmp(e, "c8w") || !strcmp(e, "6")) return MCGVC_PRECISION_C8W;
   if (!strcmp(e, "mixed") || !strcmp(e, "2")) return MCGVC_PRECISION_MIXED;
   if (!strcmp(e, "fast") || !strcmp(e, "1")) return MCGVC_PRECISION_FAST;
   if (!strcmp(e, "parity") || !strcmp(e, "3")) return MCGVC_PRECISION_PARITY;
@@ -56,11 +57,12 @@ static DevStreams* dev_streams() {
   return &d;
 }
 static RunCfg cfg(void* stream, bool backward = false) {
-  const bool c8 = g_precision == MCGVC_PRECISION_C8 || g_precision == MCGVC_PRECISION_C8H;
+  const bool c8 = g_precision == MCGVC_PRECISION_C8 || g_precision == MCGVC_PRECISION_C8H || g_precision == MCGVC_PRECISION_C8W;
   int np = (g_precision == MCGVC_PRECISION_PARITY || c8) ? 3 : (g_precision == MCGVC_PRECISION_FAST ? 1 : (backward ? 1 : 3));
-  RunCfg rc{(cudaStream_t)stream, g_backend, np, nullptr, nullptr, 0, 0};
+  RunCfg rc{(cudaStream_t)stream, g_backend, np, nullptr, nullptr, 0, 0, 0};
   rc.c8 = c8;   // stems / heads / 1-D trunk stay split-bf16 x3 in these modes
   rc.half16 = (g_precision == MCGVC_PRECISION_C8H && backward) ? 1 : 0;
+  rc.wgradHalf16 = ((g_precision == MCGVC_PRECISION_C8H || g_precision == MCGVC_PRECISION_C8W) && backward) ? 1 : 0;
   return rc;
 }
 // run a backward body on the engine streams, bracketed by event hand-offs with the caller's stream
@@ -214,8 +216,8 @@ int mcgvc_set_backend(int backend) {
 }
 int mcgvc_set_precision(int mode) {
   if (mode != MCGVC_PRECISION_PARITY && mode != MCGVC_PRECISION_FAST && mode != MCGVC_PRECISION_MIXED &&
-      mode != MCGVC_PRECISION_C8 && mode != MCGVC_PRECISION_C8H) {
-    set_error("precision must be MCGVC_PRECISION_PARITY (3), _MIXED (2), _FAST (1), _C8 (4) or _C8H (5)");
+      mode != MCGVC_PRECISION_C8 && mode != MCGVC_PRECISION_C8H && mode != MCGVC_PRECISION_C8W) {
+    set_error("precision must be MCGVC_PRECISION_PARITY (3), _MIXED (2), _FAST (1), _C8 (4), _C8H (5) or _C8W (6)");
     return 1;
   }
   g_precision = mode;

@@ -546,7 +546,7 @@ void run_wgrad(Run& r, const ActOperand& dz, const ActOperand& x, const TapList&
     }
     g.splitK = best;
   };
-  if (dz.h8 && x.h8 && r.rc.half16) {   // C8H: one fp16 pass over the 16-bit planes
+  if (dz.h8 && x.h8 && r.rc.wgradHalf16) {   // C8H / C8W: one fp16 pass over the 16-bit planes
     g.nPass = 1;
     g.half16 = 1;
     g.c8OutScale = 1.f;

@@ -67,7 +67,9 @@ struct RunCfg {
   cudaStream_t side;  // stream for the weight-gradient GEMMs of a backward pass, or null (same stream)
   cudaEvent_t forkEvent;  // persistent event used to fork to / join from the side stream
   int c8;        // 1 = C8 precision mode: fp16 main pass + two e4m3 correction passes (stems / heads: split-bf16)
-  int half16;    // C8H backward: the GEMMs of C8 layers run ONE fp16 pass on the 16-bit planes (dgrad and wgrad)
+  int half16;    // C8H backward: the data-gradient GEMMs of C8 layers run ONE fp16 pass on the 16-bit planes
+                 // (and dz keeps only its fp16 plane)
+  int wgradHalf16;  // C8H / C8W backward: the weight-gradient GEMMs of C8 layers run ONE fp16 pass on the 16-bit planes
 };
 
 // sizes (bytes) of the per-call buffers the caller provides

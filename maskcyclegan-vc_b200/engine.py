@@ -17,6 +17,7 @@ PRECISION_MIXED = 2    # forward split-bf16 x3, backward single bf16 pass
 PRECISION_FAST = 1     # single bf16 pass
 PRECISION_C8 = 4       # DEFAULT: fp16 main pass + two e4m3 correction passes (2 MMA units per MAC); meets the 1e-3 gate
 PRECISION_C8H = 5      # forward as C8; backward GEMMs of the C8 layers: one fp16 pass (TF32-class gradients)
+PRECISION_C8W = 6      # forward and data gradients as C8; weight-gradient GEMMs of the C8 layers: one fp16 pass (same 1e-3 gate)
 
 # MCGVC_LIBRARY: another build of the same library (A/B timing of two builds in one gpurun call)
 _LIB_PATH = os.environ.get("MCGVC_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcgvc.so")
@@ -116,7 +117,7 @@ def pack_class(precision=None):
     """Modes that share one packed-weight layout: split-bf16 planes (parity / mixed / fast) or the
     fp16 + 2 x e4m3 planes (C8 / C8H)."""
     p = get_precision() if precision is None else precision
-    return 1 if p in (PRECISION_C8, PRECISION_C8H) else 0
+    return 1 if p in (PRECISION_C8, PRECISION_C8H, PRECISION_C8W) else 0
 
 
 def param_count(model):

@@ -198,7 +198,7 @@ def main():
     ENG.set_precision(args.precision)
     G, D, gs, ds = build_models(0)
     ok = True
-    tol = 1e-3 if args.precision in (3, 4) else (5e-3 if args.precision == 5 else 5e-2)   # parity / C8: 1e-3; C8H: its stated gate
+    tol = 1e-3 if args.precision in (3, 4, 6) else (5e-3 if args.precision == 5 else 5e-2)   # parity / C8 / C8W: 1e-3; C8H: its stated gate
     backends = ["simt", "tc"] if args.backend == "both" else [args.backend]
     for be in backends:
         ENG.set_backend(ENG.BACKEND_SIMT if be == "simt" else ENG.BACKEND_TCGEN05)

@@ -155,7 +155,8 @@ def test_opt_in_entry_points_validate_their_arguments(pkg):
     assert b"loss_term" in lib.mcgvc_last_error()
     assert lib.mcgvc_set_precision(4) == 0 and lib.mcgvc_get_precision() == 4      # MCGVC_PRECISION_C8
     assert lib.mcgvc_set_precision(5) == 0 and lib.mcgvc_get_precision() == 5      # MCGVC_PRECISION_C8H
-    assert lib.mcgvc_set_precision(6) == 1
+    assert lib.mcgvc_set_precision(6) == 0 and lib.mcgvc_get_precision() == 6      # MCGVC_PRECISION_C8W
+    assert lib.mcgvc_set_precision(7) == 1 and lib.mcgvc_get_precision() == 6      # unknown id: refused, mode unchanged
     assert lib.mcgvc_set_precision(3) == 0
 
 
@@ -165,7 +166,7 @@ def test_precision_mode_from_the_environment():
     import sys
     code = ("import ctypes; l = ctypes.CDLL(%r); print(l.mcgvc_get_precision())"
             % os.path.join(ROOT, "maskcyclegan-vc_b200", "libmcgvc.so"))
-    for val, want in (("c8", 4), ("c8h", 5), ("mixed", 2), ("fast", 1), ("parity", 3), ("bogus", 4)):
+    for val, want in (("c8", 4), ("c8h", 5), ("c8w", 6), ("6", 6), ("mixed", 2), ("fast", 1), ("parity", 3), ("bogus", 4)):
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MCGVC_PRECISION=val),
                              capture_output=True, text=True, check=True).stdout.strip()
         assert int(out) == want, (val, out)

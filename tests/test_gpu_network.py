@@ -338,13 +338,13 @@ def test_c8_forward_shapes_and_lengths(env, B, T):
 
 
 def test_c8_train_steps_track_the_parity_mode(env):
-    """Two full train steps at batch 16 in C8 mode (pair kernels, dynamic dz scales, C8 weight-gradient
-    GEMMs) against the same steps in the default mode: losses and updated weights agree closely."""
+    """Two full train steps at batch 16 in C8 / C8W mode (pair kernels, dynamic dz scales, C8 or fp16
+    weight-gradient GEMMs) against the same steps in parity mode: losses and updated weights agree closely."""
     pkg = env["pkg"]
     e = pkg.engine
     from maskcyclegan_vc_b200 import trainstep as ts
     out = {}
-    for name, mode in (("parity", e.PRECISION_PARITY), ("c8", e.PRECISION_C8)):
+    for name, mode in (("parity", e.PRECISION_PARITY), ("c8", e.PRECISION_C8), ("c8w", e.PRECISION_C8W)):
         e.set_precision(mode)
         try:
             models = ts.build_models(pkg.Generator, pkg.Discriminator, torch.device("cuda"), seed=0)
@@ -357,11 +357,12 @@ def test_c8_train_steps_track_the_parity_mode(env):
             out[name] = (losses, [m._flat.detach().clone() for m in models])
         finally:
             e.set_precision(e.PRECISION_PARITY)
-    for (ga, da), (gb, db) in zip(out["parity"][0], out["c8"][0]):
-        assert abs(ga - gb) <= 2e-3 * abs(ga) and abs(da - db) <= 2e-3 * abs(da) + 1e-5
-    for wa, wb in zip(out["parity"][1], out["c8"][1]):
-        # Adam moves every weight by ~lr per step whatever the gradient's size: compare the update, loosely
-        assert rel(wb, wa) < 1e-3
+    for other in ("c8", "c8w"):
+        for (ga, da), (gb, db) in zip(out["parity"][0], out[other][0]):
+            assert abs(ga - gb) <= 2e-3 * abs(ga) and abs(da - db) <= 2e-3 * abs(da) + 1e-5, other
+        for wa, wb in zip(out["parity"][1], out[other][1]):
+            # Adam moves every weight by ~lr per step whatever the gradient's size: compare the update, loosely
+            assert rel(wb, wa) < 1e-3, other
 
 
 def test_fast_precision_mode_is_labelled_and_bounded(env):
@@ -473,33 +474,41 @@ def test_lean_mode_keeps_the_training_trajectory(env):
 # Referees at BASELINE's headline sizes: the ORACLE (CPU fp32 autograd), not the SIMT backend and
 # not another precision mode, judges the multi-wave CTA-pair data gradients, the grouped stride-2
 # data gradients, the split-K weight-gradient GEMMs and the normalisation backward at nImg = 64.
-@pytest.mark.parametrize("mode", ["parity", "c8"])
+def _MODES(e):
+    """Precision modes that claim the 1e-3 gate on outputs AND gradients: every referee below runs in each."""
+    return {"parity": e.PRECISION_PARITY, "c8": e.PRECISION_C8, "c8w": e.PRECISION_C8W}
+
+
+@pytest.mark.parametrize("mode", ["parity", "c8", "c8w"])
 def test_adversarial_backward_at_batch64_vs_oracle(env, mode):
     """BASELINE configs[3] batch: G -> D adversarial pass at B = 64, T = 64; packed Generator and
     Discriminator gradients, the input gradient, the fake batch and the loss within 1e-3."""
     import net_check
     e = env["pkg"].engine
-    e.set_precision(e.PRECISION_C8 if mode == "c8" else e.PRECISION_PARITY)
+    e.set_precision(_MODES(e)[mode])
     try:
         bwd = net_check.check_backward(env["G"], env["D"], env["gs"], env["ds"], 64, 64, verbose=False)
     finally:
         e.set_precision(e.PRECISION_PARITY)
+    print("%s B=64 T=64: %s" % (mode, {k: "%.2e" % v for k, v in bwd.items()}))
     for k, v in bwd.items():
         assert v < TOL, (mode, k, v)
 
 
-def test_c8_backward_long_frames_vs_oracle(env):
-    """C8 at the long-frame shape of BASELINE configs[4] (T = 512: InstanceNorm planes 8x larger,
+@pytest.mark.parametrize("mode", ["c8", "c8w"])
+def test_c8_backward_long_frames_vs_oracle(env, mode):
+    """C8 / C8W at the long-frame shape of BASELINE configs[4] (T = 512: InstanceNorm planes 8x larger,
     the 1-D trunk at L = 128), forward and backward."""
     import net_check
     e = env["pkg"].engine
-    e.set_precision(e.PRECISION_C8)
+    e.set_precision(_MODES(e)[mode])
     try:
         bwd = net_check.check_backward(env["G"], env["D"], env["gs"], env["ds"], 2, 512, verbose=False)
     finally:
         e.set_precision(e.PRECISION_PARITY)
+    print("%s B=2 T=512: %s" % (mode, {k: "%.2e" % v for k, v in bwd.items()}))
     for k, v in bwd.items():
-        assert v < TOL, (k, v)
+        assert v < TOL, (mode, k, v)
 
 
 class _CapturingOpt:
@@ -523,6 +532,23 @@ class _CapturingOpt:
         self.grads = [{n: p.grad.detach().flatten().cpu() for n, p in self._named(m) if p.grad is not None}
                       for m in self.modules]
         return self.opt.step()
+
+
+_ORACLE_ONCE = {}
+
+
+def _oracle_once(key, fn):
+    """The CPU oracle side of a batch-16 referee (10-20 s of host work) is the same for every precision
+    mode the test is parametrised over: computed once per session."""
+    if key not in _ORACLE_ONCE:
+        _ORACLE_ONCE[key] = fn()
+    return _ORACLE_ONCE[key]
+
+
+def _oracle_models():
+    torch.manual_seed(0)
+    return [O.OracleGenerator(), O.OracleGenerator(), O.OracleDiscriminator(), O.OracleDiscriminator(),
+            O.OracleDiscriminator(), O.OracleDiscriminator()]
 
 
 def _g_phase_frozen_signs(mods, batch, signs, dev):
@@ -561,7 +587,7 @@ def _g_phase_frozen_signs(mods, batch, signs, dev):
     return float(loss.detach()), l1, signs, grads
 
 
-@pytest.mark.parametrize("mode", ["parity", "c8"])
+@pytest.mark.parametrize("mode", ["parity", "c8", "c8w"])
 def test_generator_phase_at_batch16_vs_oracle(env, mode):
     """BASELINE configs[2] batch: the generator phase of the train step (6 G forwards + 4 D forwards, one
     backward through all of them; every module used 2-3 times in the graph) at batch 16, engine vs the
@@ -570,11 +596,8 @@ def test_generator_phase_at_batch16_vs_oracle(env, mode):
     e = pkg.engine
     from maskcyclegan_vc_b200 import trainstep as ts
     batch = O.synthetic_batch(16, 64, seed=4321)
-    torch.manual_seed(0)
-    om = [O.OracleGenerator(), O.OracleGenerator(), O.OracleDiscriminator(), O.OracleDiscriminator(),
-          O.OracleDiscriminator(), O.OracleDiscriminator()]
-    loss_o, l1_o, signs, grads_o = _g_phase_frozen_signs(om, batch, None, torch.device("cpu"))
-    e.set_precision(e.PRECISION_C8 if mode == "c8" else e.PRECISION_PARITY)
+    loss_o, l1_o, signs, grads_o = _oracle_once("g_phase", lambda: _g_phase_frozen_signs(_oracle_models(), batch, None, torch.device("cpu")))
+    e.set_precision(_MODES(e)[mode])
     try:
         models = ts.build_models(pkg.Generator, pkg.Discriminator, torch.device("cuda"), seed=0)
         loss_e, l1_e, _, grads_e = _g_phase_frozen_signs(models, batch, signs, torch.device("cuda"))
@@ -619,7 +642,7 @@ def _d_phase(mods, batch, dev):
     return float(loss.detach()), grads
 
 
-@pytest.mark.parametrize("mode", ["parity", "c8"])
+@pytest.mark.parametrize("mode", ["parity", "c8", "c8w"])
 def test_discriminator_phase_at_batch16_vs_oracle(env, mode):
     """BASELINE configs[2] batch: the discriminator phase (8 D + 4 G forwards, one backward; the generator
     gradients it produces are the ones train.py discards, strict mode computes them) from the seed-0
@@ -628,11 +651,8 @@ def test_discriminator_phase_at_batch16_vs_oracle(env, mode):
     e = pkg.engine
     from maskcyclegan_vc_b200 import trainstep as ts
     batch = O.synthetic_batch(16, 64, seed=4321)
-    torch.manual_seed(0)
-    om = [O.OracleGenerator(), O.OracleGenerator(), O.OracleDiscriminator(), O.OracleDiscriminator(),
-          O.OracleDiscriminator(), O.OracleDiscriminator()]
-    loss_o, grads_o = _d_phase(om, batch, torch.device("cpu"))
-    e.set_precision(e.PRECISION_C8 if mode == "c8" else e.PRECISION_PARITY)
+    loss_o, grads_o = _oracle_once("d_phase", lambda: _d_phase(_oracle_models(), batch, torch.device("cpu")))
+    e.set_precision(_MODES(e)[mode])
     try:
         models = ts.build_models(pkg.Generator, pkg.Discriminator, torch.device("cuda"), seed=0)
         loss_e, grads_e = _d_phase(models, batch, torch.device("cuda"))
@@ -646,7 +666,7 @@ def test_discriminator_phase_at_batch16_vs_oracle(env, mode):
         assert rel(fa, fb) < TOL, (mode, "module", i, rel(fa, fb))
 
 
-@pytest.mark.parametrize("mode", ["parity", "c8"])
+@pytest.mark.parametrize("mode", ["parity", "c8", "c8w"])
 def test_full_train_step_at_batch16_vs_oracle(env, mode):
     """BASELINE configs[2]: one full optimisation step (train.py:186-299) at batch 16 from seed 0 through
     trainstep.train_step, engine vs the oracle modules on the CPU.  The two phases are refereed
@@ -661,13 +681,16 @@ def test_full_train_step_at_batch16_vs_oracle(env, mode):
     e = pkg.engine
     from maskcyclegan_vc_b200 import trainstep as ts
     batch = O.synthetic_batch(16, 64, seed=4321)
-    torch.manual_seed(0)
-    om = [O.OracleGenerator(), O.OracleGenerator(), O.OracleDiscriminator(), O.OracleDiscriminator(),
-          O.OracleDiscriminator(), O.OracleDiscriminator()]
-    og = _CapturingOpt(torch.optim.Adam(list(om[0].parameters()) + list(om[1].parameters()), lr=2e-4, betas=(0.5, 0.999)), om[:2])
-    od = _CapturingOpt(torch.optim.Adam([p for m in om[2:] for p in m.parameters()], lr=1e-4, betas=(0.5, 0.999)), om[2:])
-    gl_o, dl_o = O.train_step(*om, og, od, batch)
-    e.set_precision(e.PRECISION_C8 if mode == "c8" else e.PRECISION_PARITY)
+
+    def oracle_step():
+        om = _oracle_models()
+        og = _CapturingOpt(torch.optim.Adam(list(om[0].parameters()) + list(om[1].parameters()), lr=2e-4, betas=(0.5, 0.999)), om[:2])
+        od = _CapturingOpt(torch.optim.Adam([p for m in om[2:] for p in m.parameters()], lr=1e-4, betas=(0.5, 0.999)), om[2:])
+        gl_o, dl_o = O.train_step(*om, og, od, batch)
+        return float(gl_o), float(dl_o), og, od
+
+    gl_o, dl_o, og, od = _oracle_once("full_step", oracle_step)
+    e.set_precision(_MODES(e)[mode])
     try:
         models = ts.build_models(pkg.Generator, pkg.Discriminator, torch.device("cuda"), seed=0)
         g_opt, d_opt = ts.build_optimizers(models)
@@ -692,8 +715,12 @@ def test_full_train_step_at_batch16_vs_oracle(env, mode):
     print("full step B=16 [%s]:" % mode, {k: "%.2e" % v for k, v in rep.items()})
     assert rep["g_loss"] < TOL, rep
     assert rep["d_loss"] < TOL, rep
+    # C8W: its generator gradients carry ~2x the rounding noise of C8 (2.5e-4 vs 1.1e-4, still 4x inside the
+    # element-wise gate of the phase referees), so ~2x as many near-zero elements change sign under Adam's
+    # first step and the post-update discriminator gradients deviate ~sqrt(2) more: bound 2e-2 there
+    d_bound = 2e-2 if mode == "c8w" else 1e-2
     for i in range(4):
-        assert rep["D%d" % i] < 1e-2, rep
+        assert rep["D%d" % i] < d_bound, rep
     assert worst < 5e-3, rep
 
 
@@ -761,6 +788,57 @@ def test_c8h_tcgen05_kernels_agree_with_simt_checker(env):
     print("tcgen05 vs SIMT:", {k: {kk: "%.2e" % vv for kk, vv in v.items()} for k, v in devs.items()})
     for key, v in devs["c8h"].items():
         assert v < 1e-3, (key, v)
+
+
+# ---------------------------------------------------------------------------------------------
+# C8W: forward and data-gradient GEMMs as C8; only the weight-gradient GEMMs of the C8 layers run one
+# fp16 pass (the C8H weight-gradient kernels).  Weight gradients are leaves of the backward graph, so
+# the mode claims the SAME 1e-3 gate as C8: the headline-size referees above run in it as well.
+def test_c8w_meets_the_parity_gate_and_shares_everything_but_the_weight_gradients_with_c8(env):
+    import net_check
+    e = env["pkg"].engine
+    G, D = env["G"], env["D"]
+    rep = {}
+    e.set_precision(e.PRECISION_C8W)
+    try:
+        for B, T in ((2, 64), (1, 65)):
+            bwd = net_check.check_backward(G, D, env["gs"], env["ds"], B, T, verbose=False)
+            rep[(B, T)] = {k: "%.2e" % v for k, v in bwd.items()}
+            for k, v in bwd.items():
+                assert v < TOL, (B, T, k, v)
+    finally:
+        e.set_precision(e.PRECISION_PARITY)
+    # same forward, same data-gradient chain: output and input gradient equal C8's up to the run-to-run
+    # noise of either mode (floating-point atomics in the statistics / split-K merges, ~1.5e-5); the
+    # tcgen05 weight-gradient kernels agree with the SIMT checker reading the same fp16 planes
+    x, m, _, _ = O.synthetic_batch(2, 64, seed=79)
+    res = {}
+    try:
+        for name, mode, backend in (("c8", e.PRECISION_C8, e.BACKEND_TCGEN05), ("c8w", e.PRECISION_C8W, e.BACKEND_TCGEN05),
+                                    ("c8w-simt", e.PRECISION_C8W, e.BACKEND_SIMT)):
+            e.set_precision(mode)
+            e.set_backend(backend)
+            G.zero_grad(set_to_none=True)
+            D.zero_grad(set_to_none=True)
+            xin = x.cuda().requires_grad_(True)
+            y = G(xin, m.cuda())
+            ((1 - D(y)) ** 2).mean().backward()
+            torch.cuda.synchronize()
+            res[name] = (y.detach().clone(), xin.grad.clone(), G._flat_grad.clone(), D._flat_grad.clone())
+    finally:
+        e.set_backend(e.BACKEND_TCGEN05)
+        e.set_precision(e.PRECISION_PARITY)
+    G.zero_grad(set_to_none=True)
+    D.zero_grad(set_to_none=True)
+    keys = ("G.out", "dx", "G.grads", "D.grads")
+    vs_c8 = {k: rel(a, b) for a, b, k in zip(res["c8w"], res["c8"], keys)}
+    vs_simt = {k: rel(a, b) for a, b, k in zip(res["c8w"], res["c8w-simt"], keys)}
+    print("C8W vs oracle:", rep, "| vs C8:", {k: "%.2e" % v for k, v in vs_c8.items()},
+          "| tcgen05 vs SIMT:", {k: "%.2e" % v for k, v in vs_simt.items()})
+    assert vs_c8["G.out"] < 1e-4 and vs_c8["dx"] < 2e-4, vs_c8
+    assert vs_c8["G.grads"] < TOL and vs_c8["D.grads"] < TOL, vs_c8
+    for k, v in vs_simt.items():
+        assert v < 2e-4, (k, v)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -57,7 +57,7 @@ def main():
     args = ap.parse_args()
     pkg = mcgvc_loader.load()
     eng = pkg.engine
-    eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8h": eng.PRECISION_C8H,
+    eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8w": eng.PRECISION_C8W, "c8h": eng.PRECISION_C8H,
                        "mixed": eng.PRECISION_MIXED, "fast": eng.PRECISION_FAST}[args.precision])
     torch.manual_seed(0)
     G = pkg.Generator().to("cuda")

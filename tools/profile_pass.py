@@ -17,7 +17,7 @@ pkg = mcgvc_loader.load()
 eng = pkg.engine
 mode = sys.argv[1] if len(sys.argv) > 1 else "c8"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8h": eng.PRECISION_C8H,
+eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8w": eng.PRECISION_C8W, "c8h": eng.PRECISION_C8H,
                    "mixed": eng.PRECISION_MIXED, "fast": eng.PRECISION_FAST}[mode])
 torch.manual_seed(0)
 G, D = pkg.Generator().to("cuda"), pkg.Discriminator().to("cuda")

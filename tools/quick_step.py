@@ -16,7 +16,7 @@ from maskcyclegan_vc_b200 import trainstep as ts  # noqa: E402
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8h": eng.PRECISION_C8H, "mixed": eng.PRECISION_MIXED,
+eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8w": eng.PRECISION_C8W, "c8h": eng.PRECISION_C8H, "mixed": eng.PRECISION_MIXED,
                    "fast": eng.PRECISION_FAST}[mode])
 dev = torch.device("cuda", 0)
 models = ts.build_models(pkg.Generator, pkg.Discriminator, dev, seed=0)

@@ -46,7 +46,7 @@ def cpu_time(fn, warm=1, reps=3):
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "c8"
     eng.lib()
-    eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8h": eng.PRECISION_C8H,
+    eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8w": eng.PRECISION_C8W, "c8h": eng.PRECISION_C8H,
                        "mixed": eng.PRECISION_MIXED, "fast": eng.PRECISION_FAST}[mode])
     out = {"cores": os.cpu_count(), "precision": mode}
     torch.set_num_threads(os.cpu_count())

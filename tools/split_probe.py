@@ -13,7 +13,7 @@ import mcgvc_loader  # noqa: E402
 pkg = mcgvc_loader.load()
 eng = pkg.engine
 mode = sys.argv[1] if len(sys.argv) > 1 else "c8"
-eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8h": eng.PRECISION_C8H}[mode])
+eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8w": eng.PRECISION_C8W, "c8h": eng.PRECISION_C8H}[mode])
 torch.manual_seed(0)
 G = pkg.Generator().cuda()
 D = pkg.Discriminator().cuda()
