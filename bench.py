@@ -247,7 +247,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
     ap.add_argument("--impl", default="engine")
-    ap.add_argument("--precision", default="c8", choices=["parity", "c8", "c8w", "c8h", "mixed", "fast"])
+    ap.add_argument("--precision", default="c8w", choices=["parity", "c8", "c8w", "c8h", "mixed", "fast"])
     ap.add_argument("--lean", type=int, default=0)
     ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
                     help="torch = torch.optim.Adam as in train.py:119-122; fused = one-kernel Adam on the flat buffers")

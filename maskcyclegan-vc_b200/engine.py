@@ -15,9 +15,9 @@ BACKEND_SIMT = 1
 PRECISION_PARITY = 3   # split-bf16 x3 (meets the 1e-3 parity gate; 3 MMA units per MAC)
 PRECISION_MIXED = 2    # forward split-bf16 x3, backward single bf16 pass
 PRECISION_FAST = 1     # single bf16 pass
-PRECISION_C8 = 4       # DEFAULT: fp16 main pass + two e4m3 correction passes (2 MMA units per MAC); meets the 1e-3 gate
+PRECISION_C8 = 4       # fp16 main pass + two e4m3 correction passes in every GEMM of the C8 layers (2 MMA units per MAC); meets the 1e-3 gate
 PRECISION_C8H = 5      # forward as C8; backward GEMMs of the C8 layers: one fp16 pass (TF32-class gradients)
-PRECISION_C8W = 6      # forward and data gradients as C8; weight-gradient GEMMs of the C8 layers: one fp16 pass (same 1e-3 gate)
+PRECISION_C8W = 6      # DEFAULT: forward and data gradients as C8; weight-gradient GEMMs of the C8 layers: one fp16 pass (same 1e-3 gate)
 
 # MCGVC_LIBRARY: another build of the same library (A/B timing of two builds in one gpurun call)
 _LIB_PATH = os.environ.get("MCGVC_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcgvc.so")

@@ -92,10 +92,12 @@ def test_two_rank_nccl_gradient_equals_single_process_gradient():
         assert o["reductions_after_bounce"] == 4, o
         assert o["d_arena_floats"] == (6202881 + 63) // 64 * 64, o   # 99.2 MB / 4: no downSample4 slot
         assert o["ranks_identical"] and o["still_in_arena"], o
-        # not bit-equal: batch-4 sums vs two batch-2 sums, and in the default C8 mode the power-of-two
-        # scale of each dz tensor comes from a bound over the WHOLE (local) batch, so the halves round
-        # their operands on a different grid than the full batch (measured 5e-5; a wrong average or a
-        # missed reduction would read as O(1))
+        # not bit-equal: batch-4 sums vs two batch-2 sums, and in the C8 modes the power-of-two scale of
+        # each dz tensor comes from a bound over the WHOLE (local) batch, so the halves round their
+        # operands on a different grid than the full batch (measured 5e-5 in C8).  In the default C8W
+        # mode the weight-gradient operands are additionally rounded to fp16 AFTER the two runs' ~1e-5
+        # run-to-run noise, which decorrelates part of that rounding (its own size: 2.3e-4 of the
+        # gradient norm): gate 5e-4.  A wrong average or a missed reduction would read as O(1).
         for k in ("g", "d", "g_after_bounce", "d_after_bounce"):
-            assert o[k] < 2e-4, (r, k, o[k])
+            assert o[k] < 5e-4, (r, k, o[k])
     print("2-rank NCCL vs single process:", {k: "%.2e" % ret[0][k] for k in ("g", "d", "g_after_bounce", "d_after_bounce")})

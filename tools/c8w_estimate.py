@@ -21,7 +21,6 @@ import torch
 import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
@@ -29,16 +28,20 @@ def fp16_round(t, scale=1.0):
     return (t * scale).to(torch.float16).to(torch.float64) / scale
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--frames", type=int, default=64)
-    args = ap.parse_args()
-    from mask_cyclegan_vc.model import Discriminator, Generator   # the unmodified reference modules
+def estimate(batch, frames, verbose=False):
+    """{'G': added relative error of the packed Generator gradient, 'D': ..., 'layers': [per-layer rel. err]}"""
+    import importlib.util
+    # the unmodified reference modules, loaded by PATH (another `mask_cyclegan_vc.model` -- the engine's shim --
+    # may already sit in sys.modules of the calling process)
+    spec = importlib.util.spec_from_file_location("mcgvc_ref_model_for_c8w_estimate",
+                                                  os.path.join(ROOT, "oracle", "_ref", "mask_cyclegan_vc", "model.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    Generator, Discriminator = ref.Generator, ref.Discriminator
     import maskcyclegan_oracle as O
     torch.manual_seed(0)
     G, D = Generator(), Discriminator()
-    x, m, _, _ = O.synthetic_batch(args.batch, args.frames, seed=11)
+    x, m, _, _ = O.synthetic_batch(batch, frames, seed=11)
 
     # the C8 layers (DESIGN.md section 2): Generator ds1/ds2 (conv and gate convs), up1/up2; Discriminator ds1-3
     c8 = {"G": [G.downSample1.convLayer[0], G.downSample1.convLayer_gates[0], G.downSample2.convLayer[0],
@@ -57,6 +60,7 @@ def main():
     loss = torch.mean((1 - D(fake)) ** 2)
     loss.backward()
 
+    res = {"layers": []}
     for name, net in (("G", G), ("D", D)):
         exact = torch.cat([p.grad.flatten().double() for p in net.parameters() if p.grad is not None])
         err2 = 0.0
@@ -67,11 +71,23 @@ def main():
             w16 = torch.nn.grad.conv2d_weight(fp16_round(xi), mod.weight.shape, fp16_round(dz, S), stride=mod.stride, padding=mod.padding)
             e = (w16 - w64).norm().item()
             err2 += e * e
-            print("%s conv %-22s dW %s: fp16 single pass rel. err %.2e (fp32 autograd vs fp64: %.1e)"
-                  % (name, "%dx%d s%d %d->%d" % (mod.kernel_size[0], mod.kernel_size[1], mod.stride[0], mod.in_channels, mod.out_channels),
-                     tuple(mod.weight.shape), e / w64.norm().item(), (mod.weight.grad.double() - w64).norm().item() / w64.norm().item()))
-        print("%s packed gradient: error added by the fp16 weight-gradient GEMMs = %.2e of its norm (gate 1e-3)"
-              % (name, math.sqrt(err2) / exact.norm().item()))
+            res["layers"].append(e / w64.norm().item())
+            if verbose:
+                print("%s conv %-22s dW %s: fp16 single pass rel. err %.2e (fp32 autograd vs fp64: %.1e)"
+                      % (name, "%dx%d s%d %d->%d" % (mod.kernel_size[0], mod.kernel_size[1], mod.stride[0], mod.in_channels, mod.out_channels),
+                         tuple(mod.weight.shape), e / w64.norm().item(), (mod.weight.grad.double() - w64).norm().item() / w64.norm().item()))
+        res[name] = math.sqrt(err2) / exact.norm().item()
+        if verbose:
+            print("%s packed gradient: error added by the fp16 weight-gradient GEMMs = %.2e of its norm (gate 1e-3)" % (name, res[name]))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=64)
+    args = ap.parse_args()
+    estimate(args.batch, args.frames, verbose=True)
 
 
 if __name__ == "__main__":
