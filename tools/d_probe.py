@@ -12,7 +12,7 @@ from g_timeline import capture, table  # noqa: E402
 
 pkg = mcgvc_loader.load()
 eng = pkg.engine
-mode = sys.argv[1] if len(sys.argv) > 1 else "c8"
+mode = sys.argv[1] if len(sys.argv) > 1 else "c8w"
 eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8w": eng.PRECISION_C8W, "c8h": eng.PRECISION_C8H}[mode])
 torch.manual_seed(0)
 D = pkg.Discriminator().cuda()

@@ -50,7 +50,7 @@ def table(title, evs):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--precision", default="c8")
+    ap.add_argument("--precision", default="c8w")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "g_timeline.md"))

@@ -1,5 +1,5 @@
 """Measures BASELINE.json configs 1, 2, 3 and 5 (config 4 is bench.py's headline) and prints one
-JSON object: engine on cuda:0 (default C8 mode, or argv[1]) next to the CPU oracle port where that is cheap."""
+JSON object: engine on cuda:0 (default C8W mode, or argv[1]) next to the CPU oracle port where that is cheap."""
 import json
 import os
 import sys
@@ -44,7 +44,7 @@ def cpu_time(fn, warm=1, reps=3):
 
 
 def main():
-    mode = sys.argv[1] if len(sys.argv) > 1 else "c8"
+    mode = sys.argv[1] if len(sys.argv) > 1 else "c8w"
     eng.lib()
     eng.set_precision({"parity": eng.PRECISION_PARITY, "c8": eng.PRECISION_C8, "c8w": eng.PRECISION_C8W, "c8h": eng.PRECISION_C8H,
                        "mixed": eng.PRECISION_MIXED, "fast": eng.PRECISION_FAST}[mode])
