@@ -1,5 +1,5 @@
 """Quick report of the C8 precision mode on a B200: parity of a G -> D adversarial pass against the
-CPU oracle, next to the default split-bf16 mode.    python tools/c8_check.py [B] [T]"""
+CPU oracle, next to the split-bf16 parity mode.    python tools/c8_check.py [B] [T]"""
 import os
 import sys
 
